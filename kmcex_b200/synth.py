@@ -1,0 +1,286 @@
+"""Synthetic KMC databases for tests and benchmarks (support code, not the hot path).
+
+The reference's counting stage is the external `kmc` binary (main.cpp:136-140), which is a
+missing blob, so databases are produced here: a seeded random genome, reads sampled at a
+given coverage with substitution errors, canonical k-mer counting (sort + run lengths),
+and a writer for the `.kmc_pre/.kmc_suf` layout the reference reader accepts
+(kmc_file.cpp:177-235, 428-515).
+
+All randomness is a counter-based splitmix64 evaluated with wrapping int64 tensor
+arithmetic, so the same seed gives the same database on CPU and on CUDA. torch is used as
+an array library only (sort / unique on whichever device is available).
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+_M64 = (1 << 64) - 1
+
+
+def _i64(x: int) -> int:
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def _lsr(x: torch.Tensor, s: int) -> torch.Tensor:
+    """logical shift right on int64 tensors"""
+    return (x >> s) & _i64((1 << (64 - s)) - 1)
+
+
+def splitmix64(idx: torch.Tensor, seed: int, stream: int) -> torch.Tensor:
+    """counter-based RNG: 64 random bits per index (int64 bit patterns)"""
+    z = idx + _i64(seed * 0x9E3779B97F4A7C15 + stream * 0xD1B54A32D192ED03 + 0x632BE59BD9B4E019)
+    z = z * _i64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+def _uniform_int(idx: torch.Tensor, seed: int, stream: int, n: int) -> torch.Tensor:
+    """integers in [0, n) (n < 2**31 keeps the tiny modulo bias irrelevant)"""
+    return _lsr(splitmix64(idx, seed, stream), 1) % n
+
+
+def revcomp_packed(v: torch.Tensor, k: int) -> torch.Tensor:
+    """reverse complement of 2-bit packed k-mers held in int64 (k <= 31)"""
+    x = ~v
+    x = (_lsr(x, 2) & 0x3333333333333333) | ((x & 0x3333333333333333) << 2)
+    x = (_lsr(x, 4) & 0x0F0F0F0F0F0F0F0F) | ((x & 0x0F0F0F0F0F0F0F0F) << 4)
+    x = (_lsr(x, 8) & 0x00FF00FF00FF00FF) | ((x & 0x00FF00FF00FF00FF) << 8)
+    x = (_lsr(x, 16) & 0x0000FFFF0000FFFF) | ((x & 0x0000FFFF0000FFFF) << 16)
+    x = _lsr(x, 32) | (x << 32)
+    return _lsr(x, 64 - 2 * k)
+
+
+def canonical_packed(v: torch.Tensor, k: int) -> torch.Tensor:
+    assert k <= 31
+    return torch.minimum(v, revcomp_packed(v, k))
+
+
+@dataclass
+class Spectrum:
+    k: int
+    kmers: np.ndarray   # uint64, sorted ascending, canonical, unique
+    counts: np.ndarray  # uint32
+    genome: np.ndarray  # uint8 codes (for neighbour-rich query sets)
+
+
+def genome_kmers(genome: torch.Tensor, k: int) -> torch.Tensor:
+    """packed forward k-mer starting at every genome position (int64, len G-k+1)"""
+    g = genome.to(torch.int64)
+    n = g.numel() - k + 1
+    out = torch.zeros(n, dtype=torch.int64, device=g.device)
+    for j in range(k):
+        out |= g[j:j + n] << (2 * (k - 1 - j))
+    return out
+
+
+def synth_reads_spectrum(genome_bp: int, coverage: float, read_len: int, k: int = 31, err_rate: float = 0.01,
+                         seed: int = 1, ci: int = 1, cs: int = 1023, repeat_frac: float = 0.01,
+                         device: str | None = None, chunk_reads: int = 1 << 20) -> Spectrum:
+    """Simulate reads from a random genome and count canonical k-mers (counts saturate at cs,
+    k-mers below ci dropped) -- what `kmc -k -ci -cs` would emit for such a FASTQ."""
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    G, L = int(genome_bp), int(read_len)
+    pos = torch.arange(G, dtype=torch.int64, device=dev)
+    genome = (splitmix64(pos, seed, 1) & 3)
+    # a few repeated segments so that some k-mers have genomic multiplicity > 1
+    n_rep = int(G * repeat_frac / 500)
+    if n_rep > 0 and G > 4000:
+        ridx = torch.arange(n_rep, dtype=torch.int64, device=dev)
+        src = _uniform_int(ridx, seed, 2, G - 1000)
+        dst = _uniform_int(ridx, seed, 3, G - 1000)
+        off = torch.arange(500, dtype=torch.int64, device=dev)
+        genome[(dst[:, None] + off[None, :]).reshape(-1)] = genome[(src[:, None] + off[None, :]).reshape(-1)]
+    gk = genome_kmers(genome, k)
+    per_read = L - k + 1
+    n_reads = int(G * coverage / L)
+    uniq_parts, cnt_parts = [], []
+    joff = torch.arange(per_read, dtype=torch.int64, device=dev)
+    for r0 in range(0, n_reads, chunk_reads):
+        r1 = min(n_reads, r0 + chunk_reads)
+        ridx = torch.arange(r0, r1, dtype=torch.int64, device=dev)
+        start = _uniform_int(ridx, seed, 4, G - L + 1)
+        inst = gk[(start[:, None] + joff[None, :]).reshape(-1)]
+        # substitution errors: events (read, position, delta) at rate err_rate per base
+        n_ev = int(round((r1 - r0) * L * err_rate))
+        if n_ev > 0:
+            eidx = torch.arange(n_ev, dtype=torch.int64, device=dev) + r0 * 1000003
+            er = _uniform_int(eidx, seed, 5, r1 - r0)
+            eq = _uniform_int(eidx, seed, 6, L)
+            ed = _uniform_int(eidx, seed, 7, 3) + 1
+            key = torch.unique(er * L + eq, sorted=True, return_inverse=False)   # one event per (read, pos)
+            er, eq = key // L, key % L
+            ed = _uniform_int(key + r0 * L, seed, 7, 3) + 1
+            j = eq[:, None] - torch.arange(k, dtype=torch.int64, device=dev)[None, :]      # k-mer offsets covering pos
+            ok = (j >= 0) & (j < per_read)
+            sh = 2 * (k - 1 - (eq[:, None] - j))
+            mask = (ed[:, None] << sh)[ok]
+            tgt = (er[:, None] * per_read + j)[ok]
+            acc = torch.zeros_like(inst)
+            acc.index_add_(0, tgt, mask)        # disjoint bit fields: add == or
+            inst = inst ^ acc
+        inst = canonical_packed(inst, k)
+        u, c = torch.unique(inst, sorted=True, return_counts=True)
+        uniq_parts.append(u)
+        cnt_parts.append(c)
+        del inst
+    u = torch.cat(uniq_parts)
+    c = torch.cat(cnt_parts)
+    if len(uniq_parts) > 1:
+        order = torch.argsort(u, stable=True)
+        u, c = u[order], c[order]
+        uu, inv = torch.unique_consecutive(u, return_inverse=True)
+        cc = torch.zeros(uu.numel(), dtype=torch.int64, device=dev)
+        cc.index_add_(0, inv, c)
+        u, c = uu, cc
+    c = torch.clamp(c, max=cs)
+    keep = c >= ci
+    u, c = u[keep], c[keep]
+    return Spectrum(k=k, kmers=u.cpu().numpy().astype(np.uint64), counts=c.cpu().numpy().astype(np.uint32),
+                    genome=genome.to(torch.uint8).cpu().numpy())
+
+
+def synth_direct_spectrum(genome_bp: int, coverage: float, read_len: int, k: int = 31, err_mult: float = 1.5,
+                          seed: int = 1, ci: int = 1, cs: int = 1023, device: str | None = None) -> Spectrum:
+    """Cheaper genome-derived spectrum for large shapes: every genomic k-mer gets a count around
+    coverage*(L-k+1)/L, plus err_mult single-substitution neighbours per genomic k-mer with a
+    short low-count tail (what sequencing errors leave behind)."""
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    G = int(genome_bp)
+    pos = torch.arange(G, dtype=torch.int64, device=dev)
+    genome = (splitmix64(pos, seed, 1) & 3)
+    gk = genome_kmers(genome, k)
+    n = gk.numel()
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    lam = coverage * (read_len - k + 1) / read_len
+    # sum of 8 uniforms ~ normal: mean lam, sd sqrt(lam)
+    s = torch.zeros(n, dtype=torch.float64, device=dev)
+    for t in range(8):
+        s += (_lsr(splitmix64(idx, seed, 10 + t), 11).to(torch.float64) / float(1 << 53))
+    solid_c = torch.clamp((lam + (s - 4.0) * (lam ** 0.5) * 1.2247).round().to(torch.int64), min=1)
+    n_err = int(n * err_mult)
+    eidx = torch.arange(n_err, dtype=torch.int64, device=dev)
+    src = gk[_uniform_int(eidx, seed, 20, n)]
+    epos = _uniform_int(eidx, seed, 21, k)
+    ed = _uniform_int(eidx, seed, 22, 3) + 1
+    err = src ^ (ed << (2 * epos))
+    r = _lsr(splitmix64(eidx, seed, 23), 11).to(torch.float64) / float(1 << 53)
+    err_c = torch.clamp((torch.log(1 - r) / np.log(0.45)).floor().to(torch.int64) + 1, max=8)   # geometric tail 1,2,3..
+    allk = canonical_packed(torch.cat([gk, err]), k)
+    allc = torch.cat([solid_c, err_c])
+    order = torch.argsort(allk, stable=True)
+    allk, allc = allk[order], allc[order]
+    u, inv = torch.unique_consecutive(allk, return_inverse=True)
+    c = torch.zeros(u.numel(), dtype=torch.int64, device=dev)
+    c.index_add_(0, inv, allc)
+    c = torch.clamp(c, max=cs)
+    keep = c >= ci
+    u, c = u[keep], c[keep]
+    return Spectrum(k=k, kmers=u.cpu().numpy().astype(np.uint64), counts=c.cpu().numpy().astype(np.uint32),
+                    genome=genome.to(torch.uint8).cpu().numpy())
+
+
+def write_kmc_db(base: str, kmers: np.ndarray, counts: np.ndarray, k: int = 31, lut_prefix_length: int = 3,
+                 n_bins: int = 1, counter_size: int = 2, min_count: int = 1, max_count: int = 1023,
+                 signature_len: int = 7) -> int:
+    """Write <base>.kmc_pre / <base>.kmc_suf (KMC2/3 layout, version word 0x200).
+
+    kmers must be unique packed values; they are split over n_bins by a hash of the value (KMC
+    bins by minimiser signature; the listing reader only needs sorted records per bin and a
+    per-bin LUT, kmc_file.cpp:439-449) and sorted within each bin. Returns the record count."""
+    assert (k - lut_prefix_length) % 4 == 0 and 1 <= k <= 32
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    n = kmers.size
+    suf_bytes = (k - lut_prefix_length) // 4
+    if n_bins > 1:
+        h = (kmers * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
+        bins = (h % np.uint64(n_bins)).astype(np.int64)
+    else:
+        bins = np.zeros(n, dtype=np.int64)
+    order = np.lexsort((kmers, bins))
+    kmers, counts, bins = kmers[order], counts[order], bins[order]
+    slots = 4 ** lut_prefix_length
+    prefix = (kmers >> np.uint64(8 * suf_bytes)).astype(np.int64)
+    slot_id = bins * slots + prefix
+    per_slot = np.bincount(slot_id, minlength=n_bins * slots).astype(np.uint64)
+    starts = np.zeros(n_bins * slots + 1, dtype=np.uint64)
+    np.cumsum(per_slot, out=starts[1:])
+    lut = starts.copy()          # n_bins*slots entries + the guard word
+    rec = np.zeros((n, suf_bytes + counter_size), dtype=np.uint8)
+    for b in range(suf_bytes):
+        rec[:, b] = ((kmers >> np.uint64(8 * (suf_bytes - 1 - b))) & np.uint64(0xFF)).astype(np.uint8)
+    for b in range(counter_size):
+        rec[:, suf_bytes + b] = ((counts >> np.uint32(8 * b)) & np.uint32(0xFF)).astype(np.uint8)
+    with open(base + ".kmc_suf", "wb") as f:
+        f.write(b"KMCS")
+        f.write(rec.tobytes())
+        f.write(b"KMCS")
+    header = struct.pack("<7IQB7x5I I", k, 0, counter_size, lut_prefix_length, signature_len, min_count, max_count,
+                         n, 0, 0, 0, 0, 0, 0, 0x200)
+    with open(base + ".kmc_pre", "wb") as f:
+        f.write(b"KMCP")
+        f.write(lut.tobytes())
+        f.write(np.zeros(4 ** signature_len + 1, dtype=np.uint32).tobytes())
+        f.write(header)
+        f.write(struct.pack("<I", len(header)))
+        f.write(b"KMCP")
+    return n
+
+
+def neighbour_rich_queries(sp: Spectrum, n_present: int, n_absent: int, seed: int = 7) -> np.ndarray:
+    """Query set: present k-mers (random strand), uniform random k-mers (absent w.p. ~1) and
+    single-base neighbours of present k-mers (drives the disambiguation slow path)."""
+    rng = np.random.default_rng(seed)
+    k = sp.k
+    mask = np.uint64((1 << (2 * k)) - 1)
+    pres = sp.kmers[rng.integers(0, sp.kmers.size, n_present)]
+    flip = rng.integers(0, 2, n_present).astype(bool)
+    t = torch.from_numpy(pres.astype(np.int64))
+    rc = revcomp_packed(t, k).numpy().astype(np.uint64)
+    pres = np.where(flip, rc, pres)
+    absent = rng.integers(0, 1 << 62, n_absent, dtype=np.uint64) & mask
+    nb_src = sp.kmers[rng.integers(0, sp.kmers.size, max(1, n_absent // 4))]
+    nb = ((nb_src << np.uint64(2)) & mask) | rng.integers(0, 4, nb_src.size).astype(np.uint64)
+    q = np.concatenate([pres, absent, nb])
+    rng.shuffle(q)
+    return q.astype(np.uint64)
+
+
+def to_ascii(kmers: np.ndarray, k: int) -> np.ndarray:
+    """(n, k) uint8 matrix of 'ACGT' characters"""
+    kmers = np.asarray(kmers, dtype=np.uint64)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = np.empty((kmers.size, k), dtype=np.uint8)
+    for i in range(k):
+        out[:, i] = lut[((kmers >> np.uint64(2 * (k - 1 - i))) & np.uint64(3)).astype(np.int64)]
+    return out
+
+
+def make_db(base: str, shape: str, seed: int = 1, ci: int = 1, cs: int = 1023, lut_prefix_length: int = 3,
+            n_bins: int = 1, device: str | None = None) -> Spectrum:
+    """named shapes (BASELINE.json configs, plus small ones for tests)"""
+    shapes = {
+        # name: (genome_bp, coverage, read_len, mode)
+        "tiny": (20_000, 30, 100, "reads"),
+        "small": (200_000, 40, 100, "reads"),
+        "cfg1": (2_000_000, 50, 100, "reads"),          # 1 M reads x 100 bp
+        "rs": (4_600_000, 100, 101, "reads"),          # GAGE R. sphaeroides shaped
+        "hc14": (88_000_000, 40, 101, "direct"),
+        "na12878": (3_100_000_000, 30, 101, "direct"),
+    }
+    g, c, l, mode = shapes[shape]
+    if mode == "reads":
+        sp = synth_reads_spectrum(g, c, l, seed=seed, ci=ci, cs=cs, device=device)
+    else:
+        sp = synth_direct_spectrum(g, c, l, seed=seed, ci=ci, cs=cs, device=device)
+    os.makedirs(os.path.dirname(os.path.abspath(base)), exist_ok=True)
+    write_kmc_db(base, sp.kmers, sp.counts, k=sp.k, lut_prefix_length=lut_prefix_length, n_bins=n_bins,
+                 min_count=ci, max_count=cs)
+    return sp
