@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- the kmcEx model build + kmer_to_occ path on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload rs|small|hc14]
+
+A step = one model build (KModel::init: counting pass, Bloom inserts, greedy coupled-array
+insert, rest table) from a synthetic KMC database of the named shape; `value` is k-mers
+encoded per second with the database already resident in HBM, `e2e` the same build through
+kmx_init_from_kmc (file -> pinned host -> HBM -> build, host buffers, copies inside the timed
+region).  The retrieval half of the metric (kmer_to_occ queries/s) is measured in the same
+run and reported under "query".  N > 1: see DESIGN.md "Multi-GPU" -- every rank builds from
+its own share of the work and the query batch is sharded over the ranks (weak scaling).
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from
+/root/reference by oracle/Makefile) on the host cores of this box on the same database.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synth shape, ci, lut_prefix_length, bins, BASELINE.json config it stands for)
+    "small": ("small", 2, 7, 4, "test-sized (200 kbp, 40x)"),
+    "cfg1": ("cfg1", 1, 3, 8, "configs[0]: 1M-read 100bp, ci1"),
+    "rs": ("rs", 2, 7, 16, "configs[1]: GAGE-RS-shaped synthetic (4.6 Mbp, 100x, 101bp) k31 nh7 nb5 ci2"),
+    "hc14": ("hc14", 1, 7, 64, "configs[2]: GAGE-HC14-shaped synthetic (88 Mbp, 40x) k31 nh7 nb5 ci1"),
+}
+CACHE = os.environ.get("KMX_BENCH_CACHE", "/tmp/kmx_bench")
+
+
+def rank_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def ensure_db(workload: str, seed: int = 1):
+    """generate (or reuse) the synthetic KMC database + a query set for it; returns paths and sizes"""
+    from kmcex_b200 import synth
+    shape, ci, lut, bins, _ = WORKLOADS[workload]
+    d = os.path.join(CACHE, f"{workload}_s{seed}")
+    base = os.path.join(d, "db")
+    meta_path = os.path.join(d, "meta.json")
+    if os.path.exists(meta_path):
+        with open(meta_path) as f:
+            return json.load(f)
+    os.makedirs(d, exist_ok=True)
+    sp = synth.make_db(base, shape, seed=seed, ci=ci, lut_prefix_length=lut, n_bins=bins)
+    # query set: 50 % present (random strand) / 50 % absent + neighbours, BASELINE.json configs[4] mix
+    n_q = 1 << 24
+    q = synth.neighbour_rich_queries(sp, n_q // 2, n_q // 2 - (n_q // 2) // 4, seed=seed + 100)
+    q.tofile(os.path.join(d, "queries.u64"))
+    meta = {"db": base, "queries": os.path.join(d, "queries.u64"), "n_kmers": int(sp.kmers.size), "n_queries": int(q.size), "ci": ci,
+            "suffix_bytes": os.path.getsize(base + ".kmc_suf"), "prefix_bytes": os.path.getsize(base + ".kmc_pre")}
+    tmp = meta_path + f".{os.getpid()}"
+    with open(tmp, "w") as f:
+        json.dump(meta, f)
+    os.replace(tmp, meta_path)
+    return meta
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference on the host cores
+# ---------------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    rank, _, world = rank_env()
+    if rank != 0:
+        return
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(ref):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (needs /root/reference at build time)"}))
+        return
+    meta = ensure_db(args.workload)
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    out_dir = os.path.join(CACHE, f"{args.workload}_ref_model")
+    os.makedirs(out_dir, exist_ok=True)
+    times = []
+    for step in range(args.warmup + args.steps):
+        r = subprocess.run([ref, "build", meta["db"], out_dir, str(meta["ci"]), "1023", "7", "5"], capture_output=True, text=True, env=env, check=True)
+        t = json.loads(r.stdout.strip().splitlines()[-1])
+        if step >= args.warmup:
+            times.append(t["init_s"])
+    ms = 1e3 * sum(times) / len(times)
+    value = meta["n_kmers"] / (ms / 1e3)
+    # retrieval: bounded sample of the query set, every host core (kmer_to_occ(vector, t_num), kmodel.hpp:90)
+    n_q = min(meta["n_queries"], 1 << 21)
+    qs = os.path.join(CACHE, f"{args.workload}_ref_q.u64")
+    np.fromfile(meta["queries"], dtype=np.uint64, count=n_q).tofile(qs)
+    r = subprocess.run([ref, "query", out_dir, qs, "31", qs + ".occ", str(cores)], capture_output=True, text=True, env=env, check=True)
+    tq = json.loads(r.stdout.strip().splitlines()[-1])
+    qps = n_q / tq["query_s"]
+    line = {
+        "impl": "reference", "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": meta["n_kmers"], "k": 31, "n_hash": 7, "n_bits": 5,
+                                        "ci": meta["ci"], "cs": 1023},
+        "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": cores, "kind": "reference",
+                         "sample": f"whole database ({meta['n_kmers']} k-mers), KModel::init only; build uses the reference's hard-coded 4/n_bits threads"},
+        "query": {"value": qps, "unit": "queries/s", "threads": cores, "sample": f"{n_q} queries of the bench query set"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
+    ap.add_argument("--workload", default="rs", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import kmcex_b200 as kx
+
+    rank, local_rank, world = rank_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: kmcex_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    kx._lib.check(kx.lib().kmx_set_device(local_rank))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    if rank == 0:
+        meta = ensure_db(args.workload)
+    if world > 1:
+        dist.barrier()
+    meta = ensure_db(args.workload)
+    n_kmers = meta["n_kmers"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- build, database resident in HBM ----------------
+    db = kx.KmcDatabase(meta["db"]).upload()
+    infos, wall = [], []
+    sampler = ClockSampler(local_rank)
+    for step in range(args.warmup + args.steps):
+        if step == args.warmup:
+            sampler.start()
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        m = kx.get_model(meta["ci"], 1023, 7, 5)
+        m.init(db)
+        m.sync()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            wall.append(dt)
+            infos.append(m.info)
+        if step < args.warmup + args.steps - 1:
+            m.close()
+    clocks = sampler.stop()
+    t_build = max_over_ranks(sum(wall))
+    ms_per_step = 1e3 * t_build / args.steps
+    value = world * n_kmers * args.steps / t_build            # every rank builds one model per step (replicas)
+    info = infos[-1]
+    dev_ms = float(np.mean([i["ms_total_device"] for i in infos]))
+    ins_ms = float(np.mean([i["ms_insert"] for i in infos]))
+    launches_per_step = 1 + 1 + 1 + (info["batches"] + 63) // 64 + 6     # count, scan, encode, insert launches, rest sort/index
+
+    # ---------------- build, end to end from the files (host buffers) ----------------
+    e2e_wall = []
+    for step in range(2 + args.steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        m2 = kx.get_model(meta["ci"], 1023, 7, 5)
+        m2.init(meta["db"])
+        m2.sync()
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            e2e_wall.append(dt)
+        m2.close()
+    t_e2e = max_over_ranks(sum(e2e_wall))
+    e2e_value = world * n_kmers * args.steps / t_e2e
+
+    # ---------------- retrieval ----------------
+    q_all = np.fromfile(meta["queries"], dtype=np.uint64)
+    per = q_all.size // world
+    q_host = torch.from_numpy(q_all[rank * per:(rank + 1) * per].astype(np.int64)).pin_memory()
+    q_dev = q_host.to(dev)
+    out_dev = torch.empty(per, dtype=torch.int32, device=dev)
+    out_host = torch.empty(per, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    q_ms = []
+    for step in range(args.warmup + args.steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        ev[0].record(stream)
+        m.query_device(q_dev.data_ptr(), per, out_dev.data_ptr(), stream.cuda_stream)
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        if step >= args.warmup:
+            q_ms.append(ev[0].elapsed_time(ev[1]))
+    t_q = max_over_ranks(sum(q_ms) / 1e3)
+    qps = world * per * args.steps / t_q
+    q_e2e = []
+    for step in range(2 + args.steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        kx._lib.check(kx.lib().kmx_query_packed(m._h, q_host.data_ptr(), per, out_host.data_ptr()))
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            q_e2e.append(dt)
+    t_qe = max_over_ranks(sum(q_e2e))
+    qps_e2e = world * per * args.steps / t_qe
+    assert bool((out_host.to(dev) == out_dev).all())
+
+    # ---------------- roofline of the dominant kernels ----------------
+    peak, peak_src = measured_peaks()
+    # insert_kernel: each attempt reads n_hash cells (one 32-byte sector each); each accept issues n_hash cell
+    # atomics + (n_hash-2) km_back atomics (one sector each).  DESIGN.md "Algorithmic bytes".
+    ins_bytes = 32.0 * (7 * info["insert_attempts"] + (7 + 5) * info["insert_accepted"])
+    ins_gbs = ins_bytes / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
+    roofline = {"kernel": "insert_kernel", "bound": "hbm", "achieved": ins_gbs, "peak": peak, "unit": "GB/s", "frac": ins_gbs / peak,
+                "traffic": None, "peak_source": peak_src, "ms_per_launch": ins_ms,
+                "note": "random 32-byte sectors; arrays of this workload are L2-resident, the kernel is bound by grid-barrier latency"}
+    # query kernel: sectors actually touched per query depend on the path; lower bound counted here is
+    # km_back (5) + Bloom (bf_num*11) for every query that misses the rest table, + 35 cells for those in km_back
+    line = {
+        "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": n_kmers, "k": 31, "n_hash": 7, "n_bits": 5, "ci": meta["ci"], "cs": 1023,
+                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "replicas" if world > 1 else "single"},
+        "device_ms_per_step": dev_ms,
+        "stage_ms": {k: float(np.mean([i[k] for i in infos])) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
+        "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": meta["suffix_bytes"] + meta["prefix_bytes"], "d2h_bytes_per_step": 256,
+                "ms_per_step": 1e3 * t_e2e / args.steps},
+        "query": {"value": qps, "unit": "queries/s", "batch": per, "ms_per_batch": 1e3 * t_q / args.steps,
+                  "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": per * 4}},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "roofline": roofline,
+        "clocks": clocks,
+        "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers")},
+    }
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+        cores = os.cpu_count() or 1
+        if os.path.exists(ref):
+            out_dir = os.path.join(CACHE, f"{args.workload}_ref_model")
+            os.makedirs(out_dir, exist_ok=True)
+            r = subprocess.run([ref, "build", meta["db"], out_dir, str(meta["ci"]), "1023", "7", "5"], capture_output=True, text=True,
+                               env=dict(os.environ, OMP_NUM_THREADS=str(cores)))
+            if r.returncode == 0:
+                t = json.loads(r.stdout.strip().splitlines()[-1])
+                line["cpu_baseline"] = {"value": n_kmers / t["init_s"], "unit": "k-mers/s", "cores": cores, "kind": "reference",
+                                        "sample": f"whole database ({n_kmers} k-mers), KModel::init of the unmodified reference, one run"}
+        if "cpu_baseline" not in line:
+            line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

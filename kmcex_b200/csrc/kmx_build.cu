@@ -1,0 +1,752 @@
+// kmx_build.cu -- the model build on the device: KMC listing decode, counting pass, Bloom
+// inserts, the greedy coupled-array insert, the rest-table index.
+//
+// Reference path reproduced (file:line relative to the reference root):
+//   kmc_file.cpp:428-515  CKMCFile::ReadNextKmer (record layout, LUT walk, count filter)
+//   kmodel.hpp:423-434    get_km_kmer_count (pass 1)      kmodel.hpp:473-506  Bloom inserts
+//   kmodel.hpp:508-527    batch formation                 kmodel.hpp:557-573  insert_with_thread (rounds)
+//   kmodel.hpp:543-555    insert_array                    kmodel.hpp:590-622  insert_to_array
+//   kmodel.hpp:529-540    reorder_buffer                  rest.hpp:95-135     stat / sort_suffix / transform
+//
+// The reference inserts the <= 2^18 items of a bucket ONE AFTER THE OTHER into one coupled
+// array; the result depends on that order.  insert_kernel reproduces the sequential result in
+// parallel with deterministic reservations:
+//   every iteration, each undecided item (a) re-reads its n_hash cells; a conflict with the
+//   committed state rejects it for good (bits are never cleared and the value under a set tag
+//   never changes); (b) otherwise writes its index with atomicMin into a reservation table for
+//   every position whose tag is still clear, keyed by (position, wanted value); (c) after a
+//   grid barrier it is accepted iff no smaller-index undecided item wants the OPPOSITE value at
+//   any of those positions.  Items accepted in one iteration cannot influence each other, the
+//   smallest undecided index is always decided, and what an item sees at commit time is
+//   exactly what the sequential loop would have shown it.  The reservation table is smaller
+//   than the bit array (positions alias), which can only delay an acceptance, never change it.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include "kmx_device.cuh"
+#include "kmx_launch.h"
+
+namespace cg = cooperative_groups;
+
+namespace kmx {
+
+// =========================================================================================
+// block helpers (256 threads)
+// =========================================================================================
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x) {
+	const int lane = threadIdx.x & 31;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+		if (lane >= d) x += y;
+	}
+	return x;
+}
+
+// exclusive scan of one value per thread over a 256-thread block; *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t x, uint32_t* s_warp /*[9]*/, uint32_t* total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t incl = warp_incl_scan(x);
+	__syncthreads();                      // s_warp may still be read by a previous call
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		uint32_t w = lane < 8 ? s_warp[lane] : 0;
+		uint32_t wi = warp_incl_scan(w);
+		if (lane < 8) s_warp[lane] = wi - w;
+		if (lane == 7) s_warp[8] = wi;
+	}
+	__syncthreads();
+	*total = s_warp[8];
+	return s_warp[warp] + incl - x;
+}
+
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long x, unsigned long long* s_warp /*[8]*/) {
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) x += __shfl_down_sync(0xffffffffu, x, d);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = x;
+	__syncthreads();
+	unsigned long long t = 0;
+	if (threadIdx.x == 0)
+		for (int w = 0; w < 8; w++) t += s_warp[w];
+	return t;                             // valid in thread 0
+}
+
+// =========================================================================================
+// KMC listing decode
+// =========================================================================================
+constexpr int kMaxRecBytes = 12;          // suffix <= 8 bytes (k <= 32), counter <= 4 bytes
+
+// stage the record bytes of one tile into shared memory with 16-byte loads
+__device__ __forceinline__ void stage_tile(const DevDb& db, uint64_t s0, uint32_t n_rec, uint4* s_stage) {
+	const uint64_t byte0 = s0 * db.rec_bytes;                 // multiple of 16: kTile * rec_bytes is
+	const uint32_t n_vec = (n_rec * db.rec_bytes + 15) >> 4;   // the device buffer is padded to 16
+	const uint4* src = reinterpret_cast<const uint4*>(db.suf + byte0);
+	for (uint32_t i = threadIdx.x; i < n_vec; i += blockDim.x) s_stage[i] = __ldg(src + i);
+}
+
+__device__ __forceinline__ uint32_t decode_count(const DevDb& db, const uint8_t* rec) {
+	uint32_t c = 0;
+	for (uint32_t b = 0; b < db.counter_bytes && b < 4; b++) c |= (uint32_t)rec[db.suffix_bytes + b] << (8 * b);
+	return c;
+}
+
+// number of LUT entries <= s, minus one: the slot whose range holds record s (kmc_file.cpp:439-445)
+__device__ __forceinline__ uint64_t lut_slot(const uint64_t* lut, uint64_t lo, uint64_t hi, uint64_t s) {
+	// invariant: lut[lo] <= s, answer in [lo, hi]; lut[hi + 1] > s
+	while (lo < hi) {
+		uint64_t mid = (lo + hi + 1) >> 1;
+		if (__ldg(lut + mid) <= s) lo = mid;
+		else hi = mid - 1;
+	}
+	return lo;
+}
+
+__device__ __forceinline__ uint64_t decode_kmer(const DevDb& db, const uint8_t* rec, uint64_t slot) {
+	uint64_t v = slot & db.prefix_mask;
+	for (uint32_t b = 0; b < db.suffix_bytes; b++) v = (v << 8) | rec[b];
+	return v;
+}
+
+// pass 1 (kmodel.hpp:423-434).  LIST = true only counts listed records per tile (kmx_db_list).
+template <bool LIST>
+__global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevDb db, int ci, int cs, int bf_num, CountOut* out,
+                                                    uint32_t* __restrict__ tile_cnt) {
+	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
+	__shared__ unsigned long long s_sum[8];
+	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
+	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	unsigned long long acc[6] = { 0, 0, 0, 0, 0, 0 };        // thread 0: class0..2, listed, array, bad
+	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint64_t s0 = tile * kTile;
+		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
+		__syncthreads();
+		stage_tile(db, s0, n_rec, s_stage);
+		__syncthreads();
+		uint32_t cls[3] = { 0, 0, 0 }, listed = 0, arr = 0, bad = 0;
+#pragma unroll
+		for (int j = 0; j < kTile / 256; j++) {
+			uint32_t t = threadIdx.x + j * 256;
+			if (t < n_rec) {
+				uint32_t c = decode_count(db, s_bytes + t * db.rec_bytes);
+				if (c >= db.min_count && c <= db.max_count) {
+					listed++;
+					if (!LIST) {
+						if (c < (uint32_t)ci || c > (uint32_t)cs) bad++;
+						else if (c < (uint32_t)(ci + bf_num)) cls[c - ci]++;
+						else arr++;
+					}
+				}
+			}
+		}
+		// pack the six small counters into two 64-bit sums (each < 2^12 per thread, 2^20 per block)
+		unsigned long long p0 = (unsigned long long)cls[0] | ((unsigned long long)cls[1] << 21) | ((unsigned long long)cls[2] << 42);
+		unsigned long long p1 = (unsigned long long)listed | ((unsigned long long)arr << 21) | ((unsigned long long)bad << 42);
+		p0 = block_sum(p0, s_sum);
+		p1 = block_sum(p1, s_sum);
+		if (threadIdx.x == 0) {
+			const unsigned long long m21 = (1ULL << 21) - 1;
+			acc[0] += p0 & m21; acc[1] += (p0 >> 21) & m21; acc[2] += (p0 >> 42) & m21;
+			acc[3] += p1 & m21; acc[4] += (p1 >> 21) & m21; acc[5] += (p1 >> 42) & m21;
+			tile_cnt[tile] = LIST ? (uint32_t)(p1 & m21) : (uint32_t)((p1 >> 21) & m21);
+		}
+	}
+	if (threadIdx.x == 0 && out) {
+		for (int i = 0; i < 3; i++)
+			if (acc[i]) atomicAdd(&out->class_count[i], acc[i]);
+		if (acc[3]) atomicAdd(&out->listed, acc[3]);
+		if (acc[4]) atomicAdd(&out->array_bound, acc[4]);
+		if (acc[5]) atomicAdd(&out->bad_count, acc[5]);
+	}
+}
+
+// exclusive scan of per-tile counts (single block; the tile count is N/2048)
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restrict__ cnt, uint64_t n, uint64_t* __restrict__ off) {
+	__shared__ unsigned long long s_warp[32];
+	__shared__ unsigned long long s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (uint64_t base = 0; base < n; base += 1024) {
+		uint64_t i = base + threadIdx.x;
+		unsigned long long x = i < n ? cnt[i] : 0, incl = x;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d) incl += y;
+		}
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				unsigned long long y = __shfl_up_sync(0xffffffffu, wi, d);
+				if (lane >= d) wi += y;
+			}
+			s_warp[lane] = wi - w;
+		}
+		__syncthreads();
+		unsigned long long carry = s_carry;
+		if (i < n) off[i] = carry + s_warp[warp] + incl - x;
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = carry + s_warp[warp] + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) off[n] = s_carry;
+}
+
+// pass 2.  Each thread decodes 8 CONSECUTIVE records so that the compaction keeps file order.
+// LIST = true: write every listed record (kmx_db_list).  LIST = false: Bloom-bound records are
+// inserted into their filters (kmodel.hpp:473-477,498-506), array-bound ones go to the stream.
+template <bool LIST, int K, int H>
+__global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ DevDb db, const __grid_constant__ DevModel m,
+                                                     const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out_kmer,
+                                                     uint32_t* __restrict__ out_occ) {
+	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
+	__shared__ uint32_t s_warp[9];
+	__shared__ uint64_t s_slot[2];
+	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
+	const int k = K ? K : db.k;
+	const int nh = H ? H : m.n_hash;
+	constexpr int PER = kTile / 256;
+	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const uint64_t s0 = tile * kTile;
+		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
+		__syncthreads();
+		stage_tile(db, s0, n_rec, s_stage);
+		if (threadIdx.x < 2) {
+			uint64_t s = threadIdx.x == 0 ? s0 : s0 + n_rec - 1;
+			s_slot[threadIdx.x] = lut_slot(db.lut, 0, db.lut_entries - 1, s);
+		}
+		__syncthreads();
+		const uint64_t slot_lo = s_slot[0], slot_hi = s_slot[1];
+		uint64_t kmer[PER];
+		uint32_t cnt[PER];
+		uint32_t keep = 0, n_keep = 0;
+#pragma unroll
+		for (int j = 0; j < PER; j++) {
+			uint32_t t = threadIdx.x * PER + j;
+			if (t < n_rec) {
+				const uint8_t* rec = s_bytes + t * db.rec_bytes;
+				uint32_t c = decode_count(db, rec);
+				cnt[j] = c;
+				if (c >= db.min_count && c <= db.max_count) {
+					kmer[j] = decode_kmer(db, rec, lut_slot(db.lut, slot_lo, slot_hi, s0 + t));
+					bool to_stream = LIST ? true : (c >= (uint32_t)(m.ci + m.bf_num));
+					if (to_stream) {
+						keep |= 1u << j;
+						n_keep++;
+					} else if (c >= (uint32_t)m.ci) {
+						const int f = (int)c - m.ci;
+						uint64_t r = reverse_bases(kmer[j], k);
+						HashPrep p;
+						hash_prepare(r, k, p);
+#pragma unroll
+						for (int q = 0; q < (H ? H : kMaxHash) - 1; q++)
+							if (q < nh - 1) filter_set(m.bf[f], hash_finish(p, k, c_seeds[q]));
+						hash_prepare(middle_r(r, k), k - 2, p);
+#pragma unroll
+						for (int q = 0; q < (H ? H : kMaxHash) - 2; q++)
+							if (q < nh - 2) filter_set(m.bf_back[f], hash_finish(p, k - 2, c_seeds[q]));
+					}
+				}
+			}
+		}
+		uint32_t total;
+		uint32_t rank = block_excl_scan(n_keep, s_warp, &total);
+		uint64_t dst = __ldg(tile_off + tile) + rank;
+#pragma unroll
+		for (int j = 0; j < PER; j++) {
+			if (keep & (1u << j)) {
+				out_kmer[dst] = kmer[j];
+				out_occ[dst] = cnt[j];
+				dst++;
+			}
+		}
+	}
+}
+
+static int stream_grid(uint64_t n_tiles, int sm_count, int per_sm) {
+	uint64_t cap = (uint64_t)sm_count * per_sm;
+	return (int)(n_tiles < cap ? (n_tiles ? n_tiles : 1) : cap);
+}
+
+cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, int sm_count,
+                         cudaStream_t stream) {
+	if (db.total == 0) return cudaSuccess;
+	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	count_kernel<false><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream) {
+	if (db.total == 0) return cudaSuccess;
+	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	count_kernel<true><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint64_t* d_tile_off, cudaStream_t stream) {
+	tile_scan_kernel<<<1, 1024, 0, stream>>>(d_tile_cnt, n_tiles, d_tile_off);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, uint64_t* d_item_kmer,
+                          uint32_t* d_item_occ, int sm_count, cudaStream_t stream) {
+	if (db.total == 0) return cudaSuccess;
+	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	int grid = stream_grid(n_tiles, sm_count, 8);
+	if (db.k == 31 && m.n_hash == 7)
+		encode_kernel<false, 31, 7><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ);
+	else
+		encode_kernel<false, 0, 0><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d_kmers, uint32_t* d_counts, int sm_count,
+                        cudaStream_t stream) {
+	if (db.total == 0) return cudaSuccess;
+	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	DevModel dummy = {};
+	encode_kernel<true, 0, 0><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, dummy, d_tile_off, d_kmers, d_counts);
+	return cudaGetLastError();
+}
+
+// =========================================================================================
+// greedy coupled-array insert (persistent, cooperative)
+// =========================================================================================
+constexpr uint32_t kStateShift = 30;
+constexpr uint32_t kAccepted = 1u << kStateShift, kRejected = 2u << kStateShift;
+constexpr uint32_t kEpochMax = 0x3FFFu;
+constexpr uint32_t kIdTile = 256;                           // ids per reorder tile
+
+template <int K, int H, int B>
+__global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
+	cg::grid_group grid = cg::this_grid();
+	constexpr int HM = H ? H : kMaxHash;
+	constexpr int BM = B ? B : kMaxArrays;
+	const int k = K ? K : m.k;
+	const int nh = H ? H : m.n_hash;
+	const int nb = B ? B : m.n_bits;
+	const int hk = nh - 2;
+	const uint32_t T = gridDim.x * blockDim.x;
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t total_ids = (uint32_t)nb << kBucketLog;
+	const uint32_t n_id_tiles = total_ids / kIdTile;
+	const uint32_t slot_mask = a.resv_slots - 1;
+	InsertCtl* ctl = a.ctl;
+	volatile InsertCtl* vctl = a.ctl;
+	__shared__ uint32_t s_warp[9];
+	__shared__ unsigned long long s_sum[8];
+
+	uint32_t epoch = vctl->epoch;
+	uint32_t itc = 0;                                       // rotating counter index, uniform over the grid
+	if (tid == 0) vctl->undecided[0] = vctl->undecided[1] = vctl->undecided[2] = 0;
+	grid.sync();                                            // everybody has read ctl->epoch before it is rewritten
+
+	for (unsigned long long batch = a.first_batch; batch < a.first_batch + a.n_batches; batch++) {
+		const unsigned long long base = batch * total_ids;
+		if (base >= a.n_items) break;
+		uint32_t n_cur[BM];
+#pragma unroll
+		for (int i = 0; i < BM; i++) {
+			unsigned long long b0 = base + ((unsigned long long)i << kBucketLog);
+			unsigned long long rem = (i < nb && a.n_items > b0) ? a.n_items - b0 : 0;
+			n_cur[i] = (uint32_t)(rem < kBucket ? rem : kBucket);
+		}
+		// Stale slot 0 (kmodel.hpp:520-527 + 529-540): in the final, partial batch the trailing
+		// buckets have length 0, and reorder_buffer(a, 0) returns 1 when a[0].occ != 0.  a[0] is
+		// what the previous batch left there: that bucket's first survivor, which is already in
+		// the rest table.  It is offered to the other arrays again, rejected again (the state only
+		// grows) and pushed to the rest table a second time.  Net effect: one duplicate rest entry.
+		if (tid == 0 && batch > 0) {
+			for (int i = 0; i < nb; i++) {
+				if (n_cur[i] == 0 && vctl->slot0_valid[i]) {
+					unsigned long long at = atomicAdd(&ctl->rest_n, 1ULL);
+					if (at < a.rest_cap) {
+						a.rest_kmer[at] = vctl->slot0_kmer[i];
+						a.rest_occ[at] = vctl->slot0_occ[i];
+					} else {
+						vctl->error = 2;
+					}
+				}
+			}
+		}
+
+		for (int t = 0; t < nb; t++) {
+			const bool last_round = (t == nb - 1);
+			const uint64_t* src_kmer = t == 0 ? a.item_kmer + base : a.buf_kmer[(t - 1) & 1];
+			const uint32_t* src_occ = t == 0 ? a.item_occ + base : a.buf_occ[(t - 1) & 1];
+			uint64_t* dst_kmer = a.buf_kmer[t & 1];
+			uint32_t* dst_occ = a.buf_occ[t & 1];
+
+			// ---------------- reservation iterations ----------------
+			uint32_t iter = 0;
+			while (true) {
+				const uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
+				// (a)+(b): check against the committed state, reserve
+				for (uint32_t id = tid; id < total_ids; id += T) {
+					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+					if (c >= n_cur[i]) continue;
+					if (iter > 0 && (a.status[id] >> kStateShift)) continue;
+					const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
+					const uint64_t v = __ldcg(src_kmer + id);
+					uint32_t occ = __ldcg(src_occ + id);
+					const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+					HashPrep p;
+					hash_prepare(reverse_bases(v, k), k, p);
+					uint64_t pos[HM];
+					unsigned long long cell[HM];
+#pragma unroll
+					for (int j = 0; j < HM; j++) {
+						if (j < nh) {
+							pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
+							cell[j] = __ldcg(m.cells[arr] + (pos[j] >> 5));
+						}
+					}
+					bool conflict = false;
+					uint32_t need = 0;
+#pragma unroll
+					for (int j = 0; j < HM; j++) {
+						if (j < nh) {
+							const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
+							const uint32_t val = ((uint32_t)cell[j] >> sh) & 1u, tag = ((uint32_t)(cell[j] >> 32) >> sh) & 1u;
+							const uint32_t want = (bin >> j) & 1u;
+							conflict |= (tag != 0) && (val != want);
+							need |= (tag ^ 1u) << j;
+						}
+					}
+					if (conflict) {
+						a.status[id] = kRejected;
+						atomicAdd(a.tile_fail + (id / kIdTile), 1u);
+					} else {
+						uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
+#pragma unroll
+						for (int j = 0; j < HM; j++) {
+							if (j < nh && ((need >> j) & 1u)) {
+								const uint32_t want = (bin >> j) & 1u;
+								atomicMin(table + 2 * ((uint32_t)pos[j] & slot_mask) + want, key_hi | c);
+							}
+						}
+						a.status[id] = need;
+					}
+				}
+				grid.sync();
+				// (c): accept the items nobody smaller contests
+				uint32_t undecided = 0;
+				for (uint32_t id = tid; id < total_ids; id += T) {
+					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+					if (c >= n_cur[i]) continue;
+					const uint32_t need = a.status[id];
+					if (need >> kStateShift) continue;
+					const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
+					const uint64_t v = __ldcg(src_kmer + id);
+					uint32_t occ = __ldcg(src_occ + id);
+					const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+					const uint64_t r = reverse_bases(v, k);
+					HashPrep p;
+					hash_prepare(r, k, p);
+					uint64_t pos[HM];
+					const uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
+					const uint32_t key = key_hi | c;
+					bool ok = true;
+#pragma unroll
+					for (int j = 0; j < HM; j++) {
+						if (j < nh) {
+							pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
+							if ((need >> j) & 1u) {
+								const uint32_t want = (bin >> j) & 1u;
+								ok &= __ldcg(table + 2 * ((uint32_t)pos[j] & slot_mask) + (want ^ 1u)) >= key;
+							}
+						}
+					}
+					if (ok) {
+#pragma unroll
+						for (int j = 0; j < HM; j++) {
+							if (j < nh) {
+								const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
+								const unsigned long long want = (bin >> j) & 1u;
+								atomicOr(m.cells[arr] + (pos[j] >> 5), ((1ULL << 32) | want) << sh);
+							}
+						}
+						// accepted: the (k-2)-mer goes to km_back (kmodel.hpp:546-550)
+						hash_prepare(middle_r(r, k), k - 2, p);
+#pragma unroll
+						for (int j = 0; j < HM - 2; j++)
+							if (j < hk) filter_set(m.km_back, hash_finish(p, k - 2, c_seeds[j]));
+						a.status[id] = kAccepted;
+					} else {
+						undecided++;
+					}
+				}
+				unsigned long long und_block = block_sum(undecided, s_sum);
+				if (threadIdx.x == 0) {
+					if (und_block) atomicAdd(&ctl->undecided[itc % 3], (unsigned int)und_block);
+					if (blockIdx.x == 0) vctl->undecided[(itc + 1) % 3] = 0;
+				}
+				grid.sync();
+				const uint32_t und = vctl->undecided[itc % 3];
+				itc++;
+				iter++;
+				epoch++;
+				if (epoch >= kEpochMax) {                       // keys can get no smaller: start over
+					for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
+					epoch = 0;
+					grid.sync();
+				}
+				if (und == 0) break;
+				if (iter >= a.max_iterations) {
+					if (tid == 0) vctl->error = 1;
+					return;                                     // uniform over the grid
+				}
+			}
+
+			// ---------------- reorder_buffer (kmodel.hpp:529-540) in closed form ----------------
+			// F = number of rejected items.  Rejected items below F stay where they are; the
+			// accepted slots below F ("holes", ascending) are filled by the rejected items at or
+			// above F taken in DESCENDING index order.
+			if ((int)blockIdx.x < nb) {
+				// exclusive scan of this bucket's 1024 tile counters, 4 per thread
+				const uint32_t i = blockIdx.x;
+				uint32_t* tf = a.tile_fail + i * (kBucket / kIdTile);
+				uint32_t x[4], sum = 0;
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					x[q] = __ldcg(tf + threadIdx.x * 4 + q);
+					sum += x[q];
+				}
+				uint32_t total;
+				uint32_t off = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+				for (int q = 0; q < 4; q++) {
+					tf[threadIdx.x * 4 + q] = off;
+					off += x[q];
+				}
+				if (threadIdx.x == 0) {
+					vctl->nfail[i] = total;
+					if (last_round) {
+						vctl->rest_base[i] = atomicAdd(&ctl->rest_n, (unsigned long long)total);
+						vctl->slot0_valid[i] = total ? 1u : 0u;
+					}
+				}
+			}
+			grid.sync();
+			uint32_t n_next[BM];
+			unsigned long long rest_base[BM];
+#pragma unroll
+			for (int i = 0; i < BM; i++) {
+				n_next[i] = i < nb ? vctl->nfail[i] : 0;
+				rest_base[i] = (i < nb && last_round) ? vctl->rest_base[i] : 0;
+			}
+			if (last_round) {
+#pragma unroll
+				for (int i = 0; i < BM; i++)
+					if (i < nb && rest_base[i] + n_next[i] > a.rest_cap) {
+						if (tid == 0) vctl->error = 2;
+						return;                                 // uniform over the grid
+					}
+			}
+			for (uint32_t tile = blockIdx.x; tile < n_id_tiles; tile += gridDim.x) {
+				const uint32_t id = tile * kIdTile + threadIdx.x;
+				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+				const bool valid = c < n_cur[i];                // uniform over the block: skip empty tiles
+				if (tile * kIdTile - (i << kBucketLog) >= n_cur[i]) continue;
+				const bool failed = valid && (__ldcg(a.status + id) >> kStateShift) == 2u;
+				uint32_t total;
+				const uint32_t excl = __ldcg(a.tile_fail + tile) + block_excl_scan(failed ? 1u : 0u, s_warp, &total);
+				const uint32_t F = n_next[i];
+				if (valid) {
+					if (failed) {
+						if (c < F) {
+							const uint64_t v = __ldcg(src_kmer + id);
+							const uint32_t occ = __ldcg(src_occ + id);
+							if (last_round) {
+								a.rest_kmer[rest_base[i] + c] = v;
+								a.rest_occ[rest_base[i] + c] = occ;
+								if (c == 0) {
+									vctl->slot0_kmer[i] = v;
+									vctl->slot0_occ[i] = occ;
+								}
+							} else {
+								dst_kmer[id] = v;
+								dst_occ[id] = occ;
+							}
+						} else {
+							a.rank[id] = excl;
+						}
+					} else if (c < F) {
+						a.holepos[(i << kBucketLog) + (c - excl)] = c;
+					}
+				}
+			}
+			grid.sync();
+			for (uint32_t id = tid; id < total_ids; id += T) {
+				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+				const uint32_t F = n_next[i];
+				if (c >= n_cur[i] || c < F) continue;
+				if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
+				const uint32_t d = F - __ldcg(a.rank + id) - 1;
+				const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
+				const uint64_t v = __ldcg(src_kmer + id);
+				const uint32_t occ = __ldcg(src_occ + id);
+				if (last_round) {
+					a.rest_kmer[rest_base[i] + to] = v;
+					a.rest_occ[rest_base[i] + to] = occ;
+					if (to == 0) {
+						vctl->slot0_kmer[i] = v;
+						vctl->slot0_occ[i] = occ;
+					}
+				} else {
+					dst_kmer[(i << kBucketLog) + to] = v;
+					dst_occ[(i << kBucketLog) + to] = occ;
+				}
+			}
+			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;
+			if (tid == 0) {
+				unsigned long long att = 0, fail = 0;
+				for (int i = 0; i < nb; i++) {
+					att += n_cur[i];
+					fail += n_next[i];
+				}
+				vctl->attempts += att;
+				vctl->accepted += att - fail;
+				vctl->iterations += iter;
+			}
+			grid.sync();
+#pragma unroll
+			for (int i = 0; i < BM; i++) n_cur[i] = n_next[i];
+		}
+	}
+	if (tid == 0) vctl->epoch = epoch;
+}
+
+cudaError_t insert_grid_size(int* blocks_out, int sm_count) {
+	int per_sm = 0;
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<31, 7, 5>, 256, 0);
+	if (e != cudaSuccess) return e;
+	int per_sm_g = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, insert_kernel<0, 0, 0>, 256, 0);
+	if (e != cudaSuccess) return e;
+	if (per_sm_g < per_sm) per_sm = per_sm_g;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	*blocks_out = per_sm * sm_count;
+	return cudaSuccess;
+}
+
+cudaError_t launch_insert(const DevModel& m, const InsertArgs& a, int grid_blocks, cudaStream_t stream) {
+	if (grid_blocks < m.n_bits) return cudaErrorInvalidConfiguration;
+	void* args[2] = { (void*)&m, (void*)&a };
+	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5)
+		return cudaLaunchCooperativeKernel((const void*)insert_kernel<31, 7, 5>, dim3(grid_blocks), dim3(256), args, 0, stream);
+	return cudaLaunchCooperativeKernel((const void*)insert_kernel<0, 0, 0>, dim3(grid_blocks), dim3(256), args, 0, stream);
+}
+
+// =========================================================================================
+// rest table (rest.hpp:95-135): survivors sorted by packed value, group index per prefix
+// =========================================================================================
+cudaError_t rest_sort_bytes(size_t n, size_t* temp_bytes) {
+	*temp_bytes = 0;
+	if (n == 0) return cudaSuccess;
+	return cub::DeviceRadixSort::SortPairs(nullptr, *temp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+	                                       (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 64);
+}
+
+cudaError_t launch_rest_sort(void* d_temp, size_t temp_bytes, const uint64_t* d_keys_in, uint64_t* d_keys_out,
+                             const uint32_t* d_vals_in, int32_t* d_vals_out, size_t n, int key_bits, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys_in, d_keys_out, d_vals_in, (uint32_t*)d_vals_out, (int64_t)n,
+	                                       0, key_bits, stream);
+}
+
+__global__ void rest_first_kernel(const uint64_t* __restrict__ keys, uint64_t n, int suffix_bits, int32_t* __restrict__ first) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t pre = (uint32_t)(keys[i] >> suffix_bits);
+		if (i == 0 || (uint32_t)(keys[i - 1] >> suffix_bits) != pre) first[pre] = (int32_t)i;
+	}
+}
+
+// stat() + the index half of transform() (rest.hpp:95-105,115-126): dense ids for the
+// non-empty prefixes in ascending order, pre_buffer = first entry of each group, then n
+__global__ void __launch_bounds__(1024) rest_index_kernel(const int32_t* __restrict__ first, int map_size, uint64_t n,
+                                                          int32_t* __restrict__ hash2index, int32_t* __restrict__ pre_buffer,
+                                                          int32_t* __restrict__ groups) {
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (int base = 0; base < map_size; base += 1024) {
+		int p = base + threadIdx.x;
+		int32_t f = p < map_size ? first[p] : -1;
+		uint32_t x = f >= 0 ? 1u : 0u;
+		uint32_t incl = warp_incl_scan(x);
+		if (lane == 31) s_warp[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t w = s_warp[lane];
+			uint32_t wi = warp_incl_scan(w);
+			s_warp[lane] = wi - w;
+		}
+		__syncthreads();
+		uint32_t carry = s_carry;
+		uint32_t g = carry + s_warp[warp] + incl - x;
+		if (p < map_size) {
+			hash2index[p] = x ? (int32_t)g : -1;
+			if (x) pre_buffer[g] = f;
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = g + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		pre_buffer[s_carry] = (int32_t)n;
+		*groups = (int32_t)s_carry;
+	}
+}
+
+cudaError_t launch_rest_index(const uint64_t* d_keys, uint64_t n, int suffix_bits, int map_size, int32_t* d_first,
+                              int32_t* d_hash2index, int32_t* d_pre_buffer, int32_t* d_groups, cudaStream_t stream) {
+	cudaError_t e = cudaMemsetAsync(d_first, 0xFF, (size_t)map_size * sizeof(int32_t), stream);
+	if (e != cudaSuccess) return e;
+	if (n) {
+		uint64_t blocks = (n + 255) / 256;
+		rest_first_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, stream>>>(d_keys, n, suffix_bits, d_first);
+	}
+	rest_index_kernel<<<1, 1024, 0, stream>>>(d_first, map_size, n, d_hash2index, d_pre_buffer, d_groups);
+	return cudaGetLastError();
+}
+
+// =========================================================================================
+// coupled arrays: on-disk (bit_array_1, bit_array_2 separate) <-> device (interleaved cells)
+// =========================================================================================
+__global__ void split_cells_kernel(const unsigned long long* __restrict__ cells, uint64_t n, uint32_t* __restrict__ val,
+                                   uint32_t* __restrict__ tag) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		unsigned long long c = cells[i];
+		val[i] = (uint32_t)c;
+		tag[i] = (uint32_t)(c >> 32);
+	}
+}
+__global__ void merge_cells_kernel(const uint32_t* __restrict__ val, const uint32_t* __restrict__ tag, uint64_t n,
+                                   unsigned long long* __restrict__ cells) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		cells[i] = ((unsigned long long)tag[i] << 32) | val[i];
+}
+
+cudaError_t launch_split_cells(const unsigned long long* d_cells, uint64_t n_words, uint32_t* d_val, uint32_t* d_tag, cudaStream_t stream) {
+	if (n_words == 0) return cudaSuccess;
+	uint64_t blocks = (n_words + 255) / 256;
+	split_cells_kernel<<<(int)(blocks < 65535 ? blocks : 65535), 256, 0, stream>>>(d_cells, n_words, d_val, d_tag);
+	return cudaGetLastError();
+}
+cudaError_t launch_merge_cells(const uint32_t* d_val, const uint32_t* d_tag, uint64_t n_words, unsigned long long* d_cells, cudaStream_t stream) {
+	if (n_words == 0) return cudaSuccess;
+	uint64_t blocks = (n_words + 255) / 256;
+	merge_cells_kernel<<<(int)(blocks < 65535 ? blocks : 65535), 256, 0, stream>>>(d_val, d_tag, n_words, d_cells);
+	return cudaGetLastError();
+}
+
+}  // namespace kmx

@@ -1,0 +1,1185 @@
+// kmx_host.cu -- host side of libkmx.so: KMC header parse, model object, build orchestration,
+// save/load in the reference's on-disk layout, query pipelines, and the C ABI of include/kmx.h.
+//
+// Reference interfaces mirrored (file:line relative to the reference root):
+//   kmodel.hpp:45-55,674-696  get_model / KModel ctor      kmodel.hpp:57-86    KModel::init
+//   kmodel.hpp:173-235        save / load                  kmodel.hpp:402-456  size formulas
+//   occu_bin.hpp:27-83        OccuBin                      rest.hpp:163-221    rest.bin I/O
+//   kmc_file.cpp:66-99,132-171,177-235  OpenForListing / header + LUT parse
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+#include "../../include/kmx.h"
+#include "kmx_device.cuh"
+#include "kmx_launch.h"
+
+using namespace kmx;
+
+// =========================================================================================
+// errors
+// =========================================================================================
+static thread_local char g_err[512] = "";
+static int g_device = 0;
+
+static int fail(int code, const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call)                                                                                         \
+	do {                                                                                                 \
+		cudaError_t e__ = (call);                                                                        \
+		if (e__ != cudaSuccess) return fail(KMX_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+static int require_gpu(int* sm_count) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return fail(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path): %s", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+	}
+	if (g_device >= n) return fail(KMX_ENOGPU, "device %d requested, %d present", g_device, n);
+	CU(cudaSetDevice(g_device));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, g_device));
+	if (prop.major < 10) return fail(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", g_device, prop.major, prop.minor);
+	if (sm_count) *sm_count = prop.multiProcessorCount;
+	return KMX_OK;
+}
+
+// =========================================================================================
+// OccuBin (occu_bin.hpp:27-83) as two lookup tables
+// =========================================================================================
+// Three zones over the occurrence axis: [0, E1) one bin per value; then 2^(H-1) bins of width
+// 3 whose mean is first+1; then 2^(H-2) bins of width W = (max_counter - zone3_start) / 2^(H-2)
+// whose mean is (2*first + W)/2; what is left shares the last bin.  bin -> mean keeps the FIRST
+// mean registered for a bin (unordered_map::insert), missing bins read as 0.
+static int occubin_tables(int max_counter, int n_hash, std::vector<int32_t>& occ2bin, std::vector<int32_t>& bin2mean) {
+	if (n_hash < 3 || n_hash > kMaxHash || max_counter < 1) return KMX_EARG;
+	const int e3 = 1 << n_hash, e1 = e3 / 4, e2 = e1 + e3 / 2;
+	const int z3 = e1 + 3 * (e3 / 2);
+	if (z3 > max_counter) return KMX_ERANGE;       // the reference writes past occ_bin_meta here
+	const int w3 = (max_counter - z3) / (e3 / 4);
+	const int z4 = z3 + w3 * (e3 / 4);
+	occ2bin.assign(max_counter, 0);
+	bin2mean.assign(e3, 0);
+	std::vector<char> seen(e3, 0);
+	for (int b = 0; b < e1; b++) bin2mean[b] = b;
+	for (int occ = 0; occ < max_counter; occ++) {
+		int bin, mean;
+		if (occ < e1) {
+			occ2bin[occ] = occ;
+			continue;
+		} else if (occ < z3) {
+			int idx = (occ - e1) / 3;
+			bin = e1 + idx;
+			mean = e1 + 3 * idx + 1;
+		} else if (occ < z4) {
+			int idx = (occ - z3) / w3;
+			bin = e2 + idx;
+			mean = (2 * (z3 + w3 * idx) + w3) / 2;
+		} else {
+			bin = e3 - 1;
+			mean = (2 * z4 - w3) / 2;
+		}
+		occ2bin[occ] = bin;
+		if (!seen[bin]) {
+			seen[bin] = 1;
+			bin2mean[bin] = mean;
+		}
+	}
+	return KMX_OK;
+}
+
+// kmodel.hpp:402-456.  The Bloom size is evaluated in double exactly as the reference writes it.
+static void model_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_kmers, int n_hash, uint64_t bytes[8]) {
+	const int hb = n_hash - 1, hk = n_hash - 2;
+	for (int i = 0; i < 8; i++) bytes[i] = 0;
+	for (int i = 0; i < bf_num; i++) {
+		bytes[i] = (uint64_t)(kmer_counts[i] / 5.5 * hb);
+		bytes[3 + i] = (kmer_counts[i] >> 3) * (uint64_t)hk;
+	}
+	bytes[6] = (km_kmers >> 4) * (uint64_t)n_hash;
+	bytes[7] = (km_kmers >> 4) * (uint64_t)hk;
+}
+
+static int rest_prefix_len(int k) {              // rest.hpp:78-83
+	for (int i = 7; i >= 3; i--)
+		if ((k - i) % 4 == 0) return i;
+	return 3;
+}
+
+// =========================================================================================
+// objects
+// =========================================================================================
+struct kmx_db {
+	kmx_db_info_t info;
+	std::vector<uint64_t> lut;        // lut_entries + 1 (guard = total + 1, kmc_file.cpp:223)
+	uint8_t* h_suf = nullptr;         // pinned, record bytes, padded
+	size_t suf_alloc = 0;
+	uint8_t* d_suf = nullptr;
+	uint64_t* d_lut = nullptr;
+	int device = 0, sm_count = 0;
+	bool pinned = false;
+	float ms_upload = 0;
+	cudaStream_t stream = nullptr;
+};
+
+struct RestHost {
+	int32_t k = 0, pre_len = 0, map_size = 0, pre_buffer_size = 0;
+	uint64_t suff_bin_size = 0, count = 0;
+};
+
+struct kmx_model {
+	int ci = 1, cs = 1023, n_hash = 7, n_bits = 5, bf_num = 1, k = 0;
+	int device = 0, sm_count = 0;
+	bool built = false;
+	uint64_t total_kmers = 0, km_kmers = 0, kmer_counts[3] = { 0, 0, 0 };
+	uint64_t bytes[8] = { 0 };        // see kmx_host_sizes
+	std::vector<int32_t> occ2bin, bin2mean;
+	// device
+	uint32_t* d_bf[3] = { nullptr, nullptr, nullptr };
+	uint32_t* d_bf_back[3] = { nullptr, nullptr, nullptr };
+	uint32_t* d_km_back = nullptr;
+	unsigned long long* d_cells[kMaxArrays] = { nullptr };
+	uint16_t* d_occ2bin = nullptr;
+	int32_t* d_bin2mean = nullptr;
+	int32_t* d_hash2index = nullptr;
+	int32_t* d_pre_buffer = nullptr;
+	uint64_t* d_rest_keys = nullptr;
+	int32_t* d_rest_counts = nullptr;
+	RestHost rest;
+	DevModel dm;
+	kmx_info_t info;
+	cudaStream_t stream = nullptr, stream2 = nullptr;
+	// pinned staging for host-pointer queries (two slots)
+	void* h_in[2] = { nullptr, nullptr };
+	int32_t* h_out[2] = { nullptr, nullptr };
+	void* d_in[2] = { nullptr, nullptr };
+	int32_t* d_out[2] = { nullptr, nullptr };
+	size_t stage_bytes = 0, stage_items = 0;
+	cudaEvent_t ev_done[2] = { nullptr, nullptr };
+};
+
+static size_t pad8(uint64_t bytes) { return (size_t)((bytes + 7) & ~7ULL) + 8; }
+static uint64_t cell_words(uint64_t km_byte_size) { return (km_byte_size + 3) / 4; }
+
+static void free_model_device(kmx_model* m) {
+	for (int i = 0; i < 3; i++) {
+		cudaFree(m->d_bf[i]);
+		cudaFree(m->d_bf_back[i]);
+		m->d_bf[i] = m->d_bf_back[i] = nullptr;
+	}
+	cudaFree(m->d_km_back);
+	m->d_km_back = nullptr;
+	for (int i = 0; i < kMaxArrays; i++) {
+		cudaFree(m->d_cells[i]);
+		m->d_cells[i] = nullptr;
+	}
+	cudaFree(m->d_hash2index);
+	cudaFree(m->d_pre_buffer);
+	cudaFree(m->d_rest_keys);
+	cudaFree(m->d_rest_counts);
+	m->d_hash2index = m->d_pre_buffer = nullptr;
+	m->d_rest_keys = nullptr;
+	m->d_rest_counts = nullptr;
+}
+
+// allocate + zero every filter of the model from m->kmer_counts / m->km_kmers (kmodel.hpp:402-456)
+static int alloc_filters(kmx_model* m) {
+	model_sizes(m->kmer_counts, m->bf_num, m->km_kmers, m->n_hash, m->bytes);
+	for (int i = 0; i < m->bf_num; i++) {
+		if (m->bytes[i] == 0 || m->bytes[3 + i] == 0)
+			return fail(KMX_ERANGE, "count class %d holds %llu k-mers: the reference aborts on a zero-length Bloom filter (kmodel.hpp:413-417)",
+			            m->ci + i, (unsigned long long)m->kmer_counts[i]);
+	}
+	if (m->bytes[6] == 0 || m->bytes[7] == 0)
+		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays: the reference aborts on zero-length arrays (kmodel.hpp:443-447)",
+		            (unsigned long long)m->km_kmers);
+	for (int i = 0; i < m->bf_num; i++) {
+		CU(cudaMalloc(&m->d_bf[i], pad8(m->bytes[i])));
+		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->stream));
+		CU(cudaMalloc(&m->d_bf_back[i], pad8(m->bytes[3 + i])));
+		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->stream));
+	}
+	CU(cudaMalloc(&m->d_km_back, pad8(m->bytes[7])));
+	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->stream));
+	const uint64_t words = cell_words(m->bytes[6]);
+	for (int i = 0; i < m->n_bits; i++) {
+		CU(cudaMalloc(&m->d_cells[i], (words + 1) * 8));
+		CU(cudaMemsetAsync(m->d_cells[i], 0, (words + 1) * 8, m->stream));
+	}
+	return KMX_OK;
+}
+
+static void fill_dev_model(kmx_model* m) {
+	DevModel& d = m->dm;
+	memset(&d, 0, sizeof(d));
+	d.k = m->k;
+	d.n_hash = m->n_hash;
+	d.n_bits = m->n_bits;
+	d.bf_num = m->bf_num;
+	d.ci = m->ci;
+	d.cs = m->cs;
+	d.hb = m->n_hash - 1;
+	d.hk = m->n_hash - 2;
+	d.end1 = (1 << m->n_hash) / 4;
+	for (int i = 0; i < m->bf_num; i++) {
+		d.bf[i].words = m->d_bf[i];
+		d.bf[i].mod = make_fastmod(m->bytes[i] * 8);
+		d.bf_back[i].words = m->d_bf_back[i];
+		d.bf_back[i].mod = make_fastmod(m->bytes[3 + i] * 8);
+	}
+	d.km_back.words = m->d_km_back;
+	d.km_back.mod = make_fastmod(m->bytes[7] * 8);
+	d.arr_mod = make_fastmod(m->bytes[6] * 8);
+	for (int i = 0; i < m->n_bits; i++) {
+		d.cells[i] = m->d_cells[i];
+		for (int j = 0; j < m->n_hash; j++) d.arr_seed[i][j] = h_seeds[(i * m->n_hash + j) % 128];   // kmodel.hpp:450-453
+	}
+	d.occ2bin = m->d_occ2bin;
+	d.bin2mean = m->d_bin2mean;
+	d.rest.hash2index = m->d_hash2index;
+	d.rest.pre_buffer = m->d_pre_buffer;
+	d.rest.keys = m->d_rest_keys;
+	d.rest.counts = m->d_rest_counts;
+	d.rest.count = m->rest.count;
+	d.rest.k = m->rest.k;
+	d.rest.suffix_bits = 2 * (m->rest.k - m->rest.pre_len);
+	d.rest.suffix_mask = mask2(m->rest.k - m->rest.pre_len);
+}
+
+static void fill_info(kmx_model* m) {
+	kmx_info_t& f = m->info;
+	f.ci = m->ci; f.cs = m->cs; f.n_hash = m->n_hash; f.n_bits = m->n_bits; f.bf_num = m->bf_num; f.k = m->k;
+	f.total_kmers = m->total_kmers;
+	f.km_kmers = m->km_kmers;
+	f.bf_kmers = 0;
+	f.bf_bytes = 0;
+	for (int i = 0; i < 3; i++) {
+		f.kmer_counts[i] = m->kmer_counts[i];
+		if (i < m->bf_num) {
+			f.bf_kmers += m->kmer_counts[i];
+			f.bf_bytes += m->bytes[i] + m->bytes[3 + i];
+		}
+	}
+	f.km_bytes = 2ULL * m->n_bits * m->bytes[6];
+	f.km_back_bytes = m->bytes[7];
+	f.rest_kmers = m->rest.count;
+	f.rest_bytes = m->rest.suff_bin_size + 4ULL * m->rest.count + 4ULL * m->rest.pre_buffer_size + 4ULL * m->rest.map_size;
+}
+
+// =========================================================================================
+// process-wide
+// =========================================================================================
+extern "C" const char* kmx_last_error(void) { return g_err; }
+extern "C" const char* kmx_version(void) { return "kmx 0.1 (sm_100a)"; }
+
+extern "C" int kmx_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" int kmx_set_device(int ordinal) {
+	int n = kmx_device_count();
+	if (ordinal < 0 || ordinal >= n) return fail(KMX_ENOGPU, "device %d requested, %d present", ordinal, n);
+	g_device = ordinal;
+	CU(cudaSetDevice(ordinal));
+	return KMX_OK;
+}
+
+// =========================================================================================
+// model lifetime
+// =========================================================================================
+extern "C" kmx_model* kmx_create(int ci, int cs, int n_hash, int n_bits) {
+	if (ci < 1 || cs < ci || cs > 65535 || n_hash < 3 || n_hash > kMaxHash || n_bits < 1 || n_bits > kMaxArrays) {
+		fail(KMX_EARG, "unsupported parameters ci=%d cs=%d n_hash=%d n_bits=%d (need 1<=ci<=cs<=65535, 3<=n_hash<=%d, 1<=n_bits<=%d)", ci, cs,
+		     n_hash, n_bits, kMaxHash, kMaxArrays);
+		return nullptr;
+	}
+	kmx_model* m = new kmx_model();
+	m->ci = ci; m->cs = cs; m->n_hash = n_hash; m->n_bits = n_bits;
+	m->bf_num = ci == 1 ? 1 : 3;                         // kmodel.hpp:50
+	memset(&m->info, 0, sizeof(m->info));
+	memset(&m->dm, 0, sizeof(m->dm));
+	int rc = occubin_tables(cs + 1, n_hash, m->occ2bin, m->bin2mean);
+	if (rc != KMX_OK) {
+		fail(rc, "OccuBin(%d, %d): the reference indexes past its table for cs + 1 < %d (occu_bin.hpp:38-44)", cs + 1, n_hash,
+		     (1 << n_hash) / 4 + 3 * (1 << n_hash) / 2);
+		delete m;
+		return nullptr;
+	}
+	fill_info(m);
+	return m;
+}
+
+static int model_attach_device(kmx_model* m) {
+	if (m->stream) return KMX_OK;
+	int rc = require_gpu(&m->sm_count);
+	if (rc) return rc;
+	m->device = g_device;
+	CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+	std::vector<uint16_t> o16(m->occ2bin.size());
+	for (size_t i = 0; i < o16.size(); i++) o16[i] = (uint16_t)m->occ2bin[i];
+	CU(cudaMalloc(&m->d_occ2bin, o16.size() * 2));
+	CU(cudaMemcpy(m->d_occ2bin, o16.data(), o16.size() * 2, cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&m->d_bin2mean, m->bin2mean.size() * 4));
+	CU(cudaMemcpy(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice));
+	return KMX_OK;
+}
+
+extern "C" void kmx_destroy(kmx_model* m) {
+	if (!m) return;
+	if (m->stream) {
+		cudaSetDevice(m->device);
+		cudaStreamSynchronize(m->stream);
+		cudaStreamSynchronize(m->stream2);
+		free_model_device(m);
+		cudaFree(m->d_occ2bin);
+		cudaFree(m->d_bin2mean);
+		for (int s = 0; s < 2; s++) {
+			cudaFreeHost(m->h_in[s]);
+			cudaFreeHost(m->h_out[s]);
+			cudaFree(m->d_in[s]);
+			cudaFree(m->d_out[s]);
+			if (m->ev_done[s]) cudaEventDestroy(m->ev_done[s]);
+		}
+		cudaStreamDestroy(m->stream);
+		cudaStreamDestroy(m->stream2);
+	}
+	delete m;
+}
+
+extern "C" void kmx_info(const kmx_model* m, kmx_info_t* info) {
+	if (m && info) *info = m->info;
+}
+
+extern "C" int kmx_model_sync(kmx_model* m) {
+	if (!m || !m->stream) return fail(KMX_ESTATE, "model has no device state");
+	CU(cudaStreamSynchronize(m->stream));
+	return KMX_OK;
+}
+
+// =========================================================================================
+// KMC database (listing subset)
+// =========================================================================================
+static bool read_exact(FILE* f, void* dst, size_t n) { return n == 0 || fread(dst, 1, n, f) == n; }
+
+extern "C" kmx_db* kmx_db_open(const char* db_base) {
+	if (!db_base) {
+		fail(KMX_EARG, "null database name");
+		return nullptr;
+	}
+	std::string pre_name = std::string(db_base) + ".kmc_pre", suf_name = std::string(db_base) + ".kmc_suf";
+	FILE* fp = fopen(pre_name.c_str(), "rb");
+	if (!fp) {
+		fail(KMX_EIO, "can't open the kmer_data_base %s (%s)", db_base, strerror(errno));
+		return nullptr;
+	}
+	fseeko(fp, 0, SEEK_END);
+	const uint64_t pre_size = (uint64_t)ftello(fp);
+	std::vector<uint8_t> pre(pre_size);
+	rewind(fp);
+	bool ok = pre_size >= 32 && read_exact(fp, pre.data(), pre_size);
+	fclose(fp);
+	if (!ok || memcmp(pre.data(), "KMCP", 4) != 0 || memcmp(pre.data() + pre_size - 4, "KMCP", 4) != 0) {   // kmc_file.cpp:132-171
+		fail(KMX_EFORMAT, "%s is not a KMC prefix file", pre_name.c_str());
+		return nullptr;
+	}
+	kmx_db* db = new kmx_db();
+	memset(&db->info, 0, sizeof(db->info));
+	kmx_db_info_t& h = db->info;
+	memcpy(&h.kmc_version, &pre[pre_size - 12], 4);       // kmc_file.cpp:180-184
+	if (h.kmc_version != 0x200) {
+		fail(KMX_EFORMAT, "%s: KMC database version 0x%x is not supported (only the KMC 2/3 layout 0x200)", pre_name.c_str(), h.kmc_version);
+		delete db;
+		return nullptr;
+	}
+	const uint32_t header_offset = pre[pre_size - 8];     // kmc_file.cpp:190-193: one byte
+	if ((uint64_t)header_offset + 8 > pre_size || header_offset < 37) {
+		fail(KMX_EFORMAT, "%s: bad header offset %u", pre_name.c_str(), header_offset);
+		delete db;
+		return nullptr;
+	}
+	const uint8_t* p = &pre[pre_size - 8 - header_offset];   // kmc_file.cpp:197-209
+	memcpy(&h.k, p, 4);
+	memcpy(&h.mode, p + 4, 4);
+	memcpy(&h.counter_size, p + 8, 4);
+	memcpy(&h.lut_prefix_length, p + 12, 4);
+	memcpy(&h.signature_len, p + 16, 4);
+	memcpy(&h.min_count, p + 20, 4);
+	memcpy(&h.max_count, p + 24, 4);
+	memcpy(&h.total_kmers, p + 28, 8);
+	const uint64_t body = pre_size - 12;                  // two markers and the header_offset word removed
+	const uint64_t sig_bytes = ((1ULL << (2 * h.signature_len)) + 1) * 4;
+	if (h.signature_len > 11 || sig_bytes + header_offset + 8 > body) {
+		fail(KMX_EFORMAT, "%s: signature map does not fit the file", pre_name.c_str());
+		delete db;
+		return nullptr;
+	}
+	const uint64_t lut_bytes = body - (sig_bytes + header_offset + 8);   // kmc_file.cpp:212
+	h.lut_entries = lut_bytes / 8;
+	if (h.k < 3 || h.k > 32 || h.lut_prefix_length > h.k || (h.k - h.lut_prefix_length) % 4 != 0 || h.lut_entries == 0 ||
+	    h.counter_size > 4) {
+		fail(KMX_EFORMAT, "%s: unsupported geometry k=%u lut_prefix_length=%u counter_size=%u (k <= 32 only: the reference packs k-mers in 64 bits, tools.hpp:63-76)",
+		     pre_name.c_str(), h.k, h.lut_prefix_length, h.counter_size);
+		delete db;
+		return nullptr;
+	}
+	if (h.mode != 0) {
+		fail(KMX_EFORMAT, "%s: mode %u (quality-weighted counters) is not supported", pre_name.c_str(), h.mode);
+		delete db;
+		return nullptr;
+	}
+	db->lut.resize(h.lut_entries + 1);
+	memcpy(db->lut.data(), &pre[4], (h.lut_entries + 1) * 8);
+	db->lut[h.lut_entries] = h.total_kmers + 1;           // kmc_file.cpp:223
+	h.record_bytes = (h.k - h.lut_prefix_length) / 4 + h.counter_size;   // kmc_file.cpp:230-232
+	h.suffix_bytes = (uint64_t)h.record_bytes * h.total_kmers;
+
+	FILE* fs = fopen(suf_name.c_str(), "rb");
+	if (!fs) {
+		fail(KMX_EIO, "can't open the kmer_data_base %s (%s)", db_base, strerror(errno));
+		delete db;
+		return nullptr;
+	}
+	fseeko(fs, 0, SEEK_END);
+	const uint64_t suf_size = (uint64_t)ftello(fs);
+	char marker[4];
+	rewind(fs);
+	ok = suf_size >= 8 && read_exact(fs, marker, 4) && memcmp(marker, "KMCS", 4) == 0 && suf_size - 8 >= h.suffix_bytes;
+	if (!ok) {
+		fclose(fs);
+		fail(KMX_EFORMAT, "%s is not a KMC suffix file holding %llu records", suf_name.c_str(), (unsigned long long)h.total_kmers);
+		delete db;
+		return nullptr;
+	}
+	db->suf_alloc = (size_t)((h.suffix_bytes + 15) & ~15ULL) + 16;
+	// pinned when a device is present (fast upload); plain memory otherwise so that header-only
+	// inspection works without a GPU
+	int n_dev = kmx_device_count();
+	if (n_dev > 0) {
+		cudaSetDevice(g_device);
+		if (cudaMallocHost(&db->h_suf, db->suf_alloc) != cudaSuccess) {
+			cudaGetLastError();
+			db->h_suf = nullptr;
+		}
+	}
+	bool pinned = db->h_suf != nullptr;
+	if (!pinned) db->h_suf = (uint8_t*)malloc(db->suf_alloc);
+	ok = db->h_suf && read_exact(fs, db->h_suf, h.suffix_bytes);
+	fclose(fs);
+	if (!ok) {
+		fail(KMX_EIO, "short read on %s", suf_name.c_str());
+		if (pinned) cudaFreeHost(db->h_suf); else free(db->h_suf);
+		delete db;
+		return nullptr;
+	}
+	memset(db->h_suf + h.suffix_bytes, 0, db->suf_alloc - h.suffix_bytes);
+	db->pinned = pinned;
+	db->device = g_device;
+	return db;
+}
+
+extern "C" void kmx_db_info(const kmx_db* db, kmx_db_info_t* info) {
+	if (db && info) {
+		*info = db->info;
+		info->on_device = db->d_suf != nullptr;
+	}
+}
+
+extern "C" int kmx_db_upload(kmx_db* db) {
+	if (!db) return fail(KMX_EARG, "null database");
+	if (db->d_suf) return KMX_OK;
+	int rc = require_gpu(&db->sm_count);
+	if (rc) return rc;
+	db->device = g_device;
+	if (!db->stream) CU(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+	cudaEvent_t e0, e1;
+	CU(cudaEventCreate(&e0));
+	CU(cudaEventCreate(&e1));
+	CU(cudaMalloc(&db->d_suf, db->suf_alloc));
+	CU(cudaMalloc(&db->d_lut, db->lut.size() * 8));
+	CU(cudaEventRecord(e0, db->stream));
+	CU(cudaMemcpyAsync(db->d_suf, db->h_suf, db->suf_alloc, cudaMemcpyHostToDevice, db->stream));
+	CU(cudaMemcpyAsync(db->d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, db->stream));
+	CU(cudaEventRecord(e1, db->stream));
+	CU(cudaStreamSynchronize(db->stream));
+	CU(cudaEventElapsedTime(&db->ms_upload, e0, e1));
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	return KMX_OK;
+}
+
+extern "C" void kmx_db_close(kmx_db* db) {
+	if (!db) return;
+	if (db->d_suf || db->stream) {
+		cudaSetDevice(db->device);
+		cudaFree(db->d_suf);
+		cudaFree(db->d_lut);
+		if (db->stream) cudaStreamDestroy(db->stream);
+	}
+	if (db->h_suf) {
+		if (db->pinned) cudaFreeHost(db->h_suf); else free(db->h_suf);
+	}
+	delete db;
+}
+
+static DevDb dev_db(const kmx_db* db) {
+	DevDb d;
+	memset(&d, 0, sizeof(d));
+	d.suf = db->d_suf;
+	d.lut = db->d_lut;
+	d.lut_entries = db->info.lut_entries;
+	d.total = db->info.total_kmers;
+	d.prefix_mask = (1ULL << (2 * db->info.lut_prefix_length)) - 1;
+	d.suffix_bytes = (db->info.k - db->info.lut_prefix_length) / 4;
+	d.counter_bytes = db->info.counter_size;
+	d.rec_bytes = db->info.record_bytes;
+	d.min_count = db->info.min_count;
+	d.max_count = db->info.max_count;
+	d.k = (int)db->info.k;
+	return d;
+}
+
+extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64_t* n_out) {
+	if (!db || !kmers || !counts || !n_out) return fail(KMX_EARG, "null argument");
+	int rc = kmx_db_upload(db);
+	if (rc) return rc;
+	CU(cudaSetDevice(db->device));
+	const uint64_t total = db->info.total_kmers;
+	*n_out = 0;
+	if (total == 0) return KMX_OK;
+	const uint64_t n_tiles = (total + kTile - 1) / kTile;
+	uint32_t* d_cnt = nullptr;
+	uint64_t* d_off = nullptr;
+	uint64_t* d_k = nullptr;
+	uint32_t* d_c = nullptr;
+	CU(cudaMalloc(&d_cnt, n_tiles * 4));
+	CU(cudaMalloc(&d_off, (n_tiles + 1) * 8));
+	CU(cudaMalloc(&d_k, total * 8));
+	CU(cudaMalloc(&d_c, total * 4));
+	DevDb d = dev_db(db);
+	CU(launch_list_count(d, d_cnt, db->sm_count, db->stream));
+	CU(launch_tile_scan(d_cnt, n_tiles, d_off, db->stream));
+	CU(launch_list(d, d_off, d_k, d_c, db->sm_count, db->stream));
+	uint64_t listed = 0;
+	CU(cudaMemcpyAsync(&listed, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, db->stream));
+	CU(cudaStreamSynchronize(db->stream));
+	CU(cudaMemcpy(kmers, d_k, listed * 8, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(counts, d_c, listed * 4, cudaMemcpyDeviceToHost));
+	cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_k); cudaFree(d_c);
+	*n_out = listed;
+	return KMX_OK;
+}
+
+// =========================================================================================
+// build: KModel::init (kmodel.hpp:57-86)
+// =========================================================================================
+static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_surv_occ, uint64_t n) {
+	RestHost& r = m->rest;
+	r.k = m->k;
+	r.pre_len = rest_prefix_len(m->k);                    // rest.hpp:140-149
+	r.map_size = 1 << (2 * r.pre_len);
+	r.count = n;
+	r.suff_bin_size = n * (uint64_t)((m->k - r.pre_len) / 4);
+	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "%llu rest entries overflow the reference's int indices (rest.hpp:66-70)", (unsigned long long)n);
+	CU(cudaMalloc(&m->d_hash2index, (size_t)r.map_size * 4));
+	CU(cudaMalloc(&m->d_pre_buffer, ((size_t)r.map_size + 1) * 4));
+	CU(cudaMalloc(&m->d_rest_keys, (n + 1) * 8));
+	CU(cudaMalloc(&m->d_rest_counts, (n + 1) * 4));
+	int32_t* d_first = nullptr;
+	int32_t* d_groups = nullptr;
+	void* d_temp = nullptr;
+	size_t temp_bytes = 0;
+	CU(cudaMalloc(&d_first, (size_t)r.map_size * 4));
+	CU(cudaMalloc(&d_groups, 4));
+	CU(rest_sort_bytes(n, &temp_bytes));
+	if (temp_bytes) CU(cudaMalloc(&d_temp, temp_bytes));
+	CU(launch_rest_sort(d_temp, temp_bytes, d_surv_kmer, m->d_rest_keys, d_surv_occ, m->d_rest_counts, n, 2 * m->k, m->stream));
+	CU(launch_rest_index(m->d_rest_keys, n, 2 * (m->k - r.pre_len), r.map_size, d_first, m->d_hash2index, m->d_pre_buffer, d_groups, m->stream));
+	int32_t groups = 0;
+	CU(cudaMemcpyAsync(&groups, d_groups, 4, cudaMemcpyDeviceToHost, m->stream));
+	CU(cudaStreamSynchronize(m->stream));
+	r.pre_buffer_size = groups + 1;                       // rest.hpp:119: new int[++pre_buffer_size]
+	cudaFree(d_first); cudaFree(d_groups); cudaFree(d_temp);
+	return KMX_OK;
+}
+
+extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
+	if (!m || !db) return fail(KMX_EARG, "null argument");
+	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
+	auto wall0 = std::chrono::high_resolution_clock::now();
+	int rc = model_attach_device(m);
+	if (rc) return rc;
+	CU(cudaSetDevice(m->device));
+	rc = kmx_db_upload(db);
+	if (rc) return rc;
+	if (db->device != m->device) return fail(KMX_EARG, "database is on device %d, model on device %d", db->device, m->device);
+	m->k = (int)db->info.k;
+	m->total_kmers = db->info.total_kmers;
+	if (m->k < 3) return fail(KMX_ERANGE, "k=%d: the (k-2)-mer filters need k >= 3", m->k);
+	const uint64_t total = m->total_kmers;
+	const uint64_t n_tiles = (total + kTile - 1) / kTile;
+	DevDb d = dev_db(db);
+	cudaEvent_t ev[6];
+	for (auto& e : ev) CU(cudaEventCreate(&e));
+
+	// ---- pass 1: class histogram (kmodel.hpp:423-434) ----
+	uint32_t* d_tile_cnt = nullptr;
+	uint64_t* d_tile_off = nullptr;
+	CountOut* d_count = nullptr;
+	CU(cudaMalloc(&d_tile_cnt, (n_tiles + 1) * 4));
+	CU(cudaMalloc(&d_tile_off, (n_tiles + 1) * 8));
+	CU(cudaMalloc(&d_count, sizeof(CountOut)));
+	CU(cudaEventRecord(ev[0], m->stream));
+	CU(cudaMemsetAsync(d_count, 0, sizeof(CountOut), m->stream));
+	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, m->sm_count, m->stream));
+	CU(launch_tile_scan(d_tile_cnt, n_tiles, d_tile_off, m->stream));
+	CountOut cnt;
+	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
+	CU(cudaEventRecord(ev[1], m->stream));
+	CU(cudaStreamSynchronize(m->stream));
+	if (cnt.bad_count)
+		return fail(KMX_ERANGE, "%llu records have a count below ci=%d or above cs=%d: the reference indexes out of bounds there (kmodel.hpp:427, occu_bin.hpp:70)",
+		            (unsigned long long)cnt.bad_count, m->ci, m->cs);
+	uint64_t bf_kmers = 0;
+	for (int i = 0; i < m->bf_num; i++) {
+		m->kmer_counts[i] = cnt.class_count[i];
+		bf_kmers += cnt.class_count[i];
+	}
+	m->km_kmers = total - bf_kmers;                       // kmodel.hpp:433: header total, not the listed count
+	rc = alloc_filters(m);
+	if (rc) return rc;
+	m->rest.k = m->k;
+	m->rest.pre_len = rest_prefix_len(m->k);
+	fill_dev_model(m);
+
+	// ---- pass 2: Bloom inserts + array-bound stream (kmodel.hpp:68-74) ----
+	const uint64_t n_items = cnt.array_bound;
+	uint64_t* d_item_kmer = nullptr;
+	uint32_t* d_item_occ = nullptr;
+	CU(cudaMalloc(&d_item_kmer, (n_items + 1) * 8));
+	CU(cudaMalloc(&d_item_occ, (n_items + 1) * 4));
+	CU(launch_encode(d, m->dm, d_tile_off, d_item_kmer, d_item_occ, m->sm_count, m->stream));
+	CU(cudaEventRecord(ev[2], m->stream));
+
+	// ---- greedy insert (kmodel.hpp:508-573) ----
+	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
+	const uint64_t n_batches = (n_items + batch_items - 1) / batch_items;
+	InsertArgs a;
+	memset(&a, 0, sizeof(a));
+	InsertCtl ctl;
+	memset(&ctl, 0, sizeof(ctl));
+	uint64_t rest_cap = 0;
+	if (n_items > 0) {
+		a.item_kmer = d_item_kmer;
+		a.item_occ = d_item_occ;
+		a.n_items = n_items;
+		for (int s = 0; s < 2; s++) {
+			CU(cudaMalloc(&a.buf_kmer[s], batch_items * 8));
+			CU(cudaMalloc(&a.buf_occ[s], batch_items * 4));
+		}
+		CU(cudaMalloc(&a.status, batch_items * 4));
+		CU(cudaMalloc(&a.rank, batch_items * 4));
+		CU(cudaMalloc(&a.holepos, batch_items * 4));
+		CU(cudaMalloc(&a.tile_fail, batch_items / 256 * 4));
+		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, m->stream));
+		a.resv_slots = 1u << 20;
+		if (const char* s = getenv("KMX_RESV_LOG2")) {
+			int v = atoi(s);
+			if (v >= 10 && v <= 26) a.resv_slots = 1u << v;
+		}
+		CU(cudaMalloc(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4));
+		CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, m->stream));
+		CU(cudaMalloc(&a.ctl, sizeof(InsertCtl)));
+		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), m->stream));
+		a.max_iterations = kBucket + 64;
+		int grid = 0;
+		CU(insert_grid_size(&grid, m->sm_count));
+		const uint64_t chunk = 64;                         // batches per launch
+		for (uint64_t b0 = 0; b0 < n_batches; b0 += chunk) {
+			const uint64_t nb = std::min<uint64_t>(chunk, n_batches - b0);
+			const uint64_t need = ctl.rest_n + nb * batch_items + m->n_bits;
+			if (need > rest_cap) {                          // grow the survivor list (worst case: nothing is accepted)
+				uint64_t new_cap = std::max<uint64_t>(need, rest_cap * 2);
+				if (new_cap > n_items + m->n_bits) new_cap = std::max<uint64_t>(need, n_items + m->n_bits);
+				uint64_t* nk = nullptr;
+				uint32_t* no = nullptr;
+				CU(cudaMalloc(&nk, new_cap * 8));
+				CU(cudaMalloc(&no, new_cap * 4));
+				if (ctl.rest_n) {
+					CU(cudaMemcpyAsync(nk, a.rest_kmer, ctl.rest_n * 8, cudaMemcpyDeviceToDevice, m->stream));
+					CU(cudaMemcpyAsync(no, a.rest_occ, ctl.rest_n * 4, cudaMemcpyDeviceToDevice, m->stream));
+					CU(cudaStreamSynchronize(m->stream));
+				}
+				cudaFree(a.rest_kmer);
+				cudaFree(a.rest_occ);
+				a.rest_kmer = nk;
+				a.rest_occ = no;
+				rest_cap = new_cap;
+			}
+			a.rest_cap = rest_cap;
+			a.first_batch = b0;
+			a.n_batches = nb;
+			CU(launch_insert(m->dm, a, grid, m->stream));
+			CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, m->stream));
+			CU(cudaStreamSynchronize(m->stream));
+			if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
+		}
+	}
+	CU(cudaEventRecord(ev[3], m->stream));
+
+	// ---- rest table (rest.hpp:157-161) ----
+	rc = build_rest_table(m, a.rest_kmer, a.rest_occ, ctl.rest_n);
+	if (rc) return rc;
+	CU(cudaEventRecord(ev[4], m->stream));
+	CU(cudaStreamSynchronize(m->stream));
+	fill_dev_model(m);
+	m->built = true;
+
+	kmx_info_t& f = m->info;
+	fill_info(m);
+	f.insert_attempts = ctl.attempts;
+	f.insert_accepted = ctl.accepted;
+	f.insert_iterations = ctl.iterations;
+	f.batches = n_batches;
+	f.ms_upload = db->ms_upload;
+	CU(cudaEventElapsedTime(&f.ms_count, ev[0], ev[1]));
+	CU(cudaEventElapsedTime(&f.ms_encode, ev[1], ev[2]));
+	CU(cudaEventElapsedTime(&f.ms_insert, ev[2], ev[3]));
+	CU(cudaEventElapsedTime(&f.ms_rest, ev[3], ev[4]));
+	CU(cudaEventElapsedTime(&f.ms_total_device, ev[0], ev[4]));
+	for (auto& e : ev) cudaEventDestroy(e);
+	cudaFree(d_tile_cnt); cudaFree(d_tile_off); cudaFree(d_count);
+	cudaFree(d_item_kmer); cudaFree(d_item_occ);
+	for (int s = 0; s < 2; s++) {
+		cudaFree(a.buf_kmer[s]);
+		cudaFree(a.buf_occ[s]);
+	}
+	cudaFree(a.status); cudaFree(a.rank); cudaFree(a.holepos); cudaFree(a.tile_fail); cudaFree(a.resv); cudaFree(a.ctl);
+	cudaFree(a.rest_kmer); cudaFree(a.rest_occ);
+	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - wall0).count();
+	return KMX_OK;
+}
+
+extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
+	if (!m) return fail(KMX_EARG, "null model");
+	int rc = require_gpu(nullptr);
+	if (rc) return rc;
+	kmx_db* db = kmx_db_open(db_base);
+	if (!db) return KMX_EIO;
+	rc = kmx_init_from_db(m, db);
+	kmx_db_close(db);
+	return rc;
+}
+
+// =========================================================================================
+// save / load (kmodel.hpp:173-235, rest.hpp:163-221)
+// =========================================================================================
+static int write_device(FILE* f, const void* d_ptr, uint64_t bytes, std::vector<uint8_t>& tmp) {
+	if (bytes == 0) return KMX_OK;
+	const size_t padded = (size_t)((bytes + 7) & ~7ULL);
+	if (tmp.size() < padded) tmp.resize(padded);
+	CU(cudaMemcpy(tmp.data(), d_ptr, padded, cudaMemcpyDeviceToHost));
+	if (fwrite(tmp.data(), 1, bytes, f) != bytes) return fail(KMX_EIO, "short write (%s)", strerror(errno));
+	return KMX_OK;
+}
+
+extern "C" int kmx_save(kmx_model* m, const char* dir) {
+	if (!m || !dir) return fail(KMX_EARG, "null argument");
+	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	CU(cudaSetDevice(m->device));
+	CU(cudaStreamSynchronize(m->stream));
+	std::string base(dir);
+	FILE* fh = fopen((base + "/header").c_str(), "w");
+	if (!fh) return fail(KMX_EIO, "cannot write %s/header (%s); the directory must exist (README.md:77)", dir, strerror(errno));
+	fprintf(fh, "number_hash %d\nnumber_bit %d\nci %d\ncs %d\n", m->n_hash, m->n_bits, m->ci, m->cs);   // kmodel.hpp:175-180
+	fclose(fh);
+	FILE* f = fopen((base + "/km.bin").c_str(), "wb");
+	if (!f) return fail(KMX_EIO, "cannot write %s/km.bin (%s)", dir, strerror(errno));
+	std::vector<uint8_t> tmp;
+	int rc = KMX_OK;
+	fwrite(&m->km_kmers, 8, 1, f);
+	for (int i = 0; i < m->bf_num; i++) fwrite(&m->kmer_counts[i], 8, 1, f);
+	for (int i = 0; i < m->bf_num && !rc; i++) {
+		rc = write_device(f, m->d_bf[i], m->bytes[i], tmp);
+		if (!rc) rc = write_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp);
+	}
+	if (!rc) rc = write_device(f, m->d_km_back, m->bytes[7], tmp);
+	const uint64_t words = cell_words(m->bytes[6]);
+	uint32_t* d_val = nullptr;
+	uint32_t* d_tag = nullptr;
+	if (!rc) {
+		if (cudaMalloc(&d_val, (words + 2) * 4) != cudaSuccess || cudaMalloc(&d_tag, (words + 2) * 4) != cudaSuccess)
+			rc = fail(KMX_ECUDA, "out of device memory while saving");
+	}
+	for (int i = 0; i < m->n_bits && !rc; i++) {
+		cudaError_t e = launch_split_cells(m->d_cells[i], words, d_val, d_tag, m->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+		if (e != cudaSuccess) rc = fail(KMX_ECUDA, "split kernel: %s", cudaGetErrorString(e));
+		if (!rc) rc = write_device(f, d_val, m->bytes[6], tmp);      // bit_array_1
+		if (!rc) rc = write_device(f, d_tag, m->bytes[6], tmp);      // bit_array_2
+	}
+	cudaFree(d_val);
+	cudaFree(d_tag);
+	if (fclose(f) != 0 && !rc) rc = fail(KMX_EIO, "close %s/km.bin (%s)", dir, strerror(errno));
+	if (rc) return rc;
+
+	// rest.bin (rest.hpp:197-221)
+	const RestHost& r = m->rest;
+	std::vector<uint64_t> keys(r.count);
+	std::vector<int32_t> counts(r.count), h2i(r.map_size), pre(r.pre_buffer_size);
+	if (r.count) {
+		CU(cudaMemcpy(keys.data(), m->d_rest_keys, r.count * 8, cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(counts.data(), m->d_rest_counts, r.count * 4, cudaMemcpyDeviceToHost));
+	}
+	CU(cudaMemcpy(h2i.data(), m->d_hash2index, (size_t)r.map_size * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(pre.data(), m->d_pre_buffer, (size_t)r.pre_buffer_size * 4, cudaMemcpyDeviceToHost));
+	const int sg = (r.k - r.pre_len) / 4;
+	std::vector<uint8_t> suffix((size_t)r.suff_bin_size);
+	for (uint64_t i = 0; i < r.count; i++)
+		for (int b = 0; b < sg; b++) suffix[i * sg + b] = (uint8_t)(keys[i] >> (8 * (sg - 1 - b)));
+	FILE* fr = fopen((base + "/rest.bin").c_str(), "wb");
+	if (!fr) return fail(KMX_EIO, "cannot write %s/rest.bin (%s)", dir, strerror(errno));
+	int32_t hdr[4] = { r.k, r.pre_len, r.map_size, r.pre_buffer_size };
+	fwrite(hdr, 4, 4, fr);
+	fwrite(&r.suff_bin_size, 8, 1, fr);
+	fwrite(&r.count, 8, 1, fr);
+	fwrite(h2i.data(), 4, h2i.size(), fr);
+	fwrite(pre.data(), 4, pre.size(), fr);
+	fwrite(suffix.data(), 1, suffix.size(), fr);
+	fwrite(counts.data(), 4, counts.size(), fr);
+	if (fclose(fr) != 0) return fail(KMX_EIO, "close %s/rest.bin (%s)", dir, strerror(errno));
+	return KMX_OK;
+}
+
+static int read_to_device(FILE* f, void* d_ptr, uint64_t bytes, std::vector<uint8_t>& tmp) {
+	const size_t padded = (size_t)((bytes + 7) & ~7ULL);
+	if (tmp.size() < padded) tmp.resize(padded);
+	if (bytes && fread(tmp.data(), 1, bytes, f) != bytes) return fail(KMX_EFORMAT, "km.bin is shorter than its header implies");
+	memset(tmp.data() + bytes, 0, padded - bytes);
+	CU(cudaMemcpy(d_ptr, tmp.data(), padded, cudaMemcpyHostToDevice));
+	return KMX_OK;
+}
+
+static int load_into(kmx_model* m, const std::string& base) {
+	int rc = model_attach_device(m);
+	if (rc) return rc;
+	CU(cudaSetDevice(m->device));
+	FILE* f = fopen((base + "/km.bin").c_str(), "rb");
+	if (!f) return fail(KMX_EIO, "cannot open %s/km.bin (%s)", base.c_str(), strerror(errno));
+	bool ok = fread(&m->km_kmers, 8, 1, f) == 1;
+	for (int i = 0; i < m->bf_num; i++) ok = ok && fread(&m->kmer_counts[i], 8, 1, f) == 1;
+	if (!ok) {
+		fclose(f);
+		return fail(KMX_EFORMAT, "%s/km.bin: truncated header", base.c_str());
+	}
+	rc = alloc_filters(m);
+	if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(KMX_ECUDA, "zero-fill of the filters failed");   // the copies below run on the default stream
+	std::vector<uint8_t> tmp;
+	for (int i = 0; i < m->bf_num && !rc; i++) {
+		rc = read_to_device(f, m->d_bf[i], m->bytes[i], tmp);
+		if (!rc) rc = read_to_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp);
+	}
+	if (!rc) rc = read_to_device(f, m->d_km_back, m->bytes[7], tmp);
+	const uint64_t words = cell_words(m->bytes[6]);
+	uint32_t* d_val = nullptr;
+	uint32_t* d_tag = nullptr;
+	if (!rc && (cudaMalloc(&d_val, (words + 2) * 4) != cudaSuccess || cudaMalloc(&d_tag, (words + 2) * 4) != cudaSuccess))
+		rc = fail(KMX_ECUDA, "out of device memory while loading");
+	for (int i = 0; i < m->n_bits && !rc; i++) {
+		rc = read_to_device(f, d_val, m->bytes[6], tmp);
+		if (!rc) rc = read_to_device(f, d_tag, m->bytes[6], tmp);
+		if (!rc) {
+			cudaError_t e = launch_merge_cells(d_val, d_tag, words, m->d_cells[i], m->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+			if (e != cudaSuccess) rc = fail(KMX_ECUDA, "merge kernel: %s", cudaGetErrorString(e));
+		}
+	}
+	cudaFree(d_val);
+	cudaFree(d_tag);
+	fclose(f);
+	if (rc) return rc;
+
+	// rest.bin (rest.hpp:163-195)
+	FILE* fr = fopen((base + "/rest.bin").c_str(), "rb");
+	if (!fr) return fail(KMX_EIO, "cannot open %s/rest.bin (%s)", base.c_str(), strerror(errno));
+	RestHost& r = m->rest;
+	int32_t hdr[4];
+	ok = fread(hdr, 4, 4, fr) == 4 && fread(&r.suff_bin_size, 8, 1, fr) == 1 && fread(&r.count, 8, 1, fr) == 1;
+	if (ok) {
+		r.k = hdr[0]; r.pre_len = hdr[1]; r.map_size = hdr[2]; r.pre_buffer_size = hdr[3];
+		ok = r.k >= 3 && r.k <= 32 && r.pre_len >= 1 && r.pre_len <= r.k && r.map_size == (1 << (2 * r.pre_len)) && r.pre_buffer_size >= 1 &&
+		     r.pre_buffer_size <= r.map_size + 1 && r.suff_bin_size == r.count * (uint64_t)((r.k - r.pre_len) / 4) && (r.k - r.pre_len) % 4 == 0;
+	}
+	if (!ok) {
+		fclose(fr);
+		return fail(KMX_EFORMAT, "%s/rest.bin: bad header", base.c_str());
+	}
+	const int sg = (r.k - r.pre_len) / 4;
+	std::vector<int32_t> h2i(r.map_size), pre(r.pre_buffer_size), counts(r.count);
+	std::vector<uint8_t> suffix((size_t)r.suff_bin_size);
+	ok = read_exact(fr, h2i.data(), h2i.size() * 4) && read_exact(fr, pre.data(), pre.size() * 4) &&
+	     read_exact(fr, suffix.data(), suffix.size()) && read_exact(fr, counts.data(), counts.size() * 4);
+	fclose(fr);
+	if (!ok) return fail(KMX_EFORMAT, "%s/rest.bin: truncated", base.c_str());
+	// rebuild the full keys: entry e of group g carries the prefix p with hash2index[p] == g
+	std::vector<uint64_t> keys(r.count);
+	for (int p = 0; p < r.map_size; p++) {
+		int g = h2i[p];
+		if (g < 0) continue;
+		if (g + 1 >= r.pre_buffer_size) return fail(KMX_EFORMAT, "%s/rest.bin: group index out of range", base.c_str());
+		for (int64_t e = pre[g]; e < pre[g + 1]; e++) {
+			if (e < 0 || (uint64_t)e >= r.count) return fail(KMX_EFORMAT, "%s/rest.bin: entry index out of range", base.c_str());
+			uint64_t s = 0;
+			for (int b = 0; b < sg; b++) s = (s << 8) | suffix[(size_t)e * sg + b];
+			keys[e] = ((uint64_t)p << (8 * sg)) | s;
+		}
+	}
+	m->k = r.k;
+	CU(cudaMalloc(&m->d_hash2index, (size_t)r.map_size * 4));
+	CU(cudaMalloc(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4));
+	CU(cudaMalloc(&m->d_rest_keys, (r.count + 1) * 8));
+	CU(cudaMalloc(&m->d_rest_counts, (r.count + 1) * 4));
+	CU(cudaMemcpy(m->d_hash2index, h2i.data(), h2i.size() * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(m->d_pre_buffer, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice));
+	if (r.count) {
+		CU(cudaMemcpy(m->d_rest_keys, keys.data(), r.count * 8, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(m->d_rest_counts, counts.data(), r.count * 4, cudaMemcpyHostToDevice));
+	}
+	fill_dev_model(m);
+	fill_info(m);
+	m->built = true;
+	return KMX_OK;
+}
+
+extern "C" kmx_model* kmx_load(const char* dir) {
+	if (!dir) {
+		fail(KMX_EARG, "null directory");
+		return nullptr;
+	}
+	std::string base(dir);
+	FILE* fh = fopen((base + "/header").c_str(), "r");
+	if (!fh) {
+		fail(KMX_EIO, "load_model: cant't open the header of the model ! (%s/header)", dir);
+		return nullptr;
+	}
+	char key[128];
+	int v[4] = { 0, 0, 0, 0 };
+	bool ok = true;
+	for (int i = 0; i < 4; i++) ok = ok && fscanf(fh, "%127s %d", key, &v[i]) == 2;   // kmodel.hpp:686-691: positional
+	fclose(fh);
+	if (!ok) {
+		fail(KMX_EFORMAT, "%s/header: expected four 'name value' lines", dir);
+		return nullptr;
+	}
+	if (require_gpu(nullptr)) return nullptr;
+	kmx_model* m = kmx_create(v[2], v[3], v[0], v[1]);
+	if (!m) return nullptr;
+	if (load_into(m, base) != KMX_OK) {
+		kmx_destroy(m);
+		return nullptr;
+	}
+	return m;
+}
+
+// =========================================================================================
+// retrieval (kmodel.hpp:90-116)
+// =========================================================================================
+extern "C" int kmx_query_packed_device(kmx_model* m, const uint64_t* d_kmers, size_t n, int32_t* d_out, void* stream) {
+	if (!m || (n && (!d_kmers || !d_out))) return fail(KMX_EARG, "null argument");
+	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
+	CU(launch_query_packed(m->dm, d_kmers, n, d_out, nullptr, m->sm_count, stream ? (cudaStream_t)stream : m->stream));
+	return KMX_OK;
+}
+
+extern "C" int kmx_query_ascii_device(kmx_model* m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, void* stream) {
+	if (!m || (n && (!d_flat || !d_out))) return fail(KMX_EARG, "null argument");
+	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	if (stride < (size_t)m->k) return fail(KMX_EARG, "stride %zu shorter than k=%d", stride, m->k);
+	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
+	CU(launch_query_ascii(m->dm, d_flat, stride, n, d_out, m->sm_count, stream ? (cudaStream_t)stream : m->stream));
+	return KMX_OK;
+}
+
+static int ensure_staging(kmx_model* m, size_t item_bytes) {
+	const size_t items = 1u << 22;                         // queries per pipeline step
+	const size_t bytes = items * item_bytes;
+	if (m->stage_bytes >= bytes && m->stage_items == items) return KMX_OK;
+	for (int s = 0; s < 2; s++) {
+		cudaFreeHost(m->h_in[s]); cudaFree(m->d_in[s]);
+		m->h_in[s] = nullptr; m->d_in[s] = nullptr;
+		CU(cudaMallocHost(&m->h_in[s], bytes));
+		CU(cudaMalloc(&m->d_in[s], bytes));
+		if (!m->h_out[s]) {
+			CU(cudaMallocHost((void**)&m->h_out[s], items * 4));
+			CU(cudaMalloc((void**)&m->d_out[s], items * 4));
+			CU(cudaEventCreateWithFlags(&m->ev_done[s], cudaEventDisableTiming));
+		}
+	}
+	m->stage_bytes = bytes;
+	m->stage_items = items;
+	return KMX_OK;
+}
+
+static bool is_pinned(const void* p) {
+	cudaPointerAttributes at;
+	if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
+}
+
+// host buffers -> device in steps of 4 Mi queries, two slots on two streams so that the copy of
+// step i+1 overlaps the kernel and the read-back of step i; pinned caller buffers skip staging
+static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t stride, size_t n, int32_t* out, int32_t* path, bool ascii) {
+	if (!m || (n && (!in || (!out && !path)))) return fail(KMX_EARG, "null argument");
+	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
+	if (n == 0) return KMX_OK;
+	CU(cudaSetDevice(m->device));
+	int rc = ensure_staging(m, item_bytes);
+	if (rc) return rc;
+	int32_t* res = path ? path : out;
+	const bool in_pinned = is_pinned(in), out_pinned = is_pinned(res);
+	cudaStream_t st[2] = { m->stream, m->stream2 };
+	size_t done_off[2] = { 0, 0 }, done_n[2] = { 0, 0 };
+	const uint8_t* src = (const uint8_t*)in;
+	int slot = 0;
+	for (size_t off = 0; off < n; off += m->stage_items, slot ^= 1) {
+		const size_t cnt = std::min(m->stage_items, n - off);
+		if (done_n[slot]) {                                // slot busy with an earlier step: drain it
+			CU(cudaEventSynchronize(m->ev_done[slot]));
+			if (!out_pinned) memcpy(res + done_off[slot], m->h_out[slot], done_n[slot] * 4);
+			done_n[slot] = 0;
+		}
+		const void* h_src = src + off * item_bytes;
+		if (!in_pinned) {
+			memcpy(m->h_in[slot], h_src, cnt * item_bytes);
+			h_src = m->h_in[slot];
+		}
+		CU(cudaMemcpyAsync(m->d_in[slot], h_src, cnt * item_bytes, cudaMemcpyHostToDevice, st[slot]));
+		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->d_in[slot], stride, cnt, m->d_out[slot], m->sm_count, st[slot]));
+		else CU(launch_query_packed(m->dm, (const uint64_t*)m->d_in[slot], cnt, path ? nullptr : m->d_out[slot], path ? m->d_out[slot] : nullptr, m->sm_count, st[slot]));
+		CU(cudaMemcpyAsync(out_pinned ? (void*)(res + off) : (void*)m->h_out[slot], m->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st[slot]));
+		CU(cudaEventRecord(m->ev_done[slot], st[slot]));
+		done_off[slot] = off;
+		done_n[slot] = cnt;
+	}
+	for (int s = 0; s < 2; s++) {
+		if (done_n[s]) {
+			CU(cudaEventSynchronize(m->ev_done[s]));
+			if (!out_pinned) memcpy(res + done_off[s], m->h_out[s], done_n[s] * 4);
+		}
+	}
+	return KMX_OK;
+}
+
+extern "C" int kmx_query_packed(kmx_model* m, const uint64_t* kmers, size_t n, int32_t* out) {
+	return query_host(m, kmers, 8, 8, n, out, nullptr, false);
+}
+
+extern "C" int kmx_query_path_packed(kmx_model* m, const uint64_t* kmers, size_t n, int32_t* path) {
+	return query_host(m, kmers, 8, 8, n, nullptr, path, false);
+}
+
+extern "C" int kmx_query_ascii(kmx_model* m, const char* flat, size_t stride, size_t n, int32_t* out) {
+	if (m && stride < (size_t)m->k) return fail(KMX_EARG, "stride %zu shorter than k=%d", stride, m->k);
+	return query_host(m, flat, stride, stride, n, out, nullptr, true);
+}
+
+// =========================================================================================
+// host-side known-answer entry points (no GPU needed)
+// =========================================================================================
+extern "C" uint64_t kmx_host_murmur64(const void* key, int len, uint32_t seed) {
+	// MurmurHash64A on raw bytes, via the same block/tail split the kernels use
+	const uint8_t* p = (const uint8_t*)key;
+	uint64_t h = (uint64_t)seed ^ ((uint64_t)len * kMurM);
+	const int nblocks = len / 8;
+	for (int b = 0; b < nblocks; b++) {
+		uint64_t w;
+		memcpy(&w, p + 8 * b, 8);
+		w *= kMurM; w ^= w >> 47; w *= kMurM;
+		h ^= w; h *= kMurM;
+	}
+	if (len & 7) {
+		uint64_t t = 0;
+		memcpy(&t, p + 8 * nblocks, len & 7);
+		h ^= t; h *= kMurM;
+	}
+	h ^= h >> 47; h *= kMurM; h ^= h >> 47;
+	return h;
+}
+
+extern "C" uint64_t kmx_host_hash_packed(uint64_t kmer, int len, uint32_t seed) {
+	if (len < 1 || len > 32) return 0;
+	HashPrep p;
+	hash_prepare(reverse_bases(kmer & mask2(len), len), len, p);
+	return hash_finish(p, len, seed);
+}
+
+extern "C" uint64_t kmx_host_canonical(uint64_t kmer, int k) {
+	uint64_t r;
+	return canonical(kmer & mask2(k), k, &r);
+}
+
+extern "C" uint32_t kmx_host_seed(int i) { return h_seeds[i & 127]; }
+
+extern "C" int kmx_host_occubin(int max_counter, int n_hash, int32_t* occ2bin, int32_t* bin2mean) {
+	std::vector<int32_t> a, b;
+	int rc = occubin_tables(max_counter, n_hash, a, b);
+	if (rc) return rc;
+	memcpy(occ2bin, a.data(), a.size() * 4);
+	memcpy(bin2mean, b.data(), b.size() * 4);
+	return KMX_OK;
+}
+
+extern "C" void kmx_host_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_kmers, int n_hash, uint64_t bytes[8]) {
+	model_sizes(kmer_counts, bf_num, km_kmers, n_hash, bytes);
+}
+
+extern "C" uint64_t kmx_host_fastmod(uint64_t h, uint64_t d) { return d ? fastmod(h, make_fastmod(d)) : 0; }
+
+// the closed form insert_kernel uses for reorder_buffer (kmodel.hpp:529-540)
+extern "C" int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm) {
+	int F = 0;
+	for (int i = 0; i < n; i++) F += failed[i] ? 1 : 0;
+	std::vector<int32_t> hole(F > 0 ? F : 1);
+	int excl = 0;
+	for (int i = 0; i < n; i++) {
+		if (failed[i]) {
+			if (i < F) perm[i] = i;
+			excl++;
+		} else if (i < F) {
+			hole[i - excl] = i;
+		}
+	}
+	excl = 0;
+	for (int i = 0; i < n; i++) {
+		if (failed[i]) {
+			if (i >= F) perm[hole[F - excl - 1]] = i;
+			excl++;
+		}
+	}
+	return F;
+}

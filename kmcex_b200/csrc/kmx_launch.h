@@ -1,0 +1,88 @@
+// kmx_launch.h -- host-callable launchers of the kernels in kmx_query.cu / kmx_build.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "kmx_device.cuh"
+
+namespace kmx {
+
+// ---- query (kmx_query.cu) ------------------------------------------------------------------
+cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
+                                int sm_count, cudaStream_t stream);
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, int sm_count,
+                               cudaStream_t stream);
+
+// ---- build (kmx_build.cu) ------------------------------------------------------------------
+constexpr int kTile = 2048;          // records decoded per block step (256 threads x 8)
+
+struct CountOut {                    // device-resident result of the counting pass
+	unsigned long long class_count[kMaxBf];   // kmer_counts[c - ci]          kmodel.hpp:423-434
+	unsigned long long listed;                // records passing the [min_count,max_count] filter
+	unsigned long long array_bound;           // listed records with count >= ci + bf_num
+	unsigned long long bad_count;             // listed records with count < ci or > cs (reference: out of bounds)
+};
+
+// pass 1: histogram of the low-count classes + array-bound records per tile
+cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, int sm_count,
+                         cudaStream_t stream);
+// exclusive scan of the per-tile counts into 64-bit offsets
+cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint64_t* d_tile_off, cudaStream_t stream);
+// pass 2: decode again; Bloom-bound k-mers are OR-ed into their filters, array-bound k-mers are
+// written (file order preserved) to the item stream
+cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, uint64_t* d_item_kmer,
+                          uint32_t* d_item_occ, int sm_count, cudaStream_t stream);
+// plain listing (kmx_db_list): every listed record, file order, compacted
+cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d_kmers, uint32_t* d_counts, int sm_count,
+                        cudaStream_t stream);
+cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream);
+
+// greedy coupled-array insert: persistent cooperative kernel over batches [first, first+count)
+struct InsertCtl {                    // lives in device memory, survives across launches
+	unsigned long long rest_n;        // survivors appended to the rest list so far
+	unsigned long long attempts, accepted, iterations;
+	unsigned int undecided[3];        // rotating per-iteration counters
+	unsigned int epoch;               // reservation epoch (keys of newer epochs are smaller)
+	unsigned int error;               // non-zero: iteration cap hit / rest overflow
+	unsigned int nfail[kMaxArrays];   // survivors of each bucket after the current round
+	unsigned long long rest_base[kMaxArrays];
+	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
+	unsigned int slot0_occ[kMaxArrays];
+	unsigned int slot0_valid[kMaxArrays];
+};
+
+struct InsertArgs {
+	const uint64_t* item_kmer;        // array-bound stream, file order
+	const uint32_t* item_occ;
+	unsigned long long n_items;
+	uint64_t* buf_kmer[2];            // [n_bits * kBucket] ping-pong survivor buffers
+	uint32_t* buf_occ[2];
+	uint32_t* status;                 // [n_bits * kBucket] state<<30 | reserve mask
+	uint32_t* rank;                   // [n_bits * kBucket]
+	uint32_t* holepos;                // [n_bits * kBucket]
+	uint32_t* tile_fail;              // [n_bits * kBucket / 256]
+	uint32_t* resv;                   // [n_bits][2 * resv_slots]
+	uint32_t resv_slots;              // power of two
+	uint64_t* rest_kmer;              // survivors of all batches
+	uint32_t* rest_occ;
+	unsigned long long rest_cap;
+	InsertCtl* ctl;
+	unsigned long long first_batch, n_batches;
+	unsigned int max_iterations;      // safety cap per round
+};
+
+cudaError_t insert_grid_size(int* blocks_out, int sm_count);
+cudaError_t launch_insert(const DevModel& m, const InsertArgs& a, int grid_blocks, cudaStream_t stream);
+
+// rest table: survivors -> sorted keys + group index (rest.hpp:95-135)
+cudaError_t rest_sort_bytes(size_t n, size_t* temp_bytes);
+cudaError_t launch_rest_sort(void* d_temp, size_t temp_bytes, const uint64_t* d_keys_in, uint64_t* d_keys_out,
+                             const uint32_t* d_vals_in, int32_t* d_vals_out, size_t n, int key_bits, cudaStream_t stream);
+cudaError_t launch_rest_index(const uint64_t* d_keys, uint64_t n, int suffix_bits, int map_size, int32_t* d_first,
+                              int32_t* d_hash2index, int32_t* d_pre_buffer, int32_t* d_groups, cudaStream_t stream);
+
+// (de)interleave of the coupled arrays between the on-disk and the device layout
+cudaError_t launch_split_cells(const unsigned long long* d_cells, uint64_t n_words, uint32_t* d_val, uint32_t* d_tag, cudaStream_t stream);
+cudaError_t launch_merge_cells(const uint32_t* d_val, const uint32_t* d_tag, uint64_t n_words, unsigned long long* d_cells, cudaStream_t stream);
+
+}  // namespace kmx

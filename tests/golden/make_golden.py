@@ -1,0 +1,74 @@
+"""Generate tests/golden/* from the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from
+/root/reference by oracle/Makefile).  Run in the authoring container only:
+
+    python tests/golden/make_golden.py
+
+Outputs: kat.txt (hash / canonical / OccuBin known answers printed by the reference's own
+functions) and models.json (digests of header / km.bin / rest.bin and of the kmer_to_occ output
+vector for every seeded case in cases.py, plus the digests of the generated database files)."""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def main() -> None:
+    if not os.path.exists(REF):
+        raise SystemExit("oracle/_ref/ref_driver missing: run `make -C oracle ref` (needs /root/reference)")
+    tmp = tempfile.mkdtemp(prefix="kmx_golden_")
+    # ---- known answers from the reference's own Tools / OccuBin ----
+    kat = os.path.join(tmp, "kat.txt")
+    subprocess.run([REF, "kat", kat], check=True)
+    keep = [ln for ln in open(kat) if not ln.startswith("occubin 65536 ")]
+    ob = [ln for ln in open(kat) if ln.startswith("occubin 65536 ")]
+    keep += ob[::97] + ob[-300:]                  # the 16-bit case is sampled to keep the fixture small
+    with open(os.path.join(HERE, "kat.txt"), "w") as f:
+        f.writelines(keep)
+    # ---- model builds + queries ----
+    out = {}
+    for name, p in cases.CASES.items():
+        base, sp = cases.make_case_db(name, tmp)
+        mdir = os.path.join(tmp, name + "_model")
+        os.makedirs(mdir, exist_ok=True)
+        r = subprocess.run([REF, "build", base, mdir, str(p["ci"]), str(cases.MODEL["cs"]), str(cases.MODEL["n_hash"]), str(cases.MODEL["n_bits"])],
+                           capture_output=True, text=True, check=True)
+        q = cases.case_queries(sp)
+        qf, of = os.path.join(tmp, name + "_q.bin"), os.path.join(tmp, name + "_occ.bin")
+        q.tofile(qf)
+        subprocess.run([REF, "query", mdir, qf, "31", of, "4"], capture_output=True, text=True, check=True)
+        occ = np.fromfile(of, dtype=np.int32)
+        lst = os.path.join(tmp, name + "_list.bin")
+        subprocess.run([REF, "list", base, lst], capture_output=True, text=True, check=True)
+        out[name] = {
+            "params": p, "model": cases.MODEL, "n_kmers": int(sp.kmers.size),
+            "db_md5": {"kmc_pre": cases.md5_file(base + ".kmc_pre"), "kmc_suf": cases.md5_file(base + ".kmc_suf")},
+            "listing_md5": cases.md5_file(lst),     # (u64 k-mer, u32 count) records in ReadNextKmer order
+            "model_md5": {f: cases.md5_file(os.path.join(mdir, f)) for f in ("header", "km.bin", "rest.bin")},
+            "model_bytes": {f: os.path.getsize(os.path.join(mdir, f)) for f in ("header", "km.bin", "rest.bin")},
+            "query_md5": hashlib.md5(q.tobytes()).hexdigest(),
+            "occ_md5": hashlib.md5(occ.tobytes()).hexdigest(),
+            "occ_nonzero": int((occ != 0).sum()), "occ_sum": int(occ.astype(np.int64).sum()),
+            "occ_head": occ[:64].tolist(),
+            "reference_stdout_tail": r.stdout.strip().splitlines()[-1],
+        }
+        print(name, out[name]["model_bytes"], out[name]["occ_nonzero"])
+    with open(os.path.join(HERE, "models.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

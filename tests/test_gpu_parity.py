@@ -1,0 +1,181 @@
+"""GPU suite: the CUDA path behind the C ABI (libkmx.so) against the golden digests taken from
+the unmodified reference and against the oracle, bit for bit: KMC listing, header / km.bin /
+rest.bin, kmer_to_occ outputs and the per-query path classes."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import kmcex_b200 as kx
+from kmcex_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built(case_dbs, tmp_path_factory):
+    """GPU-built and saved model per case (cached)"""
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            base, sp = case_dbs(name)
+            p = cases.CASES[name]
+            m = kx.get_model(p["ci"], cases.MODEL["cs"], cases.MODEL["n_hash"], cases.MODEL["n_bits"])
+            m.init(base)
+            out = str(tmp_path_factory.mktemp(name + "_gpu_model"))
+            m.save(out)
+            cache[name] = (m, out, sp, base)
+        return cache[name]
+    return get
+
+
+def test_extension_is_loaded_and_sees_a_b200():
+    lib = kx.lib()
+    assert lib.kmx_device_count() >= 1
+    loaded = open("/proc/self/maps").read()
+    assert "libkmx.so" in loaded
+
+
+@pytest.mark.parametrize("name", ["tiny_ci1", "small_ci2", "multi_ci1"])
+def test_gpu_listing_equals_reference_listing(name, case_dbs, golden, oracle):
+    base, sp = case_dbs(name)
+    db = kx.KmcDatabase(base)
+    kmers, counts = db.list()
+    db.close()
+    assert kmers.size == sp.kmers.size
+    rec = np.zeros(kmers.size, dtype=np.dtype([("k", "<u8"), ("c", "<u4")]))
+    rec["k"], rec["c"] = kmers, counts
+    assert hashlib.md5(rec.tobytes()).hexdigest() == golden[name]["listing_md5"]
+    ok = np.zeros(kmers.size, dtype=np.uint64)
+    oc = np.zeros(kmers.size, dtype=np.uint32)
+    assert oracle.kmxo_list(base.encode(), ok.ctypes.data, oc.ctypes.data, kmers.size, None, None) == kmers.size
+    assert (ok == kmers).all() and (oc == counts).all()
+
+
+@pytest.mark.parametrize("name", ["tiny_ci1", "small_ci2", "multi_ci1"])
+def test_gpu_build_is_byte_identical_to_the_reference(name, built, golden):
+    m, out, sp, base = built(name)
+    g = golden[name]
+    for f in ("header", "km.bin", "rest.bin"):
+        assert os.path.getsize(os.path.join(out, f)) == g["model_bytes"][f], f
+        assert cases.md5_file(os.path.join(out, f)) == g["model_md5"][f], f
+    i = m.info
+    assert i["total_kmers"] == sp.kmers.size and i["k"] == 31
+    assert i["insert_accepted"] + i["rest_kmers"] >= i["km_kmers"] - (1 << 4)     # every array k-mer lands somewhere
+    assert i["insert_attempts"] >= i["insert_accepted"] > 0
+
+
+@pytest.mark.parametrize("name", ["tiny_ci1", "small_ci2", "multi_ci1"])
+def test_gpu_query_equals_reference_outputs(name, built, golden, oracle):
+    m, out, sp, base = built(name)
+    g = golden[name]
+    q = cases.case_queries(sp)
+    assert hashlib.md5(q.tobytes()).hexdigest() == g["query_md5"]
+    occ = m.kmer_to_occ(q)
+    assert occ[:64].tolist() == g["occ_head"]
+    assert hashlib.md5(occ.tobytes()).hexdigest() == g["occ_md5"]
+    # a model LOADED from the files answers the same (get_model(dir), kmodel.hpp:680-696)
+    m2 = kx.get_model(out)
+    assert (m2.kmer_to_occ(q) == occ).all()
+    # ASCII entry point == packed entry point (the 2-bit encode happens on the device)
+    sub = q[:5000]
+    assert (m2.kmer_to_occ(synth.to_ascii(sub, 31)) == occ[:5000]).all()
+    strs = ["".join(map(chr, row)) for row in synth.to_ascii(sub[:50], 31)]
+    assert m2.kmer_to_occ(strs).tolist() == occ[:50].tolist()
+    assert m2.kmer_to_occ(strs[0]) == int(occ[0])
+    # path classes against the oracle's classification
+    h = oracle.kmxo_load(out.encode())
+    want = np.zeros(q.size, dtype=np.int32)
+    oracle.kmxo_query_path(h, q.ctypes.data, q.size, want.ctypes.data)
+    oracle.kmxo_free(h)
+    got = m2.query_path(q)
+    assert (got == want).all()
+    assert set(np.unique(got)) >= {1, 2, 3, 4}            # the fast paths are all exercised
+    m2.close()
+
+
+def test_every_present_kmer_and_all_its_neighbours(built, oracle):
+    """all present k-mers + the 8 neighbours of a sample (drives the disambiguation path, kmodel.hpp:286-359)"""
+    m, out, sp, base = built("small_ci2")
+    k = 31
+    mask = np.uint64((1 << 62) - 1)
+    sample = sp.kmers[:: max(1, sp.kmers.size // 20000)]
+    nb = [((sample << np.uint64(2)) & mask) | np.uint64(b) for b in range(4)]
+    nb += [(sample >> np.uint64(2)) | (np.uint64(b) << np.uint64(2 * (k - 1))) for b in range(4)]
+    q = np.concatenate([sp.kmers] + nb)
+    h = oracle.kmxo_load(out.encode())
+    want = np.zeros(q.size, dtype=np.int32)
+    oracle.kmxo_query_packed(h, q.ctypes.data, q.size, want.ctypes.data)
+    path = np.zeros(q.size, dtype=np.int32)
+    oracle.kmxo_query_path(h, q.ctypes.data, q.size, path.ctypes.data)
+    oracle.kmxo_free(h)
+    got = m.kmer_to_occ(q)
+    assert (got == want).all()
+    assert (path >= 5).sum() > 0          # neighbour vote / multi-candidate paths were taken
+
+
+def test_gpu_build_equals_oracle_on_a_fresh_seed(oracle, tmp_path):
+    """a database that is in no fixture: ci=2, 7-symbol LUT, 5 bins, random strand queries"""
+    base = str(tmp_path / "db")
+    sp = synth.synth_reads_spectrum(150_000, 35, 100, seed=1234, ci=2, device="cpu")
+    synth.write_kmc_db(base, sp.kmers, sp.counts, lut_prefix_length=7, n_bins=5, min_count=2)
+    ora = str(tmp_path / "ora")
+    gpu = str(tmp_path / "gpu")
+    os.makedirs(ora)
+    os.makedirs(gpu)
+    stats = np.zeros(3, dtype=np.int64)
+    assert oracle.kmxo_build(base.encode(), 2, 1023, 7, 5, ora.encode(), stats.ctypes.data) == 0
+    m = kx.get_model(2, 1023, 7, 5)
+    m.init_KModel(base)
+    m.save_model(gpu)
+    for f in ("header", "km.bin", "rest.bin"):
+        assert cases.md5_file(os.path.join(gpu, f)) == cases.md5_file(os.path.join(ora, f)), f
+    i = m.info
+    assert i["insert_attempts"] == stats[0] and i["insert_accepted"] == stats[1] and i["rest_kmers"] == stats[2]
+
+
+def test_other_geometries_equal_the_oracle(oracle, tmp_path):
+    """n_hash / n_bits other than 7 / 5 take the generic kernels"""
+    base = str(tmp_path / "db")
+    sp = synth.synth_reads_spectrum(40_000, 30, 100, seed=77, ci=1, device="cpu")
+    synth.write_kmc_db(base, sp.kmers, sp.counts, lut_prefix_length=3, n_bins=2, min_count=1)
+    q = synth.neighbour_rich_queries(sp, 5000, 5000, seed=3)
+    for nh, nb in ((6, 4), (8, 3), (7, 1)):
+        ora = str(tmp_path / f"ora_{nh}_{nb}")
+        gpu = str(tmp_path / f"gpu_{nh}_{nb}")
+        os.makedirs(ora)
+        os.makedirs(gpu)
+        stats = np.zeros(3, dtype=np.int64)
+        assert oracle.kmxo_build(base.encode(), 1, 1023, nh, nb, ora.encode(), stats.ctypes.data) == 0
+        m = kx.get_model(1, 1023, nh, nb)
+        m.init(base)
+        m.save(gpu)
+        for f in ("header", "km.bin", "rest.bin"):
+            assert cases.md5_file(os.path.join(gpu, f)) == cases.md5_file(os.path.join(ora, f)), (nh, nb, f)
+        h = oracle.kmxo_load(ora.encode())
+        want = np.zeros(q.size, dtype=np.int32)
+        oracle.kmxo_query_packed(h, q.ctypes.data, q.size, want.ctypes.data)
+        oracle.kmxo_free(h)
+        assert (m.kmer_to_occ(q) == want).all(), (nh, nb)
+        m.close()
+
+
+def test_reference_error_corners_are_reported_not_computed(tmp_path):
+    # fewer than 8 k-mers in a Bloom class: the reference aborts in new uint8_t[0]{0} (kmodel.hpp:413-417)
+    base = str(tmp_path / "db")
+    kmers = np.arange(1000, 1100, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) & np.uint64((1 << 62) - 1)
+    kmers = np.unique(kmers)
+    counts = np.full(kmers.size, 50, dtype=np.uint32)
+    counts[:3] = 1
+    synth.write_kmc_db(base, kmers, counts, lut_prefix_length=3, min_count=1)
+    m = kx.get_model(1, 1023, 7, 5)
+    with pytest.raises(kx.KmxError) as e:
+        m.init(base)
+    assert e.value.code == 6
+    with pytest.raises(kx.KmxError):
+        m.save(str(tmp_path))             # not initialised

@@ -1,0 +1,179 @@
+"""CPU suite, part 1: the C ABI loads and exports what include/kmx.h declares; the host-side
+arithmetic of the path (hash, canonical form, OccuBin, size formulas, exact modulo, survivor
+permutation) agrees with the reference's known answers (tests/golden/kat.txt, printed by the
+reference's own functions) and with the oracle."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import kmcex_b200 as kx
+from kmcex_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    text = open(os.path.join(ROOT, "include", "kmx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(kmx_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 25
+    lib = kx.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libkmx.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and kmx.h disagree"
+
+
+def test_no_torch_types_in_the_abi():
+    text = open(os.path.join(ROOT, "include", "kmx.h")).read()
+    assert "torch" not in text and "at::" not in text and "std::" not in text
+
+
+def test_murmur_and_canonical_known_answers(kat_lines, oracle):
+    lib = kx.lib()
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    n_m = n_c = 0
+    for parts in kat_lines:
+        if parts[0] == "murmur":
+            s, seed, want = parts[1], int(parts[2]), int(parts[3])
+            assert lib.kmx_host_murmur64(s.encode(), len(s), seed) == want
+            assert oracle.kmxo_murmur64(s.encode(), len(s), seed) == want
+            v = 0
+            for ch in s:
+                v = (v << 2) | code[ch]
+            assert lib.kmx_host_hash_packed(v, len(s), seed) == want      # the kernels' block/tail split
+            n_m += 1
+        elif parts[0] == "minkmer":
+            s, want = parts[1], parts[2]
+            v = w = 0
+            for ch in s:
+                v = (v << 2) | code[ch]
+            for ch in want:
+                w = (w << 2) | code[ch]
+            assert lib.kmx_host_canonical(v, len(s)) == w
+            assert oracle.kmxo_canonical(v, len(s)) == w
+            n_c += 1
+    assert n_m >= 500 and n_c >= 100
+    # the survey's probe values
+    assert lib.kmx_host_murmur64(b"ACGTACGTACGTACGTACGTACGTACGTACG", 31, 46757) == 13042456722222963169
+    assert lib.kmx_host_murmur64(b"ACGTACGTACGTACGTACGTACGTACGTACG", 31, 46769) == 17098917893835065645
+    assert lib.kmx_host_murmur64(b"CGTACGTACGTACGTACGTACGTACGTAC", 29, 46757) == 2953946542005570904
+
+
+def test_seed_table(oracle):
+    lib = kx.lib()
+    seeds = [lib.kmx_host_seed(i) for i in range(128)]
+    assert seeds[0] == 46757 and seeds[1] == 46769 and seeds[127] == 48163
+    assert seeds == [oracle.kmxo_seed(i) for i in range(128)]
+
+
+def test_occubin_known_answers(kat_lines, oracle):
+    lib = kx.lib()
+    tables = {}
+    for parts in kat_lines:
+        if parts[0] != "occubin":
+            continue
+        mc, nh, occ, b, mean = map(int, parts[1:])
+        if (mc, nh) not in tables:
+            o2b = np.zeros(mc, dtype=np.int32)
+            b2m = np.zeros(1 << nh, dtype=np.int32)
+            assert lib.kmx_host_occubin(mc, nh, o2b.ctypes.data, b2m.ctypes.data) == 0
+            o2b_o = np.zeros(mc, dtype=np.int32)
+            b2m_o = np.zeros(1 << nh, dtype=np.int32)
+            assert oracle.kmxo_occubin(mc, nh, o2b_o.ctypes.data, b2m_o.ctypes.data) == 0
+            assert (o2b == o2b_o).all() and (b2m == b2m_o).all()
+            tables[(mc, nh)] = (o2b, b2m)
+        o2b, b2m = tables[(mc, nh)]
+        assert o2b[occ] == b
+        assert (b if b < (1 << nh) // 4 else b2m[b]) == mean
+    assert set(tables) == {(1024, 7), (256, 7), (1024, 6), (65536, 8)}
+    # occu_bin.hpp:38-44 writes out of bounds when max_counter < 2^(H-2) + 3 * 2^(H-1): refused
+    tmp = np.zeros(4096, dtype=np.int32)
+    assert lib.kmx_host_occubin(200, 7, tmp.ctypes.data, tmp.ctypes.data) != 0
+
+
+def test_size_formulas():
+    lib = kx.lib()
+    rng = random.Random(5)
+    for _ in range(2000):
+        counts = [rng.randrange(0, 1 << rng.randrange(1, 40)) for _ in range(3)]
+        km = rng.randrange(0, 1 << rng.randrange(1, 40))
+        nh = rng.randrange(3, 12)
+        bf_num = rng.choice([1, 3])
+        arr = (C.c_uint64 * 3)(*counts)
+        out = (C.c_uint64 * 8)()
+        lib.kmx_host_sizes(arr, bf_num, km, nh, out)
+        for i in range(bf_num):
+            assert out[i] == int(counts[i] / 5.5 * (nh - 1))           # kmodel.hpp:411, double arithmetic
+            assert out[3 + i] == (counts[i] >> 3) * (nh - 2)            # kmodel.hpp:415
+        assert out[6] == (km >> 4) * nh and out[7] == (km >> 4) * (nh - 2)   # kmodel.hpp:437-439
+
+
+def test_fastmod_is_exact():
+    lib = kx.lib()
+    rng = random.Random(11)
+    ds = [1, 2, 3, 7, 8, 63, 64, 65, (1 << 32) - 1, 1 << 32, (1 << 32) + 1, (1 << 61) - 1, 1 << 61, 8400000000, 2863311531]
+    ds += [rng.randrange(1, 1 << rng.randrange(1, 62)) for _ in range(300)]
+    hs = [0, 1, (1 << 64) - 1, (1 << 63), (1 << 63) - 1] + [rng.randrange(0, 1 << 64) for _ in range(200)]
+    for d in ds:
+        for h in hs + [d - 1, d, d + 1, 2 * d, 3 * d - 1, ((1 << 64) - 1) // d * d, ((1 << 64) - 1) // d * d - 1]:
+            h &= (1 << 64) - 1
+            assert lib.kmx_host_fastmod(h, d) == h % d, (h, d)
+
+
+def test_reorder_closed_form_equals_two_pointer_loop(oracle):
+    lib = kx.lib()
+    rng = np.random.default_rng(3)
+    for trial in range(3000):
+        n = int(rng.integers(0, 70)) if trial < 2500 else int(rng.integers(1000, 5000))
+        p = rng.choice([0.0, 0.1, 0.5, 0.9, 1.0])
+        failed = (rng.random(n) < p).astype(np.uint8)
+        a = np.full(n + 1, -1, dtype=np.int32)
+        b = np.full(n + 1, -1, dtype=np.int32)
+        fa = np.ascontiguousarray(failed) if n else np.zeros(1, np.uint8)
+        ra = lib.kmx_host_reorder(fa.ctypes.data, n, a.ctypes.data)
+        rb = oracle.kmxo_reorder(fa.ctypes.data, n, b.ctypes.data)
+        assert ra == int(failed.sum())
+        if n > 0:
+            assert ra == rb
+            assert (a[:ra] == b[:rb]).all()
+
+
+def test_python_api_mirrors_the_reference_names():
+    for name in ("init", "init_KModel", "save", "save_model", "kmer_to_occ", "show_header_info", "show_kmodel_info"):
+        assert hasattr(kx.KModel, name)
+    m = kx.get_model(2, 1023, 7, 5)
+    i = m.info
+    assert (i["ci"], i["cs"], i["n_hash"], i["n_bits"], i["bf_num"]) == (2, 1023, 7, 5, 3)    # kmodel.hpp:50
+    assert kx.get_model(1).info["bf_num"] == 1
+    with pytest.raises(kx.KmxError):
+        kx.get_model(1, 100, 7, 5)        # OccuBin out of bounds in the reference
+    with pytest.raises(kx.KmxError):
+        kx.get_model("/nonexistent/model/dir")
+
+
+def test_kmc_header_parse_without_gpu(case_dbs, golden):
+    base, sp = case_dbs("tiny_ci1")
+    db = kx.KmcDatabase(base)
+    i = db.info
+    assert i["k"] == 31 and i["lut_prefix_length"] == 3 and i["counter_size"] == 2 and i["kmc_version"] == 0x200
+    assert i["total_kmers"] == sp.kmers.size == golden["tiny_ci1"]["n_kmers"]
+    assert i["record_bytes"] == 9 and i["suffix_bytes"] == 9 * sp.kmers.size and i["lut_entries"] == 64
+    db.close()
+    with pytest.raises(kx.KmxError):
+        kx.KmcDatabase("/nonexistent/db")
+
+
+def test_compute_entry_points_fail_loudly_without_gpu(case_dbs):
+    if kx.lib().kmx_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    base, _ = case_dbs("tiny_ci1")
+    m = kx.get_model(1, 1023, 7, 5)
+    with pytest.raises(kx.KmxError) as e:
+        m.init(base)
+    assert e.value.code == 4          # KMX_ENOGPU: no CPU fallback
+    with pytest.raises(kx.KmxError):
+        m.kmer_to_occ("ACGTACGTACGTACGTACGTACGTACGTACG")
