@@ -264,12 +264,13 @@ def main() -> None:
     q_dev = q_host.to(dev)
     out_dev = torch.empty(per, dtype=torch.int32, device=dev)
     out_host = torch.empty(per, dtype=torch.int32).pin_memory()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)                    # a real (non-NULL) stream: the kernel and the events share it
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     q_ms = []
     for step in range(args.warmup + args.steps):
         flush.fill_(step & 0xFF)
         barrier()
+        stream.wait_stream(torch.cuda.current_stream())
         ev[0].record(stream)
         m.query_device(q_dev.data_ptr(), per, out_dev.data_ptr(), stream.cuda_stream)
         ev[1].record(stream)

@@ -339,9 +339,10 @@ static int model_attach_device(kmx_model* m) {
 	std::vector<uint16_t> o16(m->occ2bin.size());
 	for (size_t i = 0; i < o16.size(); i++) o16[i] = (uint16_t)m->occ2bin[i];
 	CU(cudaMalloc(&m->d_occ2bin, o16.size() * 2));
-	CU(cudaMemcpy(m->d_occ2bin, o16.data(), o16.size() * 2, cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&m->d_bin2mean, m->bin2mean.size() * 4));
-	CU(cudaMemcpy(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice));
+	CU(cudaMemcpyAsync(m->d_occ2bin, o16.data(), o16.size() * 2, cudaMemcpyHostToDevice, m->stream));
+	CU(cudaMemcpyAsync(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice, m->stream));
+	CU(cudaStreamSynchronize(m->stream));
 	return KMX_OK;
 }
 
@@ -871,13 +872,22 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 	return KMX_OK;
 }
 
-static int read_to_device(FILE* f, void* d_ptr, uint64_t bytes, std::vector<uint8_t>& tmp) {
+// host -> device on `stream`, complete on return.  (A plain cudaMemcpy from pageable memory may
+// return while the DMA is still in flight, and the model's streams are non-blocking: kernels
+// launched on them would not wait for it.)
+static int h2d_sync(void* d_ptr, const void* h_ptr, size_t bytes, cudaStream_t stream) {
+	if (bytes == 0) return KMX_OK;
+	CU(cudaMemcpyAsync(d_ptr, h_ptr, bytes, cudaMemcpyHostToDevice, stream));
+	CU(cudaStreamSynchronize(stream));
+	return KMX_OK;
+}
+
+static int read_to_device(FILE* f, void* d_ptr, uint64_t bytes, std::vector<uint8_t>& tmp, cudaStream_t stream) {
 	const size_t padded = (size_t)((bytes + 7) & ~7ULL);
 	if (tmp.size() < padded) tmp.resize(padded);
 	if (bytes && fread(tmp.data(), 1, bytes, f) != bytes) return fail(KMX_EFORMAT, "km.bin is shorter than its header implies");
 	memset(tmp.data() + bytes, 0, padded - bytes);
-	CU(cudaMemcpy(d_ptr, tmp.data(), padded, cudaMemcpyHostToDevice));
-	return KMX_OK;
+	return h2d_sync(d_ptr, tmp.data(), padded, stream);
 }
 
 static int load_into(kmx_model* m, const std::string& base) {
@@ -896,18 +906,18 @@ static int load_into(kmx_model* m, const std::string& base) {
 	if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(KMX_ECUDA, "zero-fill of the filters failed");   // the copies below run on the default stream
 	std::vector<uint8_t> tmp;
 	for (int i = 0; i < m->bf_num && !rc; i++) {
-		rc = read_to_device(f, m->d_bf[i], m->bytes[i], tmp);
-		if (!rc) rc = read_to_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp);
+		rc = read_to_device(f, m->d_bf[i], m->bytes[i], tmp, m->stream);
+		if (!rc) rc = read_to_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp, m->stream);
 	}
-	if (!rc) rc = read_to_device(f, m->d_km_back, m->bytes[7], tmp);
+	if (!rc) rc = read_to_device(f, m->d_km_back, m->bytes[7], tmp, m->stream);
 	const uint64_t words = cell_words(m->bytes[6]);
 	uint32_t* d_val = nullptr;
 	uint32_t* d_tag = nullptr;
 	if (!rc && (cudaMalloc(&d_val, (words + 2) * 4) != cudaSuccess || cudaMalloc(&d_tag, (words + 2) * 4) != cudaSuccess))
 		rc = fail(KMX_ECUDA, "out of device memory while loading");
 	for (int i = 0; i < m->n_bits && !rc; i++) {
-		rc = read_to_device(f, d_val, m->bytes[6], tmp);
-		if (!rc) rc = read_to_device(f, d_tag, m->bytes[6], tmp);
+		rc = read_to_device(f, d_val, m->bytes[6], tmp, m->stream);
+		if (!rc) rc = read_to_device(f, d_tag, m->bytes[6], tmp, m->stream);
 		if (!rc) {
 			cudaError_t e = launch_merge_cells(d_val, d_tag, words, m->d_cells[i], m->stream);
 			if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
@@ -959,12 +969,10 @@ static int load_into(kmx_model* m, const std::string& base) {
 	CU(cudaMalloc(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4));
 	CU(cudaMalloc(&m->d_rest_keys, (r.count + 1) * 8));
 	CU(cudaMalloc(&m->d_rest_counts, (r.count + 1) * 4));
-	CU(cudaMemcpy(m->d_hash2index, h2i.data(), h2i.size() * 4, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(m->d_pre_buffer, pre.data(), pre.size() * 4, cudaMemcpyHostToDevice));
-	if (r.count) {
-		CU(cudaMemcpy(m->d_rest_keys, keys.data(), r.count * 8, cudaMemcpyHostToDevice));
-		CU(cudaMemcpy(m->d_rest_counts, counts.data(), r.count * 4, cudaMemcpyHostToDevice));
-	}
+	if ((rc = h2d_sync(m->d_hash2index, h2i.data(), h2i.size() * 4, m->stream))) return rc;
+	if ((rc = h2d_sync(m->d_pre_buffer, pre.data(), pre.size() * 4, m->stream))) return rc;
+	if ((rc = h2d_sync(m->d_rest_keys, keys.data(), r.count * 8, m->stream))) return rc;
+	if ((rc = h2d_sync(m->d_rest_counts, counts.data(), r.count * 4, m->stream))) return rc;
 	fill_dev_model(m);
 	fill_info(m);
 	m->built = true;
