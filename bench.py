@@ -317,7 +317,7 @@ def main() -> None:
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline,
         "clocks": clocks,
-        "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers")},
+        "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers", "insert_phase_cycles")},
     }
 
     # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------

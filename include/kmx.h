@@ -56,6 +56,8 @@ typedef struct kmx_info_t {
 	uint64_t insert_accepted;
 	uint64_t insert_iterations;  /* reservation iterations summed over all rounds            */
 	uint64_t batches;
+	uint64_t insert_phase_cycles[8];  /* SM cycles per phase of the insert kernel (diagnostic): reserve/commit of
+	                                      the first iteration, of later iterations, tile scan, place, move */
 	/* device times of the last build, milliseconds (CUDA events on the build stream) */
 	float ms_upload, ms_count, ms_encode, ms_insert, ms_rest, ms_total_device;
 	double build_time_cost;      /* host wall seconds of init, as the reference reports it   */

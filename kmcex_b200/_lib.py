@@ -16,6 +16,7 @@ class KmxInfo(C.Structure):
         ("kmer_counts", C.c_uint64 * 3),
         ("bf_bytes", C.c_uint64), ("km_bytes", C.c_uint64), ("km_back_bytes", C.c_uint64), ("rest_bytes", C.c_uint64),
         ("insert_attempts", C.c_uint64), ("insert_accepted", C.c_uint64), ("insert_iterations", C.c_uint64), ("batches", C.c_uint64),
+        ("insert_phase_cycles", C.c_uint64 * 8),
         ("ms_upload", C.c_float), ("ms_count", C.c_float), ("ms_encode", C.c_float), ("ms_insert", C.c_float), ("ms_rest", C.c_float),
         ("ms_total_device", C.c_float),
         ("build_time_cost", C.c_double),

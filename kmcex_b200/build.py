@@ -13,7 +13,7 @@ CSRC = os.path.join(ROOT, "kmcex_b200", "csrc")
 LIB = os.path.join(ROOT, "kmcex_b200", "libkmx.so")
 SOURCES = ["kmx_host.cu", "kmx_build.cu", "kmx_query.cu"]
 HEADERS = ["kmx_core.cuh", "kmx_device.cuh", "kmx_launch.h", os.path.join(ROOT, "include", "kmx.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["--threads", "4", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "-shared", "-cudart", "static"]
 
 

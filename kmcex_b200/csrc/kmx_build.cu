@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 
 			// ---------------- reservation iterations ----------------
 			uint32_t iter = 0;
+			long long tick = clock64();
 			while (true) {
 				const uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
 				// (a)+(b): check against the committed state, reserve
@@ -435,6 +436,11 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 					}
 				}
 				grid.sync();
+				if (tid == 0) {
+					long long now = clock64();
+					vctl->phase_cycles[iter == 0 ? 0 : 2] += (unsigned long long)(now - tick);
+					tick = now;
+				}
 				// (c): accept the items nobody smaller contests
 				uint32_t undecided = 0;
 				for (uint32_t id = tid; id < total_ids; id += T) {
@@ -488,6 +494,11 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 					if (blockIdx.x == 0) vctl->undecided[(itc + 1) % 3] = 0;
 				}
 				grid.sync();
+				if (tid == 0) {
+					long long now = clock64();
+					vctl->phase_cycles[iter == 0 ? 1 : 3] += (unsigned long long)(now - tick);
+					tick = now;
+				}
 				const uint32_t und = vctl->undecided[itc % 3];
 				itc++;
 				iter++;
@@ -534,6 +545,11 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 				}
 			}
 			grid.sync();
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[4] += (unsigned long long)(now - tick);
+				tick = now;
+			}
 			uint32_t n_next[BM];
 			unsigned long long rest_base[BM];
 #pragma unroll
@@ -583,6 +599,11 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 				}
 			}
 			grid.sync();
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[5] += (unsigned long long)(now - tick);
+				tick = now;
+			}
 			for (uint32_t id = tid; id < total_ids; id += T) {
 				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
 				const uint32_t F = n_next[i];
@@ -616,6 +637,7 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 				vctl->iterations += iter;
 			}
 			grid.sync();
+			if (tid == 0) vctl->phase_cycles[6] += (unsigned long long)(clock64() - tick);
 #pragma unroll
 			for (int i = 0; i < BM; i++) n_cur[i] = n_next[i];
 		}

@@ -8,6 +8,8 @@
 //   kmc_file.cpp:66-99,132-171,177-235  OpenForListing / header + LUT parse
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,7 +17,9 @@
 #include <sys/stat.h>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "../../include/kmx.h"
 #include "kmx_device.cuh"
@@ -41,6 +45,34 @@ static int fail(int code, const char* fmt, ...) {
 	do {                                                                                                 \
 		cudaError_t e__ = (call);                                                                        \
 		if (e__ != cudaSuccess) return fail(KMX_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+// Stream-ordered allocations from the device's default memory pool, which is told to keep
+// freed blocks: a rebuild (or the next query staging) reuses them instead of paying
+// cudaMalloc/cudaFree (hundreds of microseconds each, and cudaFree synchronises the device).
+static int dev_alloc_impl(void** p, size_t bytes, cudaStream_t s) {
+	static bool pool_ready[64] = { false };
+	int dev = 0;
+	CU(cudaGetDevice(&dev));
+	if (dev < 64 && !pool_ready[dev]) {
+		cudaMemPool_t pool;
+		CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+		uint64_t keep = ~0ULL;
+		CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+		pool_ready[dev] = true;
+	}
+	CU(cudaMallocAsync(p, bytes ? bytes : 8, s));
+	return KMX_OK;
+}
+template <class T>
+static int dev_alloc(T** p, size_t bytes, cudaStream_t s) { return dev_alloc_impl((void**)p, bytes, s); }
+static void dev_free(void* p, cudaStream_t s) {
+	if (p) cudaFreeAsync(p, s);
+}
+#define DA(ptr, bytes, stream)                                   \
+	do {                                                         \
+		int rc__ = dev_alloc(ptr, bytes, stream);                \
+		if (rc__) return rc__;                                   \
 	} while (0)
 
 static int require_gpu(int* sm_count) {
@@ -127,12 +159,11 @@ static int rest_prefix_len(int k) {              // rest.hpp:78-83
 struct kmx_db {
 	kmx_db_info_t info;
 	std::vector<uint64_t> lut;        // lut_entries + 1 (guard = total + 1, kmc_file.cpp:223)
-	uint8_t* h_suf = nullptr;         // pinned, record bytes, padded
+	int fd = -1;                      // .kmc_suf, kept open until the records are on the device
 	size_t suf_alloc = 0;
 	uint8_t* d_suf = nullptr;
 	uint64_t* d_lut = nullptr;
 	int device = 0, sm_count = 0;
-	bool pinned = false;
 	float ms_upload = 0;
 	cudaStream_t stream = nullptr;
 };
@@ -164,6 +195,12 @@ struct kmx_model {
 	DevModel dm;
 	kmx_info_t info;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
+	cudaEvent_t ev_build[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
+		CountOut count;
+		InsertCtl ctl;
+		int32_t groups;
+	}* h_pinned = nullptr;
 	// pinned staging for host-pointer queries (two slots)
 	void* h_in[2] = { nullptr, nullptr };
 	int32_t* h_out[2] = { nullptr, nullptr };
@@ -177,21 +214,22 @@ static size_t pad8(uint64_t bytes) { return (size_t)((bytes + 7) & ~7ULL) + 8; }
 static uint64_t cell_words(uint64_t km_byte_size) { return (km_byte_size + 3) / 4; }
 
 static void free_model_device(kmx_model* m) {
+	cudaStream_t s = m->stream;
 	for (int i = 0; i < 3; i++) {
-		cudaFree(m->d_bf[i]);
-		cudaFree(m->d_bf_back[i]);
+		dev_free(m->d_bf[i], s);
+		dev_free(m->d_bf_back[i], s);
 		m->d_bf[i] = m->d_bf_back[i] = nullptr;
 	}
-	cudaFree(m->d_km_back);
+	dev_free(m->d_km_back, s);
 	m->d_km_back = nullptr;
 	for (int i = 0; i < kMaxArrays; i++) {
-		cudaFree(m->d_cells[i]);
+		dev_free(m->d_cells[i], s);
 		m->d_cells[i] = nullptr;
 	}
-	cudaFree(m->d_hash2index);
-	cudaFree(m->d_pre_buffer);
-	cudaFree(m->d_rest_keys);
-	cudaFree(m->d_rest_counts);
+	dev_free(m->d_hash2index, s);
+	dev_free(m->d_pre_buffer, s);
+	dev_free(m->d_rest_keys, s);
+	dev_free(m->d_rest_counts, s);
 	m->d_hash2index = m->d_pre_buffer = nullptr;
 	m->d_rest_keys = nullptr;
 	m->d_rest_counts = nullptr;
@@ -209,16 +247,16 @@ static int alloc_filters(kmx_model* m) {
 		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays: the reference aborts on zero-length arrays (kmodel.hpp:443-447)",
 		            (unsigned long long)m->km_kmers);
 	for (int i = 0; i < m->bf_num; i++) {
-		CU(cudaMalloc(&m->d_bf[i], pad8(m->bytes[i])));
+		DA(&m->d_bf[i], pad8(m->bytes[i]), m->stream);
 		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->stream));
-		CU(cudaMalloc(&m->d_bf_back[i], pad8(m->bytes[3 + i])));
+		DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->stream);
 		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->stream));
 	}
-	CU(cudaMalloc(&m->d_km_back, pad8(m->bytes[7])));
+	DA(&m->d_km_back, pad8(m->bytes[7]), m->stream);
 	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->stream));
 	const uint64_t words = cell_words(m->bytes[6]);
 	for (int i = 0; i < m->n_bits; i++) {
-		CU(cudaMalloc(&m->d_cells[i], (words + 1) * 8));
+		DA(&m->d_cells[i], (words + 1) * 8, m->stream);
 		CU(cudaMemsetAsync(m->d_cells[i], 0, (words + 1) * 8, m->stream));
 	}
 	return KMX_OK;
@@ -338,8 +376,10 @@ static int model_attach_device(kmx_model* m) {
 	CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
 	std::vector<uint16_t> o16(m->occ2bin.size());
 	for (size_t i = 0; i < o16.size(); i++) o16[i] = (uint16_t)m->occ2bin[i];
-	CU(cudaMalloc(&m->d_occ2bin, o16.size() * 2));
-	CU(cudaMalloc(&m->d_bin2mean, m->bin2mean.size() * 4));
+	for (auto& e : m->ev_build) CU(cudaEventCreate(&e));
+	CU(cudaHostAlloc((void**)&m->h_pinned, sizeof(kmx_model::Pinned), cudaHostAllocDefault));
+	DA(&m->d_occ2bin, o16.size() * 2, m->stream);
+	DA(&m->d_bin2mean, m->bin2mean.size() * 4, m->stream);
 	CU(cudaMemcpyAsync(m->d_occ2bin, o16.data(), o16.size() * 2, cudaMemcpyHostToDevice, m->stream));
 	CU(cudaMemcpyAsync(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice, m->stream));
 	CU(cudaStreamSynchronize(m->stream));
@@ -353,15 +393,19 @@ extern "C" void kmx_destroy(kmx_model* m) {
 		cudaStreamSynchronize(m->stream);
 		cudaStreamSynchronize(m->stream2);
 		free_model_device(m);
-		cudaFree(m->d_occ2bin);
-		cudaFree(m->d_bin2mean);
+		dev_free(m->d_occ2bin, m->stream);
+		dev_free(m->d_bin2mean, m->stream);
 		for (int s = 0; s < 2; s++) {
 			cudaFreeHost(m->h_in[s]);
 			cudaFreeHost(m->h_out[s]);
-			cudaFree(m->d_in[s]);
-			cudaFree(m->d_out[s]);
+			dev_free(m->d_in[s], m->stream);
+			dev_free(m->d_out[s], m->stream);
 			if (m->ev_done[s]) cudaEventDestroy(m->ev_done[s]);
 		}
+		for (auto& e : m->ev_build)
+			if (e) cudaEventDestroy(e);
+		cudaFreeHost(m->h_pinned);
+		cudaStreamSynchronize(m->stream);
 		cudaStreamDestroy(m->stream);
 		cudaStreamDestroy(m->stream2);
 	}
@@ -383,6 +427,9 @@ extern "C" int kmx_model_sync(kmx_model* m) {
 // =========================================================================================
 static bool read_exact(FILE* f, void* dst, size_t n) { return n == 0 || fread(dst, 1, n, f) == n; }
 
+// kmc_file.cpp:66-99,132-171,177-235: both files carry a 4-byte marker at either end; the header
+// sits at the end of .kmc_pre.  Only the header and the LUT are read here; the record area of
+// .kmc_suf goes straight to the device in kmx_db_upload.
 extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	if (!db_base) {
 		fail(KMX_EARG, "null database name");
@@ -400,7 +447,7 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	rewind(fp);
 	bool ok = pre_size >= 32 && read_exact(fp, pre.data(), pre_size);
 	fclose(fp);
-	if (!ok || memcmp(pre.data(), "KMCP", 4) != 0 || memcmp(pre.data() + pre_size - 4, "KMCP", 4) != 0) {   // kmc_file.cpp:132-171
+	if (!ok || memcmp(pre.data(), "KMCP", 4) != 0 || memcmp(pre.data() + pre_size - 4, "KMCP", 4) != 0) {
 		fail(KMX_EFORMAT, "%s is not a KMC prefix file", pre_name.c_str());
 		return nullptr;
 	}
@@ -429,7 +476,7 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	memcpy(&h.max_count, p + 24, 4);
 	memcpy(&h.total_kmers, p + 28, 8);
 	const uint64_t body = pre_size - 12;                  // two markers and the header_offset word removed
-	const uint64_t sig_bytes = ((1ULL << (2 * h.signature_len)) + 1) * 4;
+	const uint64_t sig_bytes = ((1ULL << (2 * (h.signature_len & 31))) + 1) * 4;
 	if (h.signature_len > 11 || sig_bytes + header_offset + 8 > body) {
 		fail(KMX_EFORMAT, "%s: signature map does not fit the file", pre_name.c_str());
 		delete db;
@@ -455,46 +502,24 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	h.record_bytes = (h.k - h.lut_prefix_length) / 4 + h.counter_size;   // kmc_file.cpp:230-232
 	h.suffix_bytes = (uint64_t)h.record_bytes * h.total_kmers;
 
-	FILE* fs = fopen(suf_name.c_str(), "rb");
-	if (!fs) {
+	int fd = open(suf_name.c_str(), O_RDONLY);
+	if (fd < 0) {
 		fail(KMX_EIO, "can't open the kmer_data_base %s (%s)", db_base, strerror(errno));
 		delete db;
 		return nullptr;
 	}
-	fseeko(fs, 0, SEEK_END);
-	const uint64_t suf_size = (uint64_t)ftello(fs);
-	char marker[4];
-	rewind(fs);
-	ok = suf_size >= 8 && read_exact(fs, marker, 4) && memcmp(marker, "KMCS", 4) == 0 && suf_size - 8 >= h.suffix_bytes;
+	struct stat st;
+	char m0[4] = { 0 }, m1[4] = { 0 };
+	ok = fstat(fd, &st) == 0 && st.st_size >= 8 && pread(fd, m0, 4, 0) == 4 && pread(fd, m1, 4, st.st_size - 4) == 4 &&
+	     memcmp(m0, "KMCS", 4) == 0 && memcmp(m1, "KMCS", 4) == 0 && (uint64_t)st.st_size - 8 >= h.suffix_bytes;
 	if (!ok) {
-		fclose(fs);
+		close(fd);
 		fail(KMX_EFORMAT, "%s is not a KMC suffix file holding %llu records", suf_name.c_str(), (unsigned long long)h.total_kmers);
 		delete db;
 		return nullptr;
 	}
+	db->fd = fd;
 	db->suf_alloc = (size_t)((h.suffix_bytes + 15) & ~15ULL) + 16;
-	// pinned when a device is present (fast upload); plain memory otherwise so that header-only
-	// inspection works without a GPU
-	int n_dev = kmx_device_count();
-	if (n_dev > 0) {
-		cudaSetDevice(g_device);
-		if (cudaMallocHost(&db->h_suf, db->suf_alloc) != cudaSuccess) {
-			cudaGetLastError();
-			db->h_suf = nullptr;
-		}
-	}
-	bool pinned = db->h_suf != nullptr;
-	if (!pinned) db->h_suf = (uint8_t*)malloc(db->suf_alloc);
-	ok = db->h_suf && read_exact(fs, db->h_suf, h.suffix_bytes);
-	fclose(fs);
-	if (!ok) {
-		fail(KMX_EIO, "short read on %s", suf_name.c_str());
-		if (pinned) cudaFreeHost(db->h_suf); else free(db->h_suf);
-		delete db;
-		return nullptr;
-	}
-	memset(db->h_suf + h.suffix_bytes, 0, db->suf_alloc - h.suffix_bytes);
-	db->pinned = pinned;
 	db->device = g_device;
 	return db;
 }
@@ -506,40 +531,92 @@ extern "C" void kmx_db_info(const kmx_db* db, kmx_db_info_t* info) {
 	}
 }
 
+// Process-wide pinned bounce buffers for file -> device streaming (allocated once, kept).
+namespace {
+constexpr size_t kChunk = 8u << 20;
+constexpr int kReaders = 4, kSlotsPerReader = 2;
+struct Bounce {
+	std::mutex mu;
+	uint8_t* buf[kReaders][kSlotsPerReader] = {};
+	bool ready = false;
+	int acquire() {
+		if (ready) return KMX_OK;
+		for (auto& r : buf)
+			for (auto& b : r)
+				if (cudaHostAlloc((void**)&b, kChunk, cudaHostAllocPortable) != cudaSuccess) return fail(KMX_ECUDA, "pinned bounce buffer allocation failed");
+		ready = true;
+		return KMX_OK;
+	}
+};
+Bounce g_bounce;
+}  // namespace
+
+// .kmc_suf record area -> HBM: kReaders threads pread() 8 MiB chunks into pinned bounce buffers
+// and push each with its own stream, so page-cache copies and PCIe transfers overlap.
 extern "C" int kmx_db_upload(kmx_db* db) {
 	if (!db) return fail(KMX_EARG, "null database");
 	if (db->d_suf) return KMX_OK;
 	int rc = require_gpu(&db->sm_count);
 	if (rc) return rc;
 	db->device = g_device;
+	auto t0 = std::chrono::high_resolution_clock::now();
 	if (!db->stream) CU(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
-	cudaEvent_t e0, e1;
-	CU(cudaEventCreate(&e0));
-	CU(cudaEventCreate(&e1));
-	CU(cudaMalloc(&db->d_suf, db->suf_alloc));
-	CU(cudaMalloc(&db->d_lut, db->lut.size() * 8));
-	CU(cudaEventRecord(e0, db->stream));
-	CU(cudaMemcpyAsync(db->d_suf, db->h_suf, db->suf_alloc, cudaMemcpyHostToDevice, db->stream));
+	std::lock_guard<std::mutex> lock(g_bounce.mu);
+	if ((rc = g_bounce.acquire())) return rc;
+	DA(&db->d_suf, db->suf_alloc, db->stream);
+	DA(&db->d_lut, db->lut.size() * 8, db->stream);
 	CU(cudaMemcpyAsync(db->d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, db->stream));
-	CU(cudaEventRecord(e1, db->stream));
-	CU(cudaStreamSynchronize(db->stream));
-	CU(cudaEventElapsedTime(&db->ms_upload, e0, e1));
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
+	const uint64_t bytes = db->info.suffix_bytes;
+	CU(cudaMemsetAsync(db->d_suf + (bytes & ~15ULL), 0, db->suf_alloc - (bytes & ~15ULL), db->stream));
+	CU(cudaStreamSynchronize(db->stream));               // the allocation is usable from the reader streams now
+	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
+	const int n_thr = (int)std::min<uint64_t>(kReaders, n_chunks);
+	std::vector<std::thread> pool;
+	std::vector<int> status(kReaders, KMX_OK);
+	for (int t = 0; t < n_thr; t++) {
+		pool.emplace_back([&, t]() {
+			cudaSetDevice(db->device);
+			cudaStream_t st;
+			cudaEvent_t ev[kSlotsPerReader];
+			if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { status[t] = KMX_ECUDA; return; }
+			for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+			int slot = 0;
+			for (uint64_t c = t; c < n_chunks && status[t] == KMX_OK; c += n_thr, slot ^= 1) {
+				const uint64_t off = c * kChunk, len = std::min<uint64_t>(kChunk, bytes - off);
+				cudaEventSynchronize(ev[slot]);                // the previous copy out of this slot is done
+				uint8_t* b = g_bounce.buf[t][slot];
+				uint64_t got = 0;
+				while (got < len) {
+					ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + off + got));
+					if (r <= 0) { status[t] = KMX_EIO; break; }
+					got += (uint64_t)r;
+				}
+				if (status[t] != KMX_OK) break;
+				if (cudaMemcpyAsync(db->d_suf + off, b, len, cudaMemcpyHostToDevice, st) != cudaSuccess) { status[t] = KMX_ECUDA; break; }
+				cudaEventRecord(ev[slot], st);
+			}
+			if (cudaStreamSynchronize(st) != cudaSuccess && status[t] == KMX_OK) status[t] = KMX_ECUDA;
+			for (auto& e : ev) cudaEventDestroy(e);
+			cudaStreamDestroy(st);
+		});
+	}
+	for (auto& th : pool) th.join();
+	for (int t = 0; t < n_thr; t++)
+		if (status[t] != KMX_OK) return fail(status[t], status[t] == KMX_EIO ? "short read on the .kmc_suf file" : "host-to-device copy of the database failed");
+	db->ms_upload = (float)(1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count());
 	return KMX_OK;
 }
 
 extern "C" void kmx_db_close(kmx_db* db) {
 	if (!db) return;
-	if (db->d_suf || db->stream) {
+	if (db->stream) {
 		cudaSetDevice(db->device);
-		cudaFree(db->d_suf);
-		cudaFree(db->d_lut);
-		if (db->stream) cudaStreamDestroy(db->stream);
+		dev_free(db->d_suf, db->stream);
+		dev_free(db->d_lut, db->stream);
+		cudaStreamSynchronize(db->stream);
+		cudaStreamDestroy(db->stream);
 	}
-	if (db->h_suf) {
-		if (db->pinned) cudaFreeHost(db->h_suf); else free(db->h_suf);
-	}
+	if (db->fd >= 0) close(db->fd);
 	delete db;
 }
 
@@ -573,20 +650,22 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 	uint64_t* d_off = nullptr;
 	uint64_t* d_k = nullptr;
 	uint32_t* d_c = nullptr;
-	CU(cudaMalloc(&d_cnt, n_tiles * 4));
-	CU(cudaMalloc(&d_off, (n_tiles + 1) * 8));
-	CU(cudaMalloc(&d_k, total * 8));
-	CU(cudaMalloc(&d_c, total * 4));
+	cudaStream_t s = db->stream;
+	DA(&d_cnt, n_tiles * 4, s);
+	DA(&d_off, (n_tiles + 1) * 8, s);
+	DA(&d_k, total * 8, s);
+	DA(&d_c, total * 4, s);
 	DevDb d = dev_db(db);
-	CU(launch_list_count(d, d_cnt, db->sm_count, db->stream));
-	CU(launch_tile_scan(d_cnt, n_tiles, d_off, db->stream));
-	CU(launch_list(d, d_off, d_k, d_c, db->sm_count, db->stream));
+	CU(launch_list_count(d, d_cnt, db->sm_count, s));
+	CU(launch_tile_scan(d_cnt, n_tiles, d_off, s));
+	CU(launch_list(d, d_off, d_k, d_c, db->sm_count, s));
 	uint64_t listed = 0;
-	CU(cudaMemcpyAsync(&listed, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, db->stream));
-	CU(cudaStreamSynchronize(db->stream));
-	CU(cudaMemcpy(kmers, d_k, listed * 8, cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(counts, d_c, listed * 4, cudaMemcpyDeviceToHost));
-	cudaFree(d_cnt); cudaFree(d_off); cudaFree(d_k); cudaFree(d_c);
+	CU(cudaMemcpyAsync(&listed, d_off + n_tiles, 8, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	CU(cudaMemcpyAsync(kmers, d_k, listed * 8, cudaMemcpyDeviceToHost, s));
+	CU(cudaMemcpyAsync(counts, d_c, listed * 4, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	dev_free(d_cnt, s); dev_free(d_off, s); dev_free(d_k, s); dev_free(d_c, s);
 	*n_out = listed;
 	return KMX_OK;
 }
@@ -594,33 +673,31 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 // =========================================================================================
 // build: KModel::init (kmodel.hpp:57-86)
 // =========================================================================================
-static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_surv_occ, uint64_t n) {
+static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups) {
 	RestHost& r = m->rest;
+	cudaStream_t s = m->stream;
 	r.k = m->k;
 	r.pre_len = rest_prefix_len(m->k);                    // rest.hpp:140-149
 	r.map_size = 1 << (2 * r.pre_len);
 	r.count = n;
 	r.suff_bin_size = n * (uint64_t)((m->k - r.pre_len) / 4);
 	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "%llu rest entries overflow the reference's int indices (rest.hpp:66-70)", (unsigned long long)n);
-	CU(cudaMalloc(&m->d_hash2index, (size_t)r.map_size * 4));
-	CU(cudaMalloc(&m->d_pre_buffer, ((size_t)r.map_size + 1) * 4));
-	CU(cudaMalloc(&m->d_rest_keys, (n + 1) * 8));
-	CU(cudaMalloc(&m->d_rest_counts, (n + 1) * 4));
+	DA(&m->d_hash2index, (size_t)r.map_size * 4, s);
+	DA(&m->d_pre_buffer, ((size_t)r.map_size + 1) * 4, s);
+	DA(&m->d_rest_keys, (n + 1) * 8, s);
+	DA(&m->d_rest_counts, (n + 1) * 4, s);
 	int32_t* d_first = nullptr;
 	int32_t* d_groups = nullptr;
 	void* d_temp = nullptr;
 	size_t temp_bytes = 0;
-	CU(cudaMalloc(&d_first, (size_t)r.map_size * 4));
-	CU(cudaMalloc(&d_groups, 4));
+	DA(&d_first, (size_t)r.map_size * 4, s);
+	DA(&d_groups, 4, s);
 	CU(rest_sort_bytes(n, &temp_bytes));
-	if (temp_bytes) CU(cudaMalloc(&d_temp, temp_bytes));
-	CU(launch_rest_sort(d_temp, temp_bytes, d_surv_kmer, m->d_rest_keys, d_surv_occ, m->d_rest_counts, n, 2 * m->k, m->stream));
-	CU(launch_rest_index(m->d_rest_keys, n, 2 * (m->k - r.pre_len), r.map_size, d_first, m->d_hash2index, m->d_pre_buffer, d_groups, m->stream));
-	int32_t groups = 0;
-	CU(cudaMemcpyAsync(&groups, d_groups, 4, cudaMemcpyDeviceToHost, m->stream));
-	CU(cudaStreamSynchronize(m->stream));
-	r.pre_buffer_size = groups + 1;                       // rest.hpp:119: new int[++pre_buffer_size]
-	cudaFree(d_first); cudaFree(d_groups); cudaFree(d_temp);
+	if (temp_bytes) DA(&d_temp, temp_bytes, s);
+	CU(launch_rest_sort(d_temp, temp_bytes, d_surv_kmer, m->d_rest_keys, d_surv_occ, m->d_rest_counts, n, 2 * m->k, s));
+	CU(launch_rest_index(m->d_rest_keys, n, 2 * (m->k - r.pre_len), r.map_size, d_first, m->d_hash2index, m->d_pre_buffer, d_groups, s));
+	CU(cudaMemcpyAsync(h_groups, d_groups, 4, cudaMemcpyDeviceToHost, s));
+	dev_free(d_first, s); dev_free(d_groups, s); dev_free(d_temp, s);
 	return KMX_OK;
 }
 
@@ -640,27 +717,31 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	const uint64_t total = m->total_kmers;
 	const uint64_t n_tiles = (total + kTile - 1) / kTile;
 	DevDb d = dev_db(db);
-	cudaEvent_t ev[6];
-	for (auto& e : ev) CU(cudaEventCreate(&e));
+	cudaStream_t s = m->stream;
+	cudaEvent_t* ev = m->ev_build;
 
 	// ---- pass 1: class histogram (kmodel.hpp:423-434) ----
 	uint32_t* d_tile_cnt = nullptr;
 	uint64_t* d_tile_off = nullptr;
 	CountOut* d_count = nullptr;
-	CU(cudaMalloc(&d_tile_cnt, (n_tiles + 1) * 4));
-	CU(cudaMalloc(&d_tile_off, (n_tiles + 1) * 8));
-	CU(cudaMalloc(&d_count, sizeof(CountOut)));
-	CU(cudaEventRecord(ev[0], m->stream));
-	CU(cudaMemsetAsync(d_count, 0, sizeof(CountOut), m->stream));
-	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, m->sm_count, m->stream));
-	CU(launch_tile_scan(d_tile_cnt, n_tiles, d_tile_off, m->stream));
-	CountOut cnt;
-	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, m->stream));
-	CU(cudaEventRecord(ev[1], m->stream));
-	CU(cudaStreamSynchronize(m->stream));
-	if (cnt.bad_count)
+	DA(&d_tile_cnt, (n_tiles + 1) * 4, s);
+	DA(&d_tile_off, (n_tiles + 1) * 8, s);
+	DA(&d_count, sizeof(CountOut), s);
+	CU(cudaEventRecord(ev[0], s));
+	CU(cudaMemsetAsync(d_count, 0, sizeof(CountOut), s));
+	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, m->sm_count, s));
+	CU(launch_tile_scan(d_tile_cnt, n_tiles, d_tile_off, s));
+	CountOut& cnt = m->h_pinned->count;
+	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+	CU(cudaEventRecord(ev[1], s));
+	CU(cudaStreamSynchronize(s));                        // sync 1 of 3: the sizes depend on the counts
+	dev_free(d_tile_cnt, s);
+	dev_free(d_count, s);
+	if (cnt.bad_count) {
+		dev_free(d_tile_off, s);
 		return fail(KMX_ERANGE, "%llu records have a count below ci=%d or above cs=%d: the reference indexes out of bounds there (kmodel.hpp:427, occu_bin.hpp:70)",
 		            (unsigned long long)cnt.bad_count, m->ci, m->cs);
+	}
 	uint64_t bf_kmers = 0;
 	for (int i = 0; i < m->bf_num; i++) {
 		m->kmer_counts[i] = cnt.class_count[i];
@@ -668,7 +749,10 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	}
 	m->km_kmers = total - bf_kmers;                       // kmodel.hpp:433: header total, not the listed count
 	rc = alloc_filters(m);
-	if (rc) return rc;
+	if (rc) {
+		dev_free(d_tile_off, s);
+		return rc;
+	}
 	m->rest.k = m->k;
 	m->rest.pre_len = rest_prefix_len(m->k);
 	fill_dev_model(m);
@@ -677,62 +761,68 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	const uint64_t n_items = cnt.array_bound;
 	uint64_t* d_item_kmer = nullptr;
 	uint32_t* d_item_occ = nullptr;
-	CU(cudaMalloc(&d_item_kmer, (n_items + 1) * 8));
-	CU(cudaMalloc(&d_item_occ, (n_items + 1) * 4));
-	CU(launch_encode(d, m->dm, d_tile_off, d_item_kmer, d_item_occ, m->sm_count, m->stream));
-	CU(cudaEventRecord(ev[2], m->stream));
+	DA(&d_item_kmer, (n_items + 1) * 8, s);
+	DA(&d_item_occ, (n_items + 1) * 4, s);
+	CU(launch_encode(d, m->dm, d_tile_off, d_item_kmer, d_item_occ, m->sm_count, s));
+	dev_free(d_tile_off, s);
+	CU(cudaEventRecord(ev[2], s));
 
 	// ---- greedy insert (kmodel.hpp:508-573) ----
 	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
 	const uint64_t n_batches = (n_items + batch_items - 1) / batch_items;
 	InsertArgs a;
 	memset(&a, 0, sizeof(a));
-	InsertCtl ctl;
+	InsertCtl& ctl = m->h_pinned->ctl;
 	memset(&ctl, 0, sizeof(ctl));
-	uint64_t rest_cap = 0;
 	if (n_items > 0) {
 		a.item_kmer = d_item_kmer;
 		a.item_occ = d_item_occ;
 		a.n_items = n_items;
-		for (int s = 0; s < 2; s++) {
-			CU(cudaMalloc(&a.buf_kmer[s], batch_items * 8));
-			CU(cudaMalloc(&a.buf_occ[s], batch_items * 4));
+		for (int b = 0; b < 2; b++) {
+			DA(&a.buf_kmer[b], batch_items * 8, s);
+			DA(&a.buf_occ[b], batch_items * 4, s);
 		}
-		CU(cudaMalloc(&a.status, batch_items * 4));
-		CU(cudaMalloc(&a.rank, batch_items * 4));
-		CU(cudaMalloc(&a.holepos, batch_items * 4));
-		CU(cudaMalloc(&a.tile_fail, batch_items / 256 * 4));
-		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, m->stream));
-		a.resv_slots = 1u << 20;
-		if (const char* s = getenv("KMX_RESV_LOG2")) {
-			int v = atoi(s);
+		DA(&a.status, batch_items * 4, s);
+		DA(&a.rank, batch_items * 4, s);
+		DA(&a.holepos, batch_items * 4, s);
+		DA(&a.tile_fail, batch_items / 256 * 4, s);
+		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
+		a.resv_slots = 1u << 22;
+		if (const char* e = getenv("KMX_RESV_LOG2")) {
+			int v = atoi(e);
 			if (v >= 10 && v <= 26) a.resv_slots = 1u << v;
 		}
-		CU(cudaMalloc(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4));
-		CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, m->stream));
-		CU(cudaMalloc(&a.ctl, sizeof(InsertCtl)));
-		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), m->stream));
+		DA(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4, s);
+		CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, s));
+		DA(&a.ctl, sizeof(InsertCtl), s);
+		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), s));
 		a.max_iterations = kBucket + 64;
 		int grid = 0;
 		CU(insert_grid_size(&grid, m->sm_count));
+		// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
+		// all launches queue without a host round trip; beyond that it grows between launches.
+		const bool worst_case = n_items <= (1ULL << 28);
+		uint64_t rest_cap = worst_case ? n_items + m->n_bits : 0;
+		if (worst_case) {
+			DA(&a.rest_kmer, rest_cap * 8, s);
+			DA(&a.rest_occ, rest_cap * 4, s);
+		}
 		const uint64_t chunk = 64;                         // batches per launch
 		for (uint64_t b0 = 0; b0 < n_batches; b0 += chunk) {
 			const uint64_t nb = std::min<uint64_t>(chunk, n_batches - b0);
 			const uint64_t need = ctl.rest_n + nb * batch_items + m->n_bits;
-			if (need > rest_cap) {                          // grow the survivor list (worst case: nothing is accepted)
+			if (!worst_case && need > rest_cap) {
 				uint64_t new_cap = std::max<uint64_t>(need, rest_cap * 2);
-				if (new_cap > n_items + m->n_bits) new_cap = std::max<uint64_t>(need, n_items + m->n_bits);
 				uint64_t* nk = nullptr;
 				uint32_t* no = nullptr;
-				CU(cudaMalloc(&nk, new_cap * 8));
-				CU(cudaMalloc(&no, new_cap * 4));
+				DA(&nk, new_cap * 8, s);
+				DA(&no, new_cap * 4, s);
 				if (ctl.rest_n) {
-					CU(cudaMemcpyAsync(nk, a.rest_kmer, ctl.rest_n * 8, cudaMemcpyDeviceToDevice, m->stream));
-					CU(cudaMemcpyAsync(no, a.rest_occ, ctl.rest_n * 4, cudaMemcpyDeviceToDevice, m->stream));
-					CU(cudaStreamSynchronize(m->stream));
+					CU(cudaMemcpyAsync(nk, a.rest_kmer, ctl.rest_n * 8, cudaMemcpyDeviceToDevice, s));
+					CU(cudaMemcpyAsync(no, a.rest_occ, ctl.rest_n * 4, cudaMemcpyDeviceToDevice, s));
 				}
-				cudaFree(a.rest_kmer);
-				cudaFree(a.rest_occ);
+				dev_free(a.rest_kmer, s);
+				dev_free(a.rest_occ, s);
 				a.rest_kmer = nk;
 				a.rest_occ = no;
 				rest_cap = new_cap;
@@ -740,19 +830,35 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 			a.rest_cap = rest_cap;
 			a.first_batch = b0;
 			a.n_batches = nb;
-			CU(launch_insert(m->dm, a, grid, m->stream));
-			CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, m->stream));
-			CU(cudaStreamSynchronize(m->stream));
-			if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
+			CU(launch_insert(m->dm, a, grid, s));
+			if (!worst_case) {
+				CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
+				CU(cudaStreamSynchronize(s));
+				if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
+			}
 		}
+		CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 	}
-	CU(cudaEventRecord(ev[3], m->stream));
+	CU(cudaEventRecord(ev[3], s));
+	CU(cudaStreamSynchronize(s));                        // sync 2 of 3: the sort needs the survivor count
+	if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
+	dev_free(d_item_kmer, s);
+	dev_free(d_item_occ, s);
+	for (int b = 0; b < 2; b++) {
+		dev_free(a.buf_kmer[b], s);
+		dev_free(a.buf_occ[b], s);
+	}
+	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.ctl, s);
 
 	// ---- rest table (rest.hpp:157-161) ----
-	rc = build_rest_table(m, a.rest_kmer, a.rest_occ, ctl.rest_n);
+	int32_t& groups = m->h_pinned->groups;
+	rc = build_rest_table(m, a.rest_kmer, a.rest_occ, ctl.rest_n, &groups);
 	if (rc) return rc;
-	CU(cudaEventRecord(ev[4], m->stream));
-	CU(cudaStreamSynchronize(m->stream));
+	dev_free(a.rest_kmer, s);
+	dev_free(a.rest_occ, s);
+	CU(cudaEventRecord(ev[4], s));
+	CU(cudaStreamSynchronize(s));                        // sync 3 of 3
+	m->rest.pre_buffer_size = groups + 1;                 // rest.hpp:119: new int[++pre_buffer_size]
 	fill_dev_model(m);
 	m->built = true;
 
@@ -762,21 +868,13 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	f.insert_accepted = ctl.accepted;
 	f.insert_iterations = ctl.iterations;
 	f.batches = n_batches;
+	for (int i = 0; i < 8; i++) f.insert_phase_cycles[i] = ctl.phase_cycles[i];
 	f.ms_upload = db->ms_upload;
 	CU(cudaEventElapsedTime(&f.ms_count, ev[0], ev[1]));
 	CU(cudaEventElapsedTime(&f.ms_encode, ev[1], ev[2]));
 	CU(cudaEventElapsedTime(&f.ms_insert, ev[2], ev[3]));
 	CU(cudaEventElapsedTime(&f.ms_rest, ev[3], ev[4]));
 	CU(cudaEventElapsedTime(&f.ms_total_device, ev[0], ev[4]));
-	for (auto& e : ev) cudaEventDestroy(e);
-	cudaFree(d_tile_cnt); cudaFree(d_tile_off); cudaFree(d_count);
-	cudaFree(d_item_kmer); cudaFree(d_item_occ);
-	for (int s = 0; s < 2; s++) {
-		cudaFree(a.buf_kmer[s]);
-		cudaFree(a.buf_occ[s]);
-	}
-	cudaFree(a.status); cudaFree(a.rank); cudaFree(a.holepos); cudaFree(a.tile_fail); cudaFree(a.resv); cudaFree(a.ctl);
-	cudaFree(a.rest_kmer); cudaFree(a.rest_occ);
 	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - wall0).count();
 	return KMX_OK;
 }
@@ -791,7 +889,6 @@ extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
 	kmx_db_close(db);
 	return rc;
 }
-
 // =========================================================================================
 // save / load (kmodel.hpp:173-235, rest.hpp:163-221)
 // =========================================================================================
@@ -965,10 +1062,10 @@ static int load_into(kmx_model* m, const std::string& base) {
 		}
 	}
 	m->k = r.k;
-	CU(cudaMalloc(&m->d_hash2index, (size_t)r.map_size * 4));
-	CU(cudaMalloc(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4));
-	CU(cudaMalloc(&m->d_rest_keys, (r.count + 1) * 8));
-	CU(cudaMalloc(&m->d_rest_counts, (r.count + 1) * 4));
+	DA(&m->d_hash2index, (size_t)r.map_size * 4, m->stream);
+	DA(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4, m->stream);
+	DA(&m->d_rest_keys, (r.count + 1) * 8, m->stream);
+	DA(&m->d_rest_counts, (r.count + 1) * 4, m->stream);
 	if ((rc = h2d_sync(m->d_hash2index, h2i.data(), h2i.size() * 4, m->stream))) return rc;
 	if ((rc = h2d_sync(m->d_pre_buffer, pre.data(), pre.size() * 4, m->stream))) return rc;
 	if ((rc = h2d_sync(m->d_rest_keys, keys.data(), r.count * 8, m->stream))) return rc;
@@ -1034,16 +1131,17 @@ static int ensure_staging(kmx_model* m, size_t item_bytes) {
 	const size_t bytes = items * item_bytes;
 	if (m->stage_bytes >= bytes && m->stage_items == items) return KMX_OK;
 	for (int s = 0; s < 2; s++) {
-		cudaFreeHost(m->h_in[s]); cudaFree(m->d_in[s]);
+		cudaFreeHost(m->h_in[s]); dev_free(m->d_in[s], m->stream);
 		m->h_in[s] = nullptr; m->d_in[s] = nullptr;
 		CU(cudaMallocHost(&m->h_in[s], bytes));
-		CU(cudaMalloc(&m->d_in[s], bytes));
+		DA(&m->d_in[s], bytes, m->stream);
 		if (!m->h_out[s]) {
 			CU(cudaMallocHost((void**)&m->h_out[s], items * 4));
-			CU(cudaMalloc((void**)&m->d_out[s], items * 4));
+			DA(&m->d_out[s], items * 4, m->stream);
 			CU(cudaEventCreateWithFlags(&m->ev_done[s], cudaEventDisableTiming));
 		}
 	}
+	CU(cudaStreamSynchronize(m->stream));                 // the staging buffers are used from both streams
 	m->stage_bytes = bytes;
 	m->stage_items = items;
 	return KMX_OK;

@@ -49,6 +49,7 @@ struct InsertCtl {                    // lives in device memory, survives across
 	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
 	unsigned int slot0_occ[kMaxArrays];
 	unsigned int slot0_valid[kMaxArrays];
+	unsigned long long phase_cycles[8];   // SM cycles seen by thread 0: reserve/commit (first iteration, later), scan, place, move
 };
 
 struct InsertArgs {
