@@ -308,7 +308,7 @@ def main() -> None:
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": n_kmers, "k": 31, "n_hash": 7, "n_bits": 5, "ci": meta["ci"], "cs": 1023,
                    "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "replicas" if world > 1 else "single"},
-        "device_ms_per_step": dev_ms,
+        "device_ms_per_step": dev_ms, "wall_ms_steps": [round(1e3 * w, 3) for w in wall], "e2e_wall_ms_steps": [round(1e3 * w, 3) for w in e2e_wall],
         "stage_ms": {k: float(np.mean([i[k] for i in infos])) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
         "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": meta["suffix_bytes"] + meta["prefix_bytes"], "d2h_bytes_per_step": 256,
                 "ms_per_step": 1e3 * t_e2e / args.steps},

@@ -324,7 +324,7 @@ constexpr uint32_t kEpochMax = 0x3FFFu;
 constexpr uint32_t kIdTile = 256;                           // ids per reorder tile
 
 template <int K, int H, int B>
-__global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
+__global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
 	cg::grid_group grid = cg::this_grid();
 	constexpr int HM = H ? H : kMaxHash;
 	constexpr int BM = B ? B : kMaxArrays;
@@ -340,11 +340,8 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 	InsertCtl* ctl = a.ctl;
 	volatile InsertCtl* vctl = a.ctl;
 	__shared__ uint32_t s_warp[9];
-	__shared__ unsigned long long s_sum[8];
 
 	uint32_t epoch = vctl->epoch;
-	uint32_t itc = 0;                                       // rotating counter index, uniform over the grid
-	if (tid == 0) vctl->undecided[0] = vctl->undecided[1] = vctl->undecided[2] = 0;
 	grid.sync();                                            // everybody has read ctl->epoch before it is rewritten
 
 	for (unsigned long long batch = a.first_batch; batch < a.first_batch + a.n_batches; batch++) {
@@ -384,55 +381,115 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 			uint32_t* dst_occ = a.buf_occ[t & 1];
 
 			// ---------------- reservation iterations ----------------
-			uint32_t iter = 0;
+			// (a)+(b): check one item against the committed state, reject or reserve
+			auto reserve_item = [&](uint32_t id, uint32_t key_hi) {
+				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+				const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
+				const uint64_t v = __ldcg(src_kmer + id);
+				const uint32_t occ = __ldcg(src_occ + id);
+				const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+				HashPrep p;
+				hash_prepare(reverse_bases(v, k), k, p);
+				uint64_t pos[HM];
+				unsigned long long cell[HM];
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh) {
+						pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
+						cell[j] = __ldcg(m.cells[arr] + (pos[j] >> 5));
+					}
+				}
+				bool conflict = false;
+				uint32_t need = 0;
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh) {
+						const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
+						const uint32_t val = ((uint32_t)cell[j] >> sh) & 1u, tag = ((uint32_t)(cell[j] >> 32) >> sh) & 1u;
+						const uint32_t want = (bin >> j) & 1u;
+						conflict |= (tag != 0) && (val != want);
+						need |= (tag ^ 1u) << j;
+					}
+				}
+				if (conflict) {
+					a.status[id] = kRejected;
+					atomicAdd(a.tile_fail + (id / kIdTile), 1u);
+				} else {
+					uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
+#pragma unroll
+					for (int j = 0; j < HM; j++) {
+						if (j < nh && ((need >> j) & 1u)) {
+							const uint32_t want = (bin >> j) & 1u;
+							atomicMin(table + 2 * ((uint32_t)pos[j] & slot_mask) + want, key_hi | c);
+						}
+					}
+					a.status[id] = need;
+				}
+			};
+			// (c): accept the item if nobody smaller contests it; true = still undecided
+			auto commit_item = [&](uint32_t id, uint32_t key_hi) -> bool {
+				const uint32_t need = a.status[id];
+				if (need >> kStateShift) return false;
+				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+				const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
+				const uint64_t v = __ldcg(src_kmer + id);
+				const uint32_t occ = __ldcg(src_occ + id);
+				const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+				const uint64_t r = reverse_bases(v, k);
+				HashPrep p;
+				hash_prepare(r, k, p);
+				uint64_t pos[HM];
+				const uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
+				const uint32_t key = key_hi | c;
+				bool ok = true;
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh) {
+						pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
+						if ((need >> j) & 1u) {
+							const uint32_t want = (bin >> j) & 1u;
+							ok &= __ldcg(table + 2 * ((uint32_t)pos[j] & slot_mask) + (want ^ 1u)) >= key;
+						}
+					}
+				}
+				if (!ok) return true;
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh && ((need >> j) & 1u)) {          // positions already tagged hold the wanted value
+						const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
+						const unsigned long long want = (bin >> j) & 1u;
+						atomicOr(m.cells[arr] + (pos[j] >> 5), ((1ULL << 32) | want) << sh);
+					}
+				}
+				// accepted: the (k-2)-mer goes to km_back (kmodel.hpp:546-550)
+				hash_prepare(middle_r(r, k), k - 2, p);
+#pragma unroll
+				for (int j = 0; j < HM - 2; j++)
+					if (j < hk) filter_set(m.km_back, hash_finish(p, k - 2, c_seeds[j]));
+				a.status[id] = kAccepted;
+				return false;
+			};
+			// The first iteration walks every item of the round; what stays undecided is appended
+			// (order is irrelevant, the index travels in the key) to a list that the later
+			// iterations walk instead, so that their cost follows the number of open items.
+			uint32_t iter = 0, n_list = 0;
+			int cur = 0;
 			long long tick = clock64();
 			while (true) {
 				const uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
-				// (a)+(b): check against the committed state, reserve
-				for (uint32_t id = tid; id < total_ids; id += T) {
-					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-					if (c >= n_cur[i]) continue;
-					if (iter > 0 && (a.status[id] >> kStateShift)) continue;
-					const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
-					const uint64_t v = __ldcg(src_kmer + id);
-					uint32_t occ = __ldcg(src_occ + id);
-					const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
-					HashPrep p;
-					hash_prepare(reverse_bases(v, k), k, p);
-					uint64_t pos[HM];
-					unsigned long long cell[HM];
-#pragma unroll
-					for (int j = 0; j < HM; j++) {
-						if (j < nh) {
-							pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
-							cell[j] = __ldcg(m.cells[arr] + (pos[j] >> 5));
-						}
+				const uint32_t* list_cur = a.list[cur];
+				uint32_t* list_next = a.list[cur ^ 1];
+				if (tid == 0) vctl->list_n[cur ^ 1] = 0;
+				if (iter == 0) {
+					for (uint32_t id = tid; id < total_ids; id += T) {
+						if ((id & (kBucket - 1)) >= n_cur[id >> kBucketLog]) continue;
+						reserve_item(id, key_hi);
 					}
-					bool conflict = false;
-					uint32_t need = 0;
-#pragma unroll
-					for (int j = 0; j < HM; j++) {
-						if (j < nh) {
-							const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
-							const uint32_t val = ((uint32_t)cell[j] >> sh) & 1u, tag = ((uint32_t)(cell[j] >> 32) >> sh) & 1u;
-							const uint32_t want = (bin >> j) & 1u;
-							conflict |= (tag != 0) && (val != want);
-							need |= (tag ^ 1u) << j;
-						}
-					}
-					if (conflict) {
-						a.status[id] = kRejected;
-						atomicAdd(a.tile_fail + (id / kIdTile), 1u);
-					} else {
-						uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
-#pragma unroll
-						for (int j = 0; j < HM; j++) {
-							if (j < nh && ((need >> j) & 1u)) {
-								const uint32_t want = (bin >> j) & 1u;
-								atomicMin(table + 2 * ((uint32_t)pos[j] & slot_mask) + want, key_hi | c);
-							}
-						}
-						a.status[id] = need;
+				} else {
+					for (uint32_t x = tid; x < n_list; x += T) {
+						const uint32_t id = __ldcg(list_cur + x);
+						if (a.status[id] >> kStateShift) continue;
+						reserve_item(id, key_hi);
 					}
 				}
 				grid.sync();
@@ -441,57 +498,21 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 					vctl->phase_cycles[iter == 0 ? 0 : 2] += (unsigned long long)(now - tick);
 					tick = now;
 				}
-				// (c): accept the items nobody smaller contests
-				uint32_t undecided = 0;
-				for (uint32_t id = tid; id < total_ids; id += T) {
-					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-					if (c >= n_cur[i]) continue;
-					const uint32_t need = a.status[id];
-					if (need >> kStateShift) continue;
-					const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
-					const uint64_t v = __ldcg(src_kmer + id);
-					uint32_t occ = __ldcg(src_occ + id);
-					const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
-					const uint64_t r = reverse_bases(v, k);
-					HashPrep p;
-					hash_prepare(r, k, p);
-					uint64_t pos[HM];
-					const uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
-					const uint32_t key = key_hi | c;
-					bool ok = true;
-#pragma unroll
-					for (int j = 0; j < HM; j++) {
-						if (j < nh) {
-							pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
-							if ((need >> j) & 1u) {
-								const uint32_t want = (bin >> j) & 1u;
-								ok &= __ldcg(table + 2 * ((uint32_t)pos[j] & slot_mask) + (want ^ 1u)) >= key;
-							}
-						}
-					}
-					if (ok) {
-#pragma unroll
-						for (int j = 0; j < HM; j++) {
-							if (j < nh) {
-								const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
-								const unsigned long long want = (bin >> j) & 1u;
-								atomicOr(m.cells[arr] + (pos[j] >> 5), ((1ULL << 32) | want) << sh);
-							}
-						}
-						// accepted: the (k-2)-mer goes to km_back (kmodel.hpp:546-550)
-						hash_prepare(middle_r(r, k), k - 2, p);
-#pragma unroll
-						for (int j = 0; j < HM - 2; j++)
-							if (j < hk) filter_set(m.km_back, hash_finish(p, k - 2, c_seeds[j]));
-						a.status[id] = kAccepted;
+				const uint32_t n_walk = iter == 0 ? total_ids : n_list;
+				for (uint32_t x = tid; x < n_walk; x += T) {
+					uint32_t id = x;
+					if (iter == 0) {
+						if ((id & (kBucket - 1)) >= n_cur[id >> kBucketLog]) continue;
 					} else {
-						undecided++;
+						id = __ldcg(list_cur + x);
 					}
-				}
-				unsigned long long und_block = block_sum(undecided, s_sum);
-				if (threadIdx.x == 0) {
-					if (und_block) atomicAdd(&ctl->undecided[itc % 3], (unsigned int)und_block);
-					if (blockIdx.x == 0) vctl->undecided[(itc + 1) % 3] = 0;
+					if (commit_item(id, key_hi)) {
+						cg::coalesced_group g = cg::coalesced_threads();
+						uint32_t at = 0;
+						if (g.thread_rank() == 0) at = atomicAdd(&ctl->list_n[cur ^ 1], g.size());
+						at = g.shfl(at, 0);
+						list_next[at + g.thread_rank()] = id;
+					}
 				}
 				grid.sync();
 				if (tid == 0) {
@@ -499,8 +520,8 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 					vctl->phase_cycles[iter == 0 ? 1 : 3] += (unsigned long long)(now - tick);
 					tick = now;
 				}
-				const uint32_t und = vctl->undecided[itc % 3];
-				itc++;
+				n_list = vctl->list_n[cur ^ 1];
+				cur ^= 1;
 				iter++;
 				epoch++;
 				if (epoch >= kEpochMax) {                       // keys can get no smaller: start over
@@ -508,7 +529,7 @@ __global__ void __launch_bounds__(256, 2) insert_kernel(const __grid_constant__ 
 					epoch = 0;
 					grid.sync();
 				}
-				if (und == 0) break;
+				if (n_list == 0) break;
 				if (iter >= a.max_iterations) {
 					if (tid == 0) vctl->error = 1;
 					return;                                     // uniform over the grid

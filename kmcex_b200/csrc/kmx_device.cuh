@@ -18,13 +18,17 @@ struct DevFilter {
 };
 
 struct DevRest {
-	const int32_t* hash2index;       // [map_size]  dense group id or -1
-	const int32_t* pre_buffer;       // [groups+1]  first entry of each group, cumulative
+	const int32_t* hash2index;       // [map_size]  dense group id or -1          (on-disk form)
+	const int32_t* pre_buffer;       // [groups+1]  first entry of each group      (on-disk form)
 	const uint64_t* keys;            // [count]     full packed k-mers, ascending
 	const int32_t* counts;           // [count]
+	const uint32_t* fine;            // [2^fine_bits + 1] first entry of each bucket of the top fine_bits key bits
+	const uint64_t* quirk_suffix;    // [map_size]  the one suffix that false-hits for this prefix, or ~0
+	const uint32_t* quirk_index;     // [map_size]  entry whose count that false hit returns
 	uint64_t count;
 	uint64_t suffix_mask;            // low 2*(k-pre_len) bits
 	int suffix_bits;
+	int fine_bits, fine_shift;       // bucket = key >> fine_shift
 	int k;
 };
 
@@ -60,29 +64,6 @@ KMX_D bool filter_test(const DevFilter& f, uint64_t h) {
 KMX_D void filter_set(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);
 	atomicOr(f.words + (pos >> 5), bit_mask32(pos));
-}
-
-// ---- rest table: KRestData::check_kmer (rest.hpp:223-251) ----------------------------------
-// Binary search over [pre_buffer[g], pre_buffer[g+1]] with the reference's INCLUSIVE upper
-// bound: the probe can land on the first entry of the next group, where only suffix bytes are
-// compared, which yields the reference's false hits.  A probe at index == count is out of
-// bounds in the reference and counts as "no match".
-KMX_D int rest_lookup(const DevRest& R, uint64_t v) {
-	if (R.count == 0 && R.hash2index == nullptr) return 0;
-	uint32_t pre = (uint32_t)(v >> R.suffix_bits);
-	int g = __ldg(R.hash2index + pre);
-	if (g < 0) return 0;
-	uint64_t key = v & R.suffix_mask;
-	long long low = __ldg(R.pre_buffer + g), high = __ldg(R.pre_buffer + g + 1);
-	while (low <= high) {
-		long long mid = (low + high) >> 1;
-		if ((uint64_t)mid >= R.count) return 0;
-		uint64_t s = __ldg(R.keys + mid) & R.suffix_mask;
-		if (key < s) high = mid - 1;
-		else if (key > s) low = mid + 1;
-		else return __ldg(R.counts + mid);
-	}
-	return 0;
 }
 
 #endif  // __CUDACC__

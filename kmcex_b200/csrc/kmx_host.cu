@@ -33,6 +33,19 @@ using namespace kmx;
 static thread_local char g_err[512] = "";
 static int g_device = 0;
 
+// KMX_TRACE=1: host-side timeline of a build on stderr (milliseconds since the call started)
+static bool trace_on() {
+	static int on = -1;
+	if (on < 0) on = getenv("KMX_TRACE") ? 1 : 0;
+	return on == 1;
+}
+#define TRACE(t0, what)                                                                                             \
+	do {                                                                                                           \
+		if (trace_on())                                                                                            \
+			fprintf(stderr, "[kmx] %8.3f ms  %s\n",                                                                \
+			        1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - (t0)).count(), what); \
+	} while (0)
+
 static int fail(int code, const char* fmt, ...) {
 	va_list ap;
 	va_start(ap, fmt);
@@ -76,18 +89,27 @@ static void dev_free(void* p, cudaStream_t s) {
 	} while (0)
 
 static int require_gpu(int* sm_count) {
-	int n = 0;
-	cudaError_t e = cudaGetDeviceCount(&n);
-	if (e != cudaSuccess || n <= 0) {
-		cudaGetLastError();
-		return fail(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path): %s", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+	// cudaGetDeviceProperties costs milliseconds: ask once per device
+	static int cached_sm[64] = { 0 };
+	static int cached_n = -1;
+	if (cached_n < 0) {
+		int n = 0;
+		cudaError_t e = cudaGetDeviceCount(&n);
+		if (e != cudaSuccess || n <= 0) {
+			cudaGetLastError();
+			return fail(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path): %s", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+		}
+		cached_n = n;
 	}
-	if (g_device >= n) return fail(KMX_ENOGPU, "device %d requested, %d present", g_device, n);
+	if (g_device >= cached_n || g_device >= 64) return fail(KMX_ENOGPU, "device %d requested, %d present", g_device, cached_n);
 	CU(cudaSetDevice(g_device));
-	cudaDeviceProp prop;
-	CU(cudaGetDeviceProperties(&prop, g_device));
-	if (prop.major < 10) return fail(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", g_device, prop.major, prop.minor);
-	if (sm_count) *sm_count = prop.multiProcessorCount;
+	if (cached_sm[g_device] == 0) {
+		cudaDeviceProp prop;
+		CU(cudaGetDeviceProperties(&prop, g_device));
+		if (prop.major < 10) return fail(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", g_device, prop.major, prop.minor);
+		cached_sm[g_device] = prop.multiProcessorCount;
+	}
+	if (sm_count) *sm_count = cached_sm[g_device];
 	return KMX_OK;
 }
 
@@ -156,6 +178,70 @@ static int rest_prefix_len(int k) {              // rest.hpp:78-83
 // =========================================================================================
 // objects
 // =========================================================================================
+// Per-device execution context: streams, events, pinned scratch and the query staging buffers.
+// Creating these costs milliseconds (cudaHostAlloc, cudaStreamCreate), so contexts are pooled
+// for the life of the process: a model borrows one at its first device use and returns it when
+// destroyed; a database upload borrows one for the duration of the copy.
+struct DevCtx {
+	int device = 0;
+	cudaStream_t stream = nullptr, stream2 = nullptr;
+	cudaStream_t reader[4] = { nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t reader_ev[4][2] = {};
+	cudaEvent_t ev_build[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
+		CountOut count;
+		InsertCtl ctl;
+		int32_t groups;
+	}* h_pinned = nullptr;
+	// pinned staging for host-pointer queries (two slots)
+	void* h_in[2] = { nullptr, nullptr };
+	int32_t* h_out[2] = { nullptr, nullptr };
+	void* d_in[2] = { nullptr, nullptr };
+	int32_t* d_out[2] = { nullptr, nullptr };
+	DeferredQuery* d_defer[2] = { nullptr, nullptr };
+	unsigned int* d_defer_n[2] = { nullptr, nullptr };
+	size_t stage_bytes = 0, stage_items = 0;
+	cudaEvent_t ev_done[2] = { nullptr, nullptr };
+};
+
+namespace {
+std::mutex g_ctx_mu;
+std::vector<DevCtx*> g_ctx_free;
+}
+
+static int ctx_acquire(DevCtx** out) {
+	{
+		std::lock_guard<std::mutex> lock(g_ctx_mu);
+		for (size_t i = 0; i < g_ctx_free.size(); i++) {
+			if (g_ctx_free[i]->device == g_device) {
+				*out = g_ctx_free[i];
+				g_ctx_free.erase(g_ctx_free.begin() + i);
+				return KMX_OK;
+			}
+		}
+	}
+	DevCtx* c = new DevCtx();
+	c->device = g_device;
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+	for (auto& r : c->reader) CU(cudaStreamCreateWithFlags(&r, cudaStreamNonBlocking));
+	for (auto& r : c->reader_ev)
+		for (auto& e : r) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	for (auto& e : c->ev_build) CU(cudaEventCreate(&e));
+	for (auto& e : c->ev_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	CU(cudaHostAlloc((void**)&c->h_pinned, sizeof(DevCtx::Pinned), cudaHostAllocDefault));
+	*out = c;
+	return KMX_OK;
+}
+
+static void ctx_release(DevCtx* c) {
+	if (!c) return;
+	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->stream2);
+	std::lock_guard<std::mutex> lock(g_ctx_mu);
+	g_ctx_free.push_back(c);
+}
+
 struct kmx_db {
 	kmx_db_info_t info;
 	std::vector<uint64_t> lut;        // lut_entries + 1 (guard = total + 1, kmc_file.cpp:223)
@@ -165,7 +251,6 @@ struct kmx_db {
 	uint64_t* d_lut = nullptr;
 	int device = 0, sm_count = 0;
 	float ms_upload = 0;
-	cudaStream_t stream = nullptr;
 };
 
 struct RestHost {
@@ -191,30 +276,22 @@ struct kmx_model {
 	int32_t* d_pre_buffer = nullptr;
 	uint64_t* d_rest_keys = nullptr;
 	int32_t* d_rest_counts = nullptr;
+	uint32_t* d_fine = nullptr;
+	uint64_t* d_quirk_suffix = nullptr;
+	uint32_t* d_quirk_index = nullptr;
+	int fine_bits = 8;
 	RestHost rest;
 	DevModel dm;
 	kmx_info_t info;
-	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaEvent_t ev_build[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
-		CountOut count;
-		InsertCtl ctl;
-		int32_t groups;
-	}* h_pinned = nullptr;
-	// pinned staging for host-pointer queries (two slots)
-	void* h_in[2] = { nullptr, nullptr };
-	int32_t* h_out[2] = { nullptr, nullptr };
-	void* d_in[2] = { nullptr, nullptr };
-	int32_t* d_out[2] = { nullptr, nullptr };
-	size_t stage_bytes = 0, stage_items = 0;
-	cudaEvent_t ev_done[2] = { nullptr, nullptr };
+	DevCtx* x = nullptr;              // borrowed execution context (streams, events, staging)
+	std::vector<uint16_t> occ2bin16;
 };
 
 static size_t pad8(uint64_t bytes) { return (size_t)((bytes + 7) & ~7ULL) + 8; }
 static uint64_t cell_words(uint64_t km_byte_size) { return (km_byte_size + 3) / 4; }
 
 static void free_model_device(kmx_model* m) {
-	cudaStream_t s = m->stream;
+	cudaStream_t s = m->x->stream;
 	for (int i = 0; i < 3; i++) {
 		dev_free(m->d_bf[i], s);
 		dev_free(m->d_bf_back[i], s);
@@ -230,6 +307,12 @@ static void free_model_device(kmx_model* m) {
 	dev_free(m->d_pre_buffer, s);
 	dev_free(m->d_rest_keys, s);
 	dev_free(m->d_rest_counts, s);
+	dev_free(m->d_fine, s);
+	dev_free(m->d_quirk_suffix, s);
+	dev_free(m->d_quirk_index, s);
+	m->d_fine = nullptr;
+	m->d_quirk_suffix = nullptr;
+	m->d_quirk_index = nullptr;
 	m->d_hash2index = m->d_pre_buffer = nullptr;
 	m->d_rest_keys = nullptr;
 	m->d_rest_counts = nullptr;
@@ -247,17 +330,17 @@ static int alloc_filters(kmx_model* m) {
 		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays: the reference aborts on zero-length arrays (kmodel.hpp:443-447)",
 		            (unsigned long long)m->km_kmers);
 	for (int i = 0; i < m->bf_num; i++) {
-		DA(&m->d_bf[i], pad8(m->bytes[i]), m->stream);
-		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->stream));
-		DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->stream);
-		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->stream));
+		DA(&m->d_bf[i], pad8(m->bytes[i]), m->x->stream);
+		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->x->stream));
+		DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->x->stream);
+		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->x->stream));
 	}
-	DA(&m->d_km_back, pad8(m->bytes[7]), m->stream);
-	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->stream));
+	DA(&m->d_km_back, pad8(m->bytes[7]), m->x->stream);
+	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->x->stream));
 	const uint64_t words = cell_words(m->bytes[6]);
 	for (int i = 0; i < m->n_bits; i++) {
-		DA(&m->d_cells[i], (words + 1) * 8, m->stream);
-		CU(cudaMemsetAsync(m->d_cells[i], 0, (words + 1) * 8, m->stream));
+		DA(&m->d_cells[i], (words + 1) * 8, m->x->stream);
+		CU(cudaMemsetAsync(m->d_cells[i], 0, (words + 1) * 8, m->x->stream));
 	}
 	return KMX_OK;
 }
@@ -297,6 +380,11 @@ static void fill_dev_model(kmx_model* m) {
 	d.rest.k = m->rest.k;
 	d.rest.suffix_bits = 2 * (m->rest.k - m->rest.pre_len);
 	d.rest.suffix_mask = mask2(m->rest.k - m->rest.pre_len);
+	d.rest.fine = m->d_fine;
+	d.rest.quirk_suffix = m->d_quirk_suffix;
+	d.rest.quirk_index = m->d_quirk_index;
+	d.rest.fine_bits = m->fine_bits;
+	d.rest.fine_shift = 2 * m->rest.k - m->fine_bits;
 }
 
 static void fill_info(kmx_model* m) {
@@ -368,46 +456,32 @@ extern "C" kmx_model* kmx_create(int ci, int cs, int n_hash, int n_bits) {
 }
 
 static int model_attach_device(kmx_model* m) {
-	if (m->stream) return KMX_OK;
+	if (m->x) return KMX_OK;
 	int rc = require_gpu(&m->sm_count);
 	if (rc) return rc;
 	m->device = g_device;
-	CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
-	std::vector<uint16_t> o16(m->occ2bin.size());
-	for (size_t i = 0; i < o16.size(); i++) o16[i] = (uint16_t)m->occ2bin[i];
-	for (auto& e : m->ev_build) CU(cudaEventCreate(&e));
-	CU(cudaHostAlloc((void**)&m->h_pinned, sizeof(kmx_model::Pinned), cudaHostAllocDefault));
-	DA(&m->d_occ2bin, o16.size() * 2, m->stream);
-	DA(&m->d_bin2mean, m->bin2mean.size() * 4, m->stream);
-	CU(cudaMemcpyAsync(m->d_occ2bin, o16.data(), o16.size() * 2, cudaMemcpyHostToDevice, m->stream));
-	CU(cudaMemcpyAsync(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice, m->stream));
-	CU(cudaStreamSynchronize(m->stream));
+	if ((rc = ctx_acquire(&m->x))) return rc;
+	m->occ2bin16.resize(m->occ2bin.size());
+	for (size_t i = 0; i < m->occ2bin16.size(); i++) m->occ2bin16[i] = (uint16_t)m->occ2bin[i];
+	DA(&m->d_occ2bin, m->occ2bin16.size() * 2, m->x->stream);
+	DA(&m->d_bin2mean, m->bin2mean.size() * 4, m->x->stream);
+	// both sources live as long as the model; kernels that read the tables run on the same stream
+	CU(cudaMemcpyAsync(m->d_occ2bin, m->occ2bin16.data(), m->occ2bin16.size() * 2, cudaMemcpyHostToDevice, m->x->stream));
+	CU(cudaMemcpyAsync(m->d_bin2mean, m->bin2mean.data(), m->bin2mean.size() * 4, cudaMemcpyHostToDevice, m->x->stream));
 	return KMX_OK;
 }
 
 extern "C" void kmx_destroy(kmx_model* m) {
 	if (!m) return;
-	if (m->stream) {
+	if (m->x) {
 		cudaSetDevice(m->device);
-		cudaStreamSynchronize(m->stream);
-		cudaStreamSynchronize(m->stream2);
+		cudaStreamSynchronize(m->x->stream);
+		cudaStreamSynchronize(m->x->stream2);
 		free_model_device(m);
-		dev_free(m->d_occ2bin, m->stream);
-		dev_free(m->d_bin2mean, m->stream);
-		for (int s = 0; s < 2; s++) {
-			cudaFreeHost(m->h_in[s]);
-			cudaFreeHost(m->h_out[s]);
-			dev_free(m->d_in[s], m->stream);
-			dev_free(m->d_out[s], m->stream);
-			if (m->ev_done[s]) cudaEventDestroy(m->ev_done[s]);
-		}
-		for (auto& e : m->ev_build)
-			if (e) cudaEventDestroy(e);
-		cudaFreeHost(m->h_pinned);
-		cudaStreamSynchronize(m->stream);
-		cudaStreamDestroy(m->stream);
-		cudaStreamDestroy(m->stream2);
+		dev_free(m->d_occ2bin, m->x->stream);
+		dev_free(m->d_bin2mean, m->x->stream);
+		ctx_release(m->x);
+		m->x = nullptr;
 	}
 	delete m;
 }
@@ -417,8 +491,8 @@ extern "C" void kmx_info(const kmx_model* m, kmx_info_t* info) {
 }
 
 extern "C" int kmx_model_sync(kmx_model* m) {
-	if (!m || !m->stream) return fail(KMX_ESTATE, "model has no device state");
-	CU(cudaStreamSynchronize(m->stream));
+	if (!m || !m->x) return fail(KMX_ESTATE, "model has no device state");
+	CU(cudaStreamSynchronize(m->x->stream));
 	return KMX_OK;
 }
 
@@ -560,61 +634,62 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 	if (rc) return rc;
 	db->device = g_device;
 	auto t0 = std::chrono::high_resolution_clock::now();
-	if (!db->stream) CU(cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking));
+	DevCtx* x = nullptr;
+	if ((rc = ctx_acquire(&x))) return rc;
+	struct Release {
+		DevCtx* x;
+		~Release() { ctx_release(x); }
+	} release{ x };
 	std::lock_guard<std::mutex> lock(g_bounce.mu);
 	if ((rc = g_bounce.acquire())) return rc;
-	DA(&db->d_suf, db->suf_alloc, db->stream);
-	DA(&db->d_lut, db->lut.size() * 8, db->stream);
-	CU(cudaMemcpyAsync(db->d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, db->stream));
+	DA(&db->d_suf, db->suf_alloc, x->stream);
+	DA(&db->d_lut, db->lut.size() * 8, x->stream);
+	CU(cudaMemcpyAsync(db->d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, x->stream));
 	const uint64_t bytes = db->info.suffix_bytes;
-	CU(cudaMemsetAsync(db->d_suf + (bytes & ~15ULL), 0, db->suf_alloc - (bytes & ~15ULL), db->stream));
-	CU(cudaStreamSynchronize(db->stream));               // the allocation is usable from the reader streams now
+	CU(cudaMemsetAsync(db->d_suf + (bytes & ~15ULL), 0, db->suf_alloc - (bytes & ~15ULL), x->stream));
+	CU(cudaStreamSynchronize(x->stream));                // the allocation is usable from the reader streams now
+	TRACE(t0, "upload: buffers ready");
 	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
 	const int n_thr = (int)std::min<uint64_t>(kReaders, n_chunks);
-	std::vector<std::thread> pool;
 	std::vector<int> status(kReaders, KMX_OK);
-	for (int t = 0; t < n_thr; t++) {
-		pool.emplace_back([&, t]() {
-			cudaSetDevice(db->device);
-			cudaStream_t st;
-			cudaEvent_t ev[kSlotsPerReader];
-			if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { status[t] = KMX_ECUDA; return; }
-			for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-			int slot = 0;
-			for (uint64_t c = t; c < n_chunks && status[t] == KMX_OK; c += n_thr, slot ^= 1) {
-				const uint64_t off = c * kChunk, len = std::min<uint64_t>(kChunk, bytes - off);
-				cudaEventSynchronize(ev[slot]);                // the previous copy out of this slot is done
-				uint8_t* b = g_bounce.buf[t][slot];
-				uint64_t got = 0;
-				while (got < len) {
-					ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + off + got));
-					if (r <= 0) { status[t] = KMX_EIO; break; }
-					got += (uint64_t)r;
-				}
-				if (status[t] != KMX_OK) break;
-				if (cudaMemcpyAsync(db->d_suf + off, b, len, cudaMemcpyHostToDevice, st) != cudaSuccess) { status[t] = KMX_ECUDA; break; }
-				cudaEventRecord(ev[slot], st);
+	auto work = [&](int t) {
+		cudaSetDevice(db->device);
+		cudaStream_t st = x->reader[t];
+		int slot = 0;
+		for (uint64_t c = t; c < n_chunks && status[t] == KMX_OK; c += n_thr, slot ^= 1) {
+			const uint64_t off = c * kChunk, len = std::min<uint64_t>(kChunk, bytes - off);
+			cudaEventSynchronize(x->reader_ev[t][slot]);       // the previous copy out of this slot is done
+			uint8_t* b = g_bounce.buf[t][slot];
+			uint64_t got = 0;
+			while (got < len) {
+				ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + off + got));
+				if (r <= 0) { status[t] = KMX_EIO; break; }
+				got += (uint64_t)r;
 			}
-			if (cudaStreamSynchronize(st) != cudaSuccess && status[t] == KMX_OK) status[t] = KMX_ECUDA;
-			for (auto& e : ev) cudaEventDestroy(e);
-			cudaStreamDestroy(st);
-		});
-	}
+			if (status[t] != KMX_OK) break;
+			if (cudaMemcpyAsync(db->d_suf + off, b, len, cudaMemcpyHostToDevice, st) != cudaSuccess) { status[t] = KMX_ECUDA; break; }
+			cudaEventRecord(x->reader_ev[t][slot], st);
+		}
+		if (cudaStreamSynchronize(st) != cudaSuccess && status[t] == KMX_OK) status[t] = KMX_ECUDA;
+	};
+	std::vector<std::thread> pool;
+	for (int t = 1; t < n_thr; t++) pool.emplace_back(work, t);
+	if (n_thr > 0) work(0);
 	for (auto& th : pool) th.join();
 	for (int t = 0; t < n_thr; t++)
 		if (status[t] != KMX_OK) return fail(status[t], status[t] == KMX_EIO ? "short read on the .kmc_suf file" : "host-to-device copy of the database failed");
 	db->ms_upload = (float)(1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count());
+	TRACE(t0, "upload: done");
 	return KMX_OK;
 }
 
 extern "C" void kmx_db_close(kmx_db* db) {
 	if (!db) return;
-	if (db->stream) {
+	if (db->d_suf || db->d_lut) {
 		cudaSetDevice(db->device);
-		dev_free(db->d_suf, db->stream);
-		dev_free(db->d_lut, db->stream);
-		cudaStreamSynchronize(db->stream);
-		cudaStreamDestroy(db->stream);
+		cudaDeviceSynchronize();
+		dev_free(db->d_suf, nullptr);
+		dev_free(db->d_lut, nullptr);
 	}
 	if (db->fd >= 0) close(db->fd);
 	delete db;
@@ -650,7 +725,13 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 	uint64_t* d_off = nullptr;
 	uint64_t* d_k = nullptr;
 	uint32_t* d_c = nullptr;
-	cudaStream_t s = db->stream;
+	DevCtx* x = nullptr;
+	if ((rc = ctx_acquire(&x))) return rc;
+	struct Release {
+		DevCtx* x;
+		~Release() { ctx_release(x); }
+	} release{ x };
+	cudaStream_t s = x->stream;
 	DA(&d_cnt, n_tiles * 4, s);
 	DA(&d_off, (n_tiles + 1) * 8, s);
 	DA(&d_k, total * 8, s);
@@ -666,6 +747,7 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 	CU(cudaMemcpyAsync(counts, d_c, listed * 4, cudaMemcpyDeviceToHost, s));
 	CU(cudaStreamSynchronize(s));
 	dev_free(d_cnt, s); dev_free(d_off, s); dev_free(d_k, s); dev_free(d_c, s);
+	CU(cudaStreamSynchronize(s));
 	*n_out = listed;
 	return KMX_OK;
 }
@@ -673,9 +755,25 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 // =========================================================================================
 // build: KModel::init (kmodel.hpp:57-86)
 // =========================================================================================
+// bucket index over the top key bits (about one entry per bucket) + the per-prefix false-hit table
+// that reproduces the inclusive upper bound of KRestData::check_kmer (rest.hpp:233-237)
+static int build_rest_side_tables(kmx_model* m) {
+	const RestHost& r = m->rest;
+	cudaStream_t s = m->x->stream;
+	int bits = 8;
+	while (bits < 26 && bits < 2 * r.k && (1ULL << bits) < r.count) bits++;
+	m->fine_bits = bits;
+	DA(&m->d_fine, ((size_t)(1u << bits) + 1) * 4, s);
+	DA(&m->d_quirk_suffix, (size_t)r.map_size * 8, s);
+	DA(&m->d_quirk_index, (size_t)r.map_size * 4, s);
+	fill_dev_model(m);
+	CU(launch_rest_side_tables(m->dm.rest, r.map_size, m->d_fine, m->d_quirk_suffix, m->d_quirk_index, s));
+	return KMX_OK;
+}
+
 static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups) {
 	RestHost& r = m->rest;
-	cudaStream_t s = m->stream;
+	cudaStream_t s = m->x->stream;
 	r.k = m->k;
 	r.pre_len = rest_prefix_len(m->k);                    // rest.hpp:140-149
 	r.map_size = 1 << (2 * r.pre_len);
@@ -707,9 +805,11 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	auto wall0 = std::chrono::high_resolution_clock::now();
 	int rc = model_attach_device(m);
 	if (rc) return rc;
+	TRACE(wall0, "device attached");
 	CU(cudaSetDevice(m->device));
 	rc = kmx_db_upload(db);
 	if (rc) return rc;
+	TRACE(wall0, "database on device");
 	if (db->device != m->device) return fail(KMX_EARG, "database is on device %d, model on device %d", db->device, m->device);
 	m->k = (int)db->info.k;
 	m->total_kmers = db->info.total_kmers;
@@ -717,8 +817,8 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	const uint64_t total = m->total_kmers;
 	const uint64_t n_tiles = (total + kTile - 1) / kTile;
 	DevDb d = dev_db(db);
-	cudaStream_t s = m->stream;
-	cudaEvent_t* ev = m->ev_build;
+	cudaStream_t s = m->x->stream;
+	cudaEvent_t* ev = m->x->ev_build;
 
 	// ---- pass 1: class histogram (kmodel.hpp:423-434) ----
 	uint32_t* d_tile_cnt = nullptr;
@@ -731,10 +831,12 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	CU(cudaMemsetAsync(d_count, 0, sizeof(CountOut), s));
 	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, m->sm_count, s));
 	CU(launch_tile_scan(d_tile_cnt, n_tiles, d_tile_off, s));
-	CountOut& cnt = m->h_pinned->count;
+	CountOut& cnt = m->x->h_pinned->count;
 	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, s));
 	CU(cudaEventRecord(ev[1], s));
+	TRACE(wall0, "count pass queued");
 	CU(cudaStreamSynchronize(s));                        // sync 1 of 3: the sizes depend on the counts
+	TRACE(wall0, "count pass done");
 	dev_free(d_tile_cnt, s);
 	dev_free(d_count, s);
 	if (cnt.bad_count) {
@@ -772,7 +874,7 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	const uint64_t n_batches = (n_items + batch_items - 1) / batch_items;
 	InsertArgs a;
 	memset(&a, 0, sizeof(a));
-	InsertCtl& ctl = m->h_pinned->ctl;
+	InsertCtl& ctl = m->x->h_pinned->ctl;
 	memset(&ctl, 0, sizeof(ctl));
 	if (n_items > 0) {
 		a.item_kmer = d_item_kmer;
@@ -785,6 +887,8 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		DA(&a.status, batch_items * 4, s);
 		DA(&a.rank, batch_items * 4, s);
 		DA(&a.holepos, batch_items * 4, s);
+		DA(&a.list[0], batch_items * 4, s);
+		DA(&a.list[1], batch_items * 4, s);
 		DA(&a.tile_fail, batch_items / 256 * 4, s);
 		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
 		a.resv_slots = 1u << 22;
@@ -840,7 +944,9 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 	}
 	CU(cudaEventRecord(ev[3], s));
+	TRACE(wall0, "encode + insert queued");
 	CU(cudaStreamSynchronize(s));                        // sync 2 of 3: the sort needs the survivor count
+	TRACE(wall0, "insert done");
 	if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
 	dev_free(d_item_kmer, s);
 	dev_free(d_item_occ, s);
@@ -848,16 +954,20 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		dev_free(a.buf_kmer[b], s);
 		dev_free(a.buf_occ[b], s);
 	}
-	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.ctl, s);
+	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.ctl, s);
 
 	// ---- rest table (rest.hpp:157-161) ----
-	int32_t& groups = m->h_pinned->groups;
+	int32_t& groups = m->x->h_pinned->groups;
 	rc = build_rest_table(m, a.rest_kmer, a.rest_occ, ctl.rest_n, &groups);
 	if (rc) return rc;
 	dev_free(a.rest_kmer, s);
 	dev_free(a.rest_occ, s);
+	rc = build_rest_side_tables(m);
+	if (rc) return rc;
 	CU(cudaEventRecord(ev[4], s));
+	TRACE(wall0, "rest table queued");
 	CU(cudaStreamSynchronize(s));                        // sync 3 of 3
+	TRACE(wall0, "rest table done");
 	m->rest.pre_buffer_size = groups + 1;                 // rest.hpp:119: new int[++pre_buffer_size]
 	fill_dev_model(m);
 	m->built = true;
@@ -905,7 +1015,7 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 	if (!m || !dir) return fail(KMX_EARG, "null argument");
 	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
 	CU(cudaSetDevice(m->device));
-	CU(cudaStreamSynchronize(m->stream));
+	CU(cudaStreamSynchronize(m->x->stream));
 	std::string base(dir);
 	FILE* fh = fopen((base + "/header").c_str(), "w");
 	if (!fh) return fail(KMX_EIO, "cannot write %s/header (%s); the directory must exist (README.md:77)", dir, strerror(errno));
@@ -930,8 +1040,8 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 			rc = fail(KMX_ECUDA, "out of device memory while saving");
 	}
 	for (int i = 0; i < m->n_bits && !rc; i++) {
-		cudaError_t e = launch_split_cells(m->d_cells[i], words, d_val, d_tag, m->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+		cudaError_t e = launch_split_cells(m->d_cells[i], words, d_val, d_tag, m->x->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(m->x->stream);
 		if (e != cudaSuccess) rc = fail(KMX_ECUDA, "split kernel: %s", cudaGetErrorString(e));
 		if (!rc) rc = write_device(f, d_val, m->bytes[6], tmp);      // bit_array_1
 		if (!rc) rc = write_device(f, d_tag, m->bytes[6], tmp);      // bit_array_2
@@ -1000,24 +1110,24 @@ static int load_into(kmx_model* m, const std::string& base) {
 		return fail(KMX_EFORMAT, "%s/km.bin: truncated header", base.c_str());
 	}
 	rc = alloc_filters(m);
-	if (!rc && cudaStreamSynchronize(m->stream) != cudaSuccess) rc = fail(KMX_ECUDA, "zero-fill of the filters failed");   // the copies below run on the default stream
+	if (!rc && cudaStreamSynchronize(m->x->stream) != cudaSuccess) rc = fail(KMX_ECUDA, "zero-fill of the filters failed");   // the copies below run on the default stream
 	std::vector<uint8_t> tmp;
 	for (int i = 0; i < m->bf_num && !rc; i++) {
-		rc = read_to_device(f, m->d_bf[i], m->bytes[i], tmp, m->stream);
-		if (!rc) rc = read_to_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp, m->stream);
+		rc = read_to_device(f, m->d_bf[i], m->bytes[i], tmp, m->x->stream);
+		if (!rc) rc = read_to_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp, m->x->stream);
 	}
-	if (!rc) rc = read_to_device(f, m->d_km_back, m->bytes[7], tmp, m->stream);
+	if (!rc) rc = read_to_device(f, m->d_km_back, m->bytes[7], tmp, m->x->stream);
 	const uint64_t words = cell_words(m->bytes[6]);
 	uint32_t* d_val = nullptr;
 	uint32_t* d_tag = nullptr;
 	if (!rc && (cudaMalloc(&d_val, (words + 2) * 4) != cudaSuccess || cudaMalloc(&d_tag, (words + 2) * 4) != cudaSuccess))
 		rc = fail(KMX_ECUDA, "out of device memory while loading");
 	for (int i = 0; i < m->n_bits && !rc; i++) {
-		rc = read_to_device(f, d_val, m->bytes[6], tmp, m->stream);
-		if (!rc) rc = read_to_device(f, d_tag, m->bytes[6], tmp, m->stream);
+		rc = read_to_device(f, d_val, m->bytes[6], tmp, m->x->stream);
+		if (!rc) rc = read_to_device(f, d_tag, m->bytes[6], tmp, m->x->stream);
 		if (!rc) {
-			cudaError_t e = launch_merge_cells(d_val, d_tag, words, m->d_cells[i], m->stream);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+			cudaError_t e = launch_merge_cells(d_val, d_tag, words, m->d_cells[i], m->x->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(m->x->stream);
 			if (e != cudaSuccess) rc = fail(KMX_ECUDA, "merge kernel: %s", cudaGetErrorString(e));
 		}
 	}
@@ -1062,14 +1172,16 @@ static int load_into(kmx_model* m, const std::string& base) {
 		}
 	}
 	m->k = r.k;
-	DA(&m->d_hash2index, (size_t)r.map_size * 4, m->stream);
-	DA(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4, m->stream);
-	DA(&m->d_rest_keys, (r.count + 1) * 8, m->stream);
-	DA(&m->d_rest_counts, (r.count + 1) * 4, m->stream);
-	if ((rc = h2d_sync(m->d_hash2index, h2i.data(), h2i.size() * 4, m->stream))) return rc;
-	if ((rc = h2d_sync(m->d_pre_buffer, pre.data(), pre.size() * 4, m->stream))) return rc;
-	if ((rc = h2d_sync(m->d_rest_keys, keys.data(), r.count * 8, m->stream))) return rc;
-	if ((rc = h2d_sync(m->d_rest_counts, counts.data(), r.count * 4, m->stream))) return rc;
+	DA(&m->d_hash2index, (size_t)r.map_size * 4, m->x->stream);
+	DA(&m->d_pre_buffer, ((size_t)r.pre_buffer_size + 1) * 4, m->x->stream);
+	DA(&m->d_rest_keys, (r.count + 1) * 8, m->x->stream);
+	DA(&m->d_rest_counts, (r.count + 1) * 4, m->x->stream);
+	if ((rc = h2d_sync(m->d_hash2index, h2i.data(), h2i.size() * 4, m->x->stream))) return rc;
+	if ((rc = h2d_sync(m->d_pre_buffer, pre.data(), pre.size() * 4, m->x->stream))) return rc;
+	if ((rc = h2d_sync(m->d_rest_keys, keys.data(), r.count * 8, m->x->stream))) return rc;
+	if ((rc = h2d_sync(m->d_rest_counts, counts.data(), r.count * 4, m->x->stream))) return rc;
+	if ((rc = build_rest_side_tables(m))) return rc;
+	CU(cudaStreamSynchronize(m->x->stream));
 	fill_dev_model(m);
 	fill_info(m);
 	m->built = true;
@@ -1109,41 +1221,67 @@ extern "C" kmx_model* kmx_load(const char* dir) {
 // =========================================================================================
 // retrieval (kmodel.hpp:90-116)
 // =========================================================================================
-extern "C" int kmx_query_packed_device(kmx_model* m, const uint64_t* d_kmers, size_t n, int32_t* d_out, void* stream) {
-	if (!m || (n && (!d_kmers || !d_out))) return fail(KMX_EARG, "null argument");
+// device-resident batches: in steps of 16 Mi queries so that the deferred-query list (sized for the
+// worst case, every query deferred) stays at 256 MiB; the list comes from the stream-ordered pool
+template <bool ASCII>
+static int query_device(kmx_model* m, const void* d_in, size_t stride, size_t n, int32_t* d_out, void* stream) {
+	if (!m || (n && (!d_in || !d_out))) return fail(KMX_EARG, "null argument");
 	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	if (ASCII && stride < (size_t)m->k) return fail(KMX_EARG, "stride %zu shorter than k=%d", stride, m->k);
 	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
-	CU(launch_query_packed(m->dm, d_kmers, n, d_out, nullptr, m->sm_count, stream ? (cudaStream_t)stream : m->stream));
+	if (n == 0) return KMX_OK;
+	cudaStream_t s = stream ? (cudaStream_t)stream : m->x->stream;
+	const size_t step = 1u << 24;
+	DeferredQuery* d_defer = nullptr;
+	unsigned int* d_defer_n = nullptr;
+	DA(&d_defer, std::min(n, step) * sizeof(DeferredQuery), s);
+	DA(&d_defer_n, sizeof(unsigned int), s);
+	for (size_t off = 0; off < n; off += step) {
+		const size_t cnt = std::min(step, n - off);
+		if (ASCII) CU(launch_query_ascii(m->dm, (const char*)d_in + off * stride, stride, cnt, d_out + off, d_defer, d_defer_n, m->sm_count, s));
+		else CU(launch_query_packed(m->dm, (const uint64_t*)d_in + off, cnt, d_out + off, nullptr, d_defer, d_defer_n, m->sm_count, s));
+	}
+	dev_free(d_defer, s);
+	dev_free(d_defer_n, s);
 	return KMX_OK;
+}
+
+extern "C" int kmx_query_packed_device(kmx_model* m, const uint64_t* d_kmers, size_t n, int32_t* d_out, void* stream) {
+	return query_device<false>(m, d_kmers, 8, n, d_out, stream);
 }
 
 extern "C" int kmx_query_ascii_device(kmx_model* m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, void* stream) {
-	if (!m || (n && (!d_flat || !d_out))) return fail(KMX_EARG, "null argument");
-	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
-	if (stride < (size_t)m->k) return fail(KMX_EARG, "stride %zu shorter than k=%d", stride, m->k);
-	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
-	CU(launch_query_ascii(m->dm, d_flat, stride, n, d_out, m->sm_count, stream ? (cudaStream_t)stream : m->stream));
-	return KMX_OK;
+	return query_device<true>(m, d_flat, stride, n, d_out, stream);
 }
 
-static int ensure_staging(kmx_model* m, size_t item_bytes) {
+static int ensure_staging(kmx_model* m, size_t item_bytes, bool need_h_in, bool need_h_out) {
+	DevCtx* x = m->x;
 	const size_t items = 1u << 22;                         // queries per pipeline step
 	const size_t bytes = items * item_bytes;
-	if (m->stage_bytes >= bytes && m->stage_items == items) return KMX_OK;
+	x->stage_items = items;
+	bool fresh = false;
 	for (int s = 0; s < 2; s++) {
-		cudaFreeHost(m->h_in[s]); dev_free(m->d_in[s], m->stream);
-		m->h_in[s] = nullptr; m->d_in[s] = nullptr;
-		CU(cudaMallocHost(&m->h_in[s], bytes));
-		DA(&m->d_in[s], bytes, m->stream);
-		if (!m->h_out[s]) {
-			CU(cudaMallocHost((void**)&m->h_out[s], items * 4));
-			DA(&m->d_out[s], items * 4, m->stream);
-			CU(cudaEventCreateWithFlags(&m->ev_done[s], cudaEventDisableTiming));
+		if (x->stage_bytes < bytes) {
+			dev_free(x->d_in[s], x->stream);
+			x->d_in[s] = nullptr;
+			DA(&x->d_in[s], bytes, x->stream);
+			if (x->h_in[s]) {
+				cudaFreeHost(x->h_in[s]);
+				x->h_in[s] = nullptr;
+			}
+			fresh = true;
+		}
+		if (need_h_in && !x->h_in[s]) CU(cudaMallocHost(&x->h_in[s], std::max(bytes, x->stage_bytes)));
+		if (need_h_out && !x->h_out[s]) CU(cudaMallocHost((void**)&x->h_out[s], items * 4));
+		if (!x->d_out[s]) {
+			DA(&x->d_out[s], items * 4, x->stream);
+			DA(&x->d_defer[s], items * sizeof(DeferredQuery), x->stream);
+			DA(&x->d_defer_n[s], sizeof(unsigned int), x->stream);
+			fresh = true;
 		}
 	}
-	CU(cudaStreamSynchronize(m->stream));                 // the staging buffers are used from both streams
-	m->stage_bytes = bytes;
-	m->stage_items = items;
+	if (x->stage_bytes < bytes) x->stage_bytes = bytes;
+	if (fresh) CU(cudaStreamSynchronize(x->stream));      // the staging buffers are used from both streams
 	return KMX_OK;
 }
 
@@ -1164,38 +1302,39 @@ static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t st
 	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
 	if (n == 0) return KMX_OK;
 	CU(cudaSetDevice(m->device));
-	int rc = ensure_staging(m, item_bytes);
-	if (rc) return rc;
 	int32_t* res = path ? path : out;
 	const bool in_pinned = is_pinned(in), out_pinned = is_pinned(res);
-	cudaStream_t st[2] = { m->stream, m->stream2 };
+	int rc = ensure_staging(m, item_bytes, !in_pinned, !out_pinned);
+	if (rc) return rc;
+	cudaStream_t st[2] = { m->x->stream, m->x->stream2 };
 	size_t done_off[2] = { 0, 0 }, done_n[2] = { 0, 0 };
 	const uint8_t* src = (const uint8_t*)in;
 	int slot = 0;
-	for (size_t off = 0; off < n; off += m->stage_items, slot ^= 1) {
-		const size_t cnt = std::min(m->stage_items, n - off);
+	for (size_t off = 0; off < n; off += m->x->stage_items, slot ^= 1) {
+		const size_t cnt = std::min(m->x->stage_items, n - off);
 		if (done_n[slot]) {                                // slot busy with an earlier step: drain it
-			CU(cudaEventSynchronize(m->ev_done[slot]));
-			if (!out_pinned) memcpy(res + done_off[slot], m->h_out[slot], done_n[slot] * 4);
+			CU(cudaEventSynchronize(m->x->ev_done[slot]));
+			if (!out_pinned) memcpy(res + done_off[slot], m->x->h_out[slot], done_n[slot] * 4);
 			done_n[slot] = 0;
 		}
 		const void* h_src = src + off * item_bytes;
 		if (!in_pinned) {
-			memcpy(m->h_in[slot], h_src, cnt * item_bytes);
-			h_src = m->h_in[slot];
+			memcpy(m->x->h_in[slot], h_src, cnt * item_bytes);
+			h_src = m->x->h_in[slot];
 		}
-		CU(cudaMemcpyAsync(m->d_in[slot], h_src, cnt * item_bytes, cudaMemcpyHostToDevice, st[slot]));
-		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->d_in[slot], stride, cnt, m->d_out[slot], m->sm_count, st[slot]));
-		else CU(launch_query_packed(m->dm, (const uint64_t*)m->d_in[slot], cnt, path ? nullptr : m->d_out[slot], path ? m->d_out[slot] : nullptr, m->sm_count, st[slot]));
-		CU(cudaMemcpyAsync(out_pinned ? (void*)(res + off) : (void*)m->h_out[slot], m->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st[slot]));
-		CU(cudaEventRecord(m->ev_done[slot], st[slot]));
+		CU(cudaMemcpyAsync(m->x->d_in[slot], h_src, cnt * item_bytes, cudaMemcpyHostToDevice, st[slot]));
+		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->x->d_in[slot], stride, cnt, m->x->d_out[slot], m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
+		else CU(launch_query_packed(m->dm, (const uint64_t*)m->x->d_in[slot], cnt, path ? nullptr : m->x->d_out[slot], path ? m->x->d_out[slot] : nullptr,
+		                            m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
+		CU(cudaMemcpyAsync(out_pinned ? (void*)(res + off) : (void*)m->x->h_out[slot], m->x->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st[slot]));
+		CU(cudaEventRecord(m->x->ev_done[slot], st[slot]));
 		done_off[slot] = off;
 		done_n[slot] = cnt;
 	}
 	for (int s = 0; s < 2; s++) {
 		if (done_n[s]) {
-			CU(cudaEventSynchronize(m->ev_done[s]));
-			if (!out_pinned) memcpy(res + done_off[s], m->h_out[s], done_n[s] * 4);
+			CU(cudaEventSynchronize(m->x->ev_done[s]));
+			if (!out_pinned) memcpy(res + done_off[s], m->x->h_out[s], done_n[s] * 4);
 		}
 	}
 	return KMX_OK;

@@ -8,10 +8,19 @@
 namespace kmx {
 
 // ---- query (kmx_query.cu) ------------------------------------------------------------------
+struct DeferredQuery {               // a query whose answer needs its 8 neighbours
+	uint64_t kmer;                   // canonical form
+	uint32_t index;                  // position in the batch
+	uint32_t pad;
+};
+// d_defer needs room for n entries (worst case: every query is deferred); d_defer_n is one counter
 cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
-                                int sm_count, cudaStream_t stream);
-cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, int sm_count,
-                               cudaStream_t stream);
+                                DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream);
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, DeferredQuery* d_defer,
+                               unsigned int* d_defer_n, int sm_count, cudaStream_t stream);
+// bucket index + false-hit table of the rest table (R.keys/hash2index/pre_buffer/fine_bits set)
+cudaError_t launch_rest_side_tables(const DevRest& R, int map_size, uint32_t* d_fine, uint64_t* d_quirk_suffix, uint32_t* d_quirk_index,
+                                    cudaStream_t stream);
 
 // ---- build (kmx_build.cu) ------------------------------------------------------------------
 constexpr int kTile = 2048;          // records decoded per block step (256 threads x 8)
@@ -41,7 +50,7 @@ cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_coun
 struct InsertCtl {                    // lives in device memory, survives across launches
 	unsigned long long rest_n;        // survivors appended to the rest list so far
 	unsigned long long attempts, accepted, iterations;
-	unsigned int undecided[3];        // rotating per-iteration counters
+	unsigned int list_n[2];           // entries of the two undecided-item lists
 	unsigned int epoch;               // reservation epoch (keys of newer epochs are smaller)
 	unsigned int error;               // non-zero: iteration cap hit / rest overflow
 	unsigned int nfail[kMaxArrays];   // survivors of each bucket after the current round
@@ -62,6 +71,7 @@ struct InsertArgs {
 	uint32_t* rank;                   // [n_bits * kBucket]
 	uint32_t* holepos;                // [n_bits * kBucket]
 	uint32_t* tile_fail;              // [n_bits * kBucket / 256]
+	uint32_t* list[2];                // [n_bits * kBucket] ids still undecided, ping-pong
 	uint32_t* resv;                   // [n_bits][2 * resv_slots]
 	uint32_t resv_slots;              // power of two
 	uint64_t* rest_kmer;              // survivors of all batches

@@ -1,4 +1,4 @@
-// kmx_query.cu -- batched KModel::kmer_to_occ on the device (one thread per query).
+// kmx_query.cu -- batched KModel::kmer_to_occ on the device.
 //
 // Reference path reproduced (file:line relative to the reference root):
 //   kmodel.hpp:100-116  kmer_to_occ(string)          kmodel.hpp:286-323  kmer_to_bin
@@ -7,11 +7,17 @@
 //   kmodel.hpp:625-671  find_bitarray / _one         rest.hpp:223-251    KRestData::check_kmer
 //   tools.hpp:160-167   get_min_kmer                 occu_bin.hpp:67-83  occ_to_bin / bin_to_mean
 //
+// Two kernels.  query_fast_kernel (one thread per query) answers every query whose answer
+// does not need the neighbours; the others (a Bloom hit next to one array candidate, or several
+// array candidates: <1 % of a typical batch, but 9x the work) are appended to a list that
+// query_slow_kernel works off with 8 lanes per query, one per neighbour, so that a warp of the
+// fast kernel never waits for a single lane walking 8 neighbours.
+//
 // All probes of a stage are issued before any of them is tested (the reference short-circuits,
 // but a probe has no side effect, so the answer is the same): the Bloom/km_back probes form one
-// wave of independent 4-byte loads, the n_bits*n_hash coupled-array probes one wave of 8-byte
-// loads.  The hash of a (string, seed) pair is computed once and reduced modulo each filter
-// length it is used with: seeds 0..n_hash-2 serve every Bloom filter and the first array.
+// wave of independent 4-byte loads that overlaps the rest-table lookup, the n_bits*n_hash
+// coupled-array probes one wave of 8-byte loads.  The hash of a (string, seed) pair is computed
+// once and reduced modulo each filter length it is used with.
 #include <cuda_runtime.h>
 #include "kmx_device.cuh"
 #include "kmx_launch.h"
@@ -30,10 +36,28 @@ struct QueryCfg {
 __host__ __device__ constexpr int kHmax(int H) { return H ? H : kMaxHash; }
 __host__ __device__ constexpr int kBmax(int B) { return B ? B : kMaxArrays; }
 
+// the seed-dependent hashes every stage shares: seeds 0..H-2 on the k-mer, 0..H-3 on the (k-2)-mer
+template <int K, int H, int B>
+struct QueryHashes {
+	HashPrep p31;
+	uint64_t h31[kHmax(H) - 1], h29[kHmax(H) - 2];
+	__device__ __forceinline__ void compute(const QueryCfg<K, H, B>& c, uint64_t r) {
+		HashPrep p29;
+		hash_prepare(r, c.k(), p31);
+		hash_prepare(middle_r(r, c.k()), c.k() - 2, p29);
+#pragma unroll
+		for (int j = 0; j < kHmax(H) - 1; j++)
+			if (j < c.h() - 1) h31[j] = hash_finish(p31, c.k(), c_seeds[j]);
+#pragma unroll
+		for (int j = 0; j < kHmax(H) - 2; j++)
+			if (j < c.h() - 2) h29[j] = hash_finish(p29, c.k() - 2, c_seeds[j]);
+	}
+};
+
 // check_all_bf (kmodel.hpp:361-371): first filter pair, in the order {0} (ci == 1) or {1,0,2},
 // whose k-mer filter (n_hash-1 hashes) and back filter (n_hash-2 hashes) both hit -> i + ci
 template <int K, int H, int B>
-__device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const uint64_t* h31, const uint64_t* h29) {
+__device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q) {
 	const DevModel& m = c.m;
 	const int hb = c.h() - 1, hk = c.h() - 2;
 	bool hit[kMaxBf];
@@ -44,10 +68,10 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const ui
 			bool ok = true;
 #pragma unroll
 			for (int j = 0; j < kHmax(H) - 1; j++)
-				if (j < hb) ok &= filter_test(m.bf[i], h31[j]);
+				if (j < hb) ok &= filter_test(m.bf[i], q.h31[j]);
 #pragma unroll
 			for (int j = 0; j < kHmax(H) - 2; j++)
-				if (j < hk) ok &= filter_test(m.bf_back[i], h29[j]);
+				if (j < hk) ok &= filter_test(m.bf_back[i], q.h29[j]);
 			hit[i] = ok;
 		}
 	}
@@ -59,36 +83,34 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const ui
 }
 
 template <int K, int H, int B>
-__device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B>& c, const uint64_t* h29) {
+__device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q) {
 	const int hk = c.h() - 2;
 	bool ok = true;
 #pragma unroll
 	for (int j = 0; j < kHmax(H) - 2; j++)
-		if (j < hk) ok &= filter_test(c.m.km_back, h29[j]);
+		if (j < hk) ok &= filter_test(c.m.km_back, q.h29[j]);
 	return ok;
 }
 
-// all seeds the coupled arrays use on the k-mer string: array i, hash j -> HashSeeds[(i*H+j)%128]
-// (kmodel.hpp:450-453).  For i*H+j < 128 that is simply seed number i*H+j.
+// probe every coupled array (kmodel.hpp:625-671): are all tag bits set, and which bin do the value
+// bits spell (tools.hpp:54-61).  Array i, hash j uses HashSeeds[(i*H+j)%128] (kmodel.hpp:450-453);
+// for i == 0 those are the seeds whose hashes are already in q.h31.
 template <int K, int H, int B>
-__device__ __forceinline__ uint64_t array_hash(const QueryCfg<K, H, B>& c, const HashPrep& p31, int i, int j) {
-	return hash_finish(p31, c.k(), c.m.arr_seed[i][j]);
-}
-
-// decode array i: tag bits all set? and the bin spelled by the value bits (tools.hpp:54-61)
-template <int K, int H, int B>
-__device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const HashPrep& p31, int* bins, bool* full) {
+__device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q, int* bins, bool* full) {
 	const DevModel& m = c.m;
 	unsigned long long cell[kBmax(B)][kHmax(H)];
-	uint32_t sh[kBmax(B)][kHmax(H)];
+	unsigned long long sh[kBmax(B)];        // 5 bits per hash (n_hash <= 12 fits), packed
 #pragma unroll
 	for (int i = 0; i < kBmax(B); i++) {
+		sh[i] = 0;
 #pragma unroll
 		for (int j = 0; j < kHmax(H); j++) {
 			if (i < c.b() && j < c.h()) {
-				uint64_t pos = fastmod(array_hash(c, p31, i, j), m.arr_mod);
-				sh[i][j] = ((uint32_t)pos & 31u) ^ 7u;
+				const uint64_t h = (i == 0 && j < c.h() - 1) ? q.h31[j < kHmax(H) - 1 ? j : 0] : hash_finish(q.p31, c.k(), m.arr_seed[i][j]);
+				const uint64_t pos = fastmod(h, m.arr_mod);
+				if (j < 12) sh[i] |= (unsigned long long)(((uint32_t)pos & 31u) ^ 7u) << (5 * j);
 				cell[i][j] = __ldg(m.cells[i] + (pos >> 5));
+				if (j >= 12) cell[i][j] = (cell[i][j] >> (((uint32_t)pos & 31u) ^ 7u)) & 0x100000001ULL;   // n_hash > 12: shift now
 			}
 		}
 	}
@@ -99,9 +121,9 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const H
 #pragma unroll
 		for (int j = 0; j < kHmax(H); j++) {
 			if (i < c.b() && j < c.h()) {
-				uint32_t val = (uint32_t)cell[i][j], tag = (uint32_t)(cell[i][j] >> 32);
-				bin |= (int)((val >> sh[i][j]) & 1u) << j;
-				ok &= ((tag >> sh[i][j]) & 1u) != 0;
+				const unsigned long long x = j < 12 ? (cell[i][j] >> ((uint32_t)(sh[i] >> (5 * j)) & 31u)) : cell[i][j];
+				bin |= (int)((uint32_t)x & 1u) << j;      // bit 0 = value
+				ok &= ((uint32_t)(x >> 32) & 1u) != 0;     // bit 32 = tag
 			}
 		}
 		bins[i] = bin;
@@ -109,163 +131,260 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const H
 	}
 }
 
+// ---- rest table: KRestData::check_kmer (rest.hpp:223-251) ----------------------------------
+// The reference searches [pre_buffer[g], pre_buffer[g+1]] with an INCLUSIVE upper bound.  Its
+// outcome is: the count of an entry of group g whose suffix equals the key's, if there is one
+// (the group is sorted, the extra slot is only probed once everything in the group compared
+// smaller); otherwise, if the key's suffix is larger than every suffix of the group and equals
+// the suffix of the FIRST entry of the next group (the slot the inclusive bound lets in), that
+// entry's count -- the reference's false hit; otherwise 0.  A probe past the last entry is out
+// of bounds there and counts as "no match" here.  Because keys are sorted globally, "in group g
+// with equal suffix" is "equal full key", found through a bucket index over the top key bits;
+// the false-hit suffix of each prefix is precomputed (rest_quirk_kernel).
+__device__ __forceinline__ int rest_lookup_indexed(const DevRest& R, uint64_t v) {
+	const uint32_t b = (uint32_t)(v >> R.fine_shift);
+	uint32_t lo = __ldg(R.fine + b), hi = __ldg(R.fine + b + 1);
+	while (hi - lo > 4) {                          // long bucket (skewed data): bisect down first
+		const uint32_t mid = (lo + hi) >> 1;
+		if (__ldg(R.keys + mid) <= v) lo = mid; else hi = mid;
+	}
+	for (uint32_t e = lo; e < hi; e++)
+		if (__ldg(R.keys + e) == v) return __ldg(R.counts + e);
+	const uint32_t pre = (uint32_t)(v >> R.suffix_bits);
+	if (__ldg(R.quirk_suffix + pre) == (v & R.suffix_mask)) return __ldg(R.counts + __ldg(R.quirk_index + pre));
+	return 0;
+}
+
 // get_candidates (kmodel.hpp:326-342) for one neighbour; returns -1 when it adds nothing
 template <int K, int H, int B>
-__device__ __noinline__ int neighbour_candidate(const DevModel& m, uint64_t nb) {
+__device__ __forceinline__ int neighbour_candidate(const DevModel& m, uint64_t nb) {
 	QueryCfg<K, H, B> c(m);
 	uint64_t r;
-	uint64_t v = canonical(nb, c.k(), &r);
-	int occ = rest_lookup(m.rest, v);
+	const uint64_t v = canonical(nb, c.k(), &r);
+	int occ = rest_lookup_indexed(m.rest, v);
 	if (occ > 0) return (int)__ldg(m.occ2bin + (occ > m.cs ? m.cs : occ));   // occ > cs is out of bounds in the reference
-	HashPrep p31, p29;
-	hash_prepare(r, c.k(), p31);
-	hash_prepare(middle_r(r, c.k()), c.k() - 2, p29);
-	uint64_t h31[kHmax(H)], h29[kHmax(H)];
-#pragma unroll
-	for (int j = 0; j < kHmax(H) - 1; j++)
-		if (j < c.h() - 1) h31[j] = hash_finish(p31, c.k(), c_seeds[j]);
-#pragma unroll
-	for (int j = 0; j < kHmax(H) - 2; j++)
-		if (j < c.h() - 2) h29[j] = hash_finish(p29, c.k() - 2, c_seeds[j]);
-	occ = check_all_bf(c, h31, h29);
+	QueryHashes<K, H, B> q;
+	q.compute(c, r);
+	occ = check_all_bf(c, q);
 	if (occ != 0) return occ;
-	if (!check_km_back(c, h29)) return -1;
+	if (!check_km_back(c, q)) return -1;
 	// find_bitarray_one (kmodel.hpp:650-671): last fully tagged array seen, stopping at the first non-zero bin
 	int bins[kBmax(B)];
 	bool full[kBmax(B)];
-	probe_arrays(c, p31, bins, full);
+	probe_arrays(c, q, bins, full);
 	int result = -1;
 #pragma unroll
-	for (int i = 0; i < kBmax(B); i++) {
+	for (int i = 0; i < kBmax(B); i++)
 		if (i < c.b() && full[i] && (result <= 0)) result = bins[i];
-	}
 	return result;
 }
 
-// get_neighbor_kmer_bin (kmodel.hpp:344-359): successors (drop first base, append A,C,G,T) then
-// predecessors (prepend A,C,G,T, drop last base), on the canonical string of the query
-template <int K, int H, int B>
-__device__ __noinline__ int neighbour_bins(const DevModel& m, uint64_t v, int* cand) {
-	const int k = K ? K : m.k;
-	int n = 0;
-	for (int b = 0; b < 4; b++) {
-		int x = neighbour_candidate<K, H, B>(m, ((v << 2) & mask2(k)) | (uint64_t)b);
-		if (x >= 0) cand[n++] = x;
-	}
-	for (int b = 0; b < 4; b++) {
-		int x = neighbour_candidate<K, H, B>(m, (v >> 2) | ((uint64_t)b << (2 * (k - 1))));
-		if (x >= 0) cand[n++] = x;
-	}
-	return n;
+// neighbour number j of the canonical k-mer v (kmodel.hpp:344-359): j < 4 successors (drop the
+// first base, append ACGT[j]), j >= 4 predecessors (prepend ACGT[j-4], drop the last base)
+__device__ __forceinline__ uint64_t neighbour_of(uint64_t v, int j, int k) {
+	return j < 4 ? (((v << 2) & mask2(k)) | (uint64_t)j) : ((v >> 2) | ((uint64_t)(j - 4) << (2 * (k - 1))));
 }
 
-// kmer_to_occ for one packed k-mer; *path gets the path class documented in kmx.h
+// everything kmer_to_occ decides before it needs the neighbours
+struct Primary {
+	int occ;          // Bloom answer (check_all_bf)
+	int nc;           // array candidates (bins > 0 of fully tagged arrays)
+	int cands[kMaxArrays];
+	int path;
+	int answer;       // final occurrence when path is not 5 / 6
+};
+
 template <int K, int H, int B>
-__device__ __forceinline__ int query_one(const DevModel& m, uint64_t raw, int* path) {
+__device__ __forceinline__ int bin_to_mean(const QueryCfg<K, H, B>& c, int bin) {
+	if (bin < c.m.end1) return bin;
+	return bin < (1 << c.h()) ? __ldg(c.m.bin2mean + bin) : 0;   // unordered_map::operator[] yields 0 for a missing bin
+}
+
+template <int K, int H, int B>
+__device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uint64_t r, Primary& P) {
 	QueryCfg<K, H, B> c(m);
-	const int k = c.k();
-	uint64_t r;
-	uint64_t v = canonical(raw & mask2(k), k, &r);
-	int occ = rest_lookup(m.rest, v);
-	if (occ != 0) {
-		*path = 1;
-		return occ;
+	// the rest lookup's loads and the Bloom wave are independent of each other
+	QueryHashes<K, H, B> q;
+	q.compute(c, r);
+	const bool in_back = check_km_back(c, q);
+	P.occ = check_all_bf(c, q);
+	const int rest = rest_lookup_indexed(m.rest, v);
+	P.nc = 0;
+	if (rest != 0) {                       // kmodel.hpp:104-105
+		P.path = 1;
+		P.answer = rest;
+		return;
 	}
-	HashPrep p31, p29;
-	hash_prepare(r, k, p31);
-	hash_prepare(middle_r(r, k), k - 2, p29);
-	uint64_t h31[kHmax(H)], h29[kHmax(H)];
-#pragma unroll
-	for (int j = 0; j < kHmax(H) - 1; j++)
-		if (j < c.h() - 1) h31[j] = hash_finish(p31, k, c_seeds[j]);
-#pragma unroll
-	for (int j = 0; j < kHmax(H) - 2; j++)
-		if (j < c.h() - 2) h29[j] = hash_finish(p29, k - 2, c_seeds[j]);
-	bool in_back = check_km_back(c, h29);
-	occ = check_all_bf(c, h31, h29);
-	if (!in_back) {
-		*path = 2;
-		return occ;          // kmodel.hpp:109-111: Bloom answer (possibly 0) when km_back misses
+	if (!in_back) {                        // kmodel.hpp:109-111: Bloom answer (possibly 0) when km_back misses
+		P.path = 2;
+		P.answer = P.occ;
+		return;
 	}
 	int bins[kBmax(B)];
 	bool full[kBmax(B)];
-	probe_arrays(c, p31, bins, full);
-	int cands[kBmax(B)];
-	int nc = 0;
+	probe_arrays(c, q, bins, full);
 #pragma unroll
 	for (int i = 0; i < kBmax(B); i++)
-		if (i < c.b() && full[i] && bins[i] > 0) cands[nc++] = bins[i];
-	int bin;
-	if (nc == 0) {
-		*path = 3;
-		bin = occ;
-	} else if (nc == 1) {
-		*path = occ ? 5 : 4;
-		bin = cands[0];
-		if (occ) {
-			int nb[8];
-			int n = neighbour_bins<K, H, B>(m, v, nb);
-			int low = 0;
-			for (int i = 0; i < n; i++) low += nb[i] < m.ci + m.bf_num;
-			if (low >= n / 2) bin = occ;
-		}
+		if (i < c.b() && full[i] && bins[i] > 0) P.cands[P.nc++] = bins[i];
+	if (P.nc == 0) {
+		P.path = 3;
+		P.answer = bin_to_mean(c, P.occ);
+	} else if (P.nc == 1 && P.occ == 0) {
+		P.path = 4;
+		P.answer = bin_to_mean(c, P.cands[0]);
 	} else {
-		*path = 6;
-		int nb[8];
-		int n = neighbour_bins<K, H, B>(m, v, nb);
-		if (n <= 0) {
-			bin = 0;
-		} else {
-			int min_dist = 2 << 20;
-			bin = cands[0];
-			for (int i = 0; i < nc; i++) {
-				int cur = 2 << 20;
-				for (int j = 0; j < n; j++) {
-					int d = cands[i] - nb[j];
-					d = d < 0 ? -d : d;
-					cur = d < cur ? d : cur;
-				}
-				if (min_dist > cur) {
-					min_dist = cur;
-					bin = cands[i];
-				}
-			}
-		}
+		P.path = P.nc == 1 ? 5 : 6;
+		P.answer = 0;
 	}
-	if (bin < m.end1) return bin;
-	return bin < (1 << c.h()) ? __ldg(m.bin2mean + bin) : 0;   // unordered_map::operator[] yields 0 for a missing bin
 }
 
 // 2-bit encode of an ASCII k-mer (tools.hpp:63-76: bytes other than C/G/T encode as A)
 __device__ __forceinline__ uint64_t encode_ascii(const char* s, int k) {
 	uint64_t v = 0;
 	for (int i = 0; i < k; i++) {
-		char ch = s[i];
-		uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
+		const char ch = s[i];
+		const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
 		v = (v << 2) | code;
 	}
 	return v;
 }
 
-template <int K, int H, int B>
-__global__ void __launch_bounds__(256) query_packed_kernel(const __grid_constant__ DevModel m, const uint64_t* __restrict__ kmers,
-                                                           size_t n, int32_t* __restrict__ out, int32_t* __restrict__ path_out) {
+template <int K, int H, int B, bool ASCII>
+__global__ void __launch_bounds__(256, 2) query_fast_kernel(const __grid_constant__ DevModel m, const void* __restrict__ input, size_t stride,
+                                                            size_t n, int32_t* __restrict__ out, int32_t* __restrict__ path_out,
+                                                            DeferredQuery* __restrict__ defer, unsigned int* __restrict__ defer_n) {
+	const int k = K ? K : m.k;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		int path = 0;
-		int occ = query_one<K, H, B>(m, kmers[i], &path);
-		if (out) out[i] = occ;
-		if (path_out) path_out[i] = path;
+		const uint64_t raw = ASCII ? encode_ascii((const char*)input + i * stride, k) : ((const uint64_t*)input)[i];
+		uint64_t r;
+		const uint64_t v = canonical(raw & mask2(k), k, &r);
+		Primary P;
+		query_primary<K, H, B>(m, v, r, P);
+		if (path_out) path_out[i] = P.path;
+		if (P.path >= 5) {
+			// warp-aggregated append
+			const unsigned int active = __activemask();
+			const int lane = threadIdx.x & 31;
+			const int leader = __ffs(active) - 1;
+			unsigned int at = 0;
+			if (lane == leader) at = atomicAdd(defer_n, (unsigned int)__popc(active));
+			at = __shfl_sync(active, at, leader);
+			at += __popc(active & ((1u << lane) - 1u));
+			defer[at].kmer = v;
+			defer[at].index = (uint32_t)i;
+		} else if (out) {
+			out[i] = P.answer;
+		}
 	}
 }
 
+// kmer_to_bin's neighbour rules (kmodel.hpp:286-323), 8 lanes per deferred query
 template <int K, int H, int B>
-__global__ void __launch_bounds__(256) query_ascii_kernel(const __grid_constant__ DevModel m, const char* __restrict__ flat, size_t stride,
-                                                          size_t n, int32_t* __restrict__ out) {
-	const int k = K ? K : m.k;
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		int path = 0;
-		out[i] = query_one<K, H, B>(m, encode_ascii(flat + i * stride, k), &path);
+__global__ void __launch_bounds__(256, 2) query_slow_kernel(const __grid_constant__ DevModel m, const DeferredQuery* __restrict__ defer,
+                                                            const unsigned int* __restrict__ defer_n, int32_t* __restrict__ out) {
+	QueryCfg<K, H, B> c(m);
+	const int k = c.k();
+	const unsigned int n = *defer_n;
+	const unsigned int groups_per_grid = gridDim.x * (blockDim.x / 8);
+	const int sub = threadIdx.x & 7;
+	for (unsigned int base = 0; base < n; base += groups_per_grid) {     // uniform trip count: the shuffles below need the whole warp
+		const unsigned int g = base + blockIdx.x * (blockDim.x / 8) + (threadIdx.x >> 3);
+		const bool live = g < n;
+		const uint64_t v = live ? defer[g].kmer : 0;
+		Primary P;
+		P.nc = 0;
+		P.occ = 0;
+		int x = -1;
+		if (live) {
+			query_primary<K, H, B>(m, v, reverse_bases(v, k), P);           // the same decision the fast kernel took
+			x = neighbour_candidate<K, H, B>(m, neighbour_of(v, sub, k));
+		}
+		// reductions over the 8 lanes of the group
+		int n_cand = x >= 0 ? 1 : 0, n_low = (x >= 0 && x < m.ci + m.bf_num) ? 1 : 0;
+		int dist[kBmax(B)];
+#pragma unroll
+		for (int i = 0; i < kBmax(B); i++) {
+			int d = 2 << 20;
+			if (i < P.nc && x >= 0) {
+				d = P.cands[i] - x;
+				d = d < 0 ? -d : d;
+			}
+			dist[i] = d;
+		}
+#pragma unroll
+		for (int off = 4; off > 0; off >>= 1) {
+			n_cand += __shfl_xor_sync(0xffffffffu, n_cand, off, 8);
+			n_low += __shfl_xor_sync(0xffffffffu, n_low, off, 8);
+#pragma unroll
+			for (int i = 0; i < kBmax(B); i++) {
+				const int o = __shfl_xor_sync(0xffffffffu, dist[i], off, 8);
+				dist[i] = o < dist[i] ? o : dist[i];
+			}
+		}
+		if (live && sub == 0) {
+			int bin;
+			if (P.nc == 1) {                   // kmodel.hpp:293-301: Bloom hit + one array candidate: neighbour vote
+				bin = (n_low >= n_cand / 2) ? P.occ : P.cands[0];
+			} else if (n_cand <= 0) {          // kmodel.hpp:305-309
+				bin = 0;
+			} else {                           // kmodel.hpp:310-322: candidate closest to any neighbour, first wins ties
+				int min_dist = 2 << 20;
+				bin = P.cands[0];
+#pragma unroll
+				for (int i = 0; i < kBmax(B); i++) {
+					if (i < P.nc && min_dist > dist[i]) {
+						min_dist = dist[i];
+						bin = P.cands[i];
+					}
+				}
+			}
+			out[defer[g].index] = bin_to_mean(c, bin);
+		}
 	}
+}
+
+// rest table side structures (built once per model, after the rest table itself)
+__global__ void rest_fine_kernel(const uint64_t* __restrict__ keys, uint32_t n, int fine_shift, uint32_t n_buckets, uint32_t* __restrict__ fine) {
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b <= n_buckets; b += gridDim.x * blockDim.x) {
+		// first entry whose bucket (key >> fine_shift) is >= b
+		uint32_t lo = 0, hi = n;
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if ((keys[mid] >> fine_shift) < (uint64_t)b) lo = mid + 1; else hi = mid;
+		}
+		fine[b] = lo;
+	}
+}
+
+__global__ void rest_quirk_kernel(const uint64_t* __restrict__ keys, uint64_t n, const int32_t* __restrict__ hash2index,
+                                  const int32_t* __restrict__ pre_buffer, int map_size, uint64_t suffix_mask,
+                                  uint64_t* __restrict__ quirk_suffix, uint32_t* __restrict__ quirk_index) {
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < map_size; p += gridDim.x * blockDim.x) {
+		uint64_t s = ~0ULL;                    // never equals a masked suffix
+		uint32_t at = 0;
+		const int g = hash2index[p];
+		if (g >= 0) {
+			const long long lo = pre_buffer[g], hi = pre_buffer[g + 1];
+			if (hi > lo && (uint64_t)hi < n) {
+				const uint64_t next_first = keys[hi] & suffix_mask, last = keys[hi - 1] & suffix_mask;
+				if (next_first > last) {
+					s = next_first;
+					at = (uint32_t)hi;
+				}
+			}
+		}
+		quirk_suffix[p] = s;
+		quirk_index[p] = at;
+	}
+}
+
+cudaError_t launch_rest_side_tables(const DevRest& R, int map_size, uint32_t* d_fine, uint64_t* d_quirk_suffix, uint32_t* d_quirk_index,
+                                    cudaStream_t stream) {
+	const uint32_t n_buckets = 1u << R.fine_bits;
+	rest_fine_kernel<<<(n_buckets + 256) / 256, 256, 0, stream>>>(R.keys, (uint32_t)R.count, R.fine_shift, n_buckets, d_fine);
+	rest_quirk_kernel<<<(map_size + 255) / 256, 256, 0, stream>>>(R.keys, R.count, R.hash2index, R.pre_buffer, map_size, R.suffix_mask,
+	                                                              d_quirk_suffix, d_quirk_index);
+	return cudaGetLastError();
 }
 
 static int query_grid(size_t n, int sm_count) {
@@ -274,26 +393,32 @@ static int query_grid(size_t n, int sm_count) {
 	return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
-cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
-                                int sm_count, cudaStream_t stream) {
+template <bool ASCII>
+static cudaError_t launch_query(const DevModel& m, const void* d_in, size_t stride, size_t n, int32_t* d_out, int32_t* d_path,
+                                DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	int grid = query_grid(n, sm_count);
-	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5)
-		query_packed_kernel<31, 7, 5><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path);
-	else
-		query_packed_kernel<0, 0, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path);
+	cudaError_t e = cudaMemsetAsync(d_defer_n, 0, sizeof(unsigned int), stream);
+	if (e != cudaSuccess) return e;
+	const int grid = query_grid(n, sm_count);
+	const int slow_grid = sm_count * 2;
+	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5) {
+		query_fast_kernel<31, 7, 5, ASCII><<<grid, 256, 0, stream>>>(m, d_in, stride, n, d_out, d_path, d_defer, d_defer_n);
+		if (d_out) query_slow_kernel<31, 7, 5><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
+	} else {
+		query_fast_kernel<0, 0, 0, ASCII><<<grid, 256, 0, stream>>>(m, d_in, stride, n, d_out, d_path, d_defer, d_defer_n);
+		if (d_out) query_slow_kernel<0, 0, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
+	}
 	return cudaGetLastError();
 }
 
-cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, int sm_count,
-                               cudaStream_t stream) {
-	if (n == 0) return cudaSuccess;
-	int grid = query_grid(n, sm_count);
-	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5)
-		query_ascii_kernel<31, 7, 5><<<grid, 256, 0, stream>>>(m, d_flat, stride, n, d_out);
-	else
-		query_ascii_kernel<0, 0, 0><<<grid, 256, 0, stream>>>(m, d_flat, stride, n, d_out);
-	return cudaGetLastError();
+cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
+                                DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
+	return launch_query<false>(m, d_kmers, 8, n, d_out, d_path, d_defer, d_defer_n, sm_count, stream);
+}
+
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, DeferredQuery* d_defer,
+                               unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
+	return launch_query<true>(m, d_flat, stride, n, d_out, nullptr, d_defer, d_defer_n, sm_count, stream);
 }
 
 }  // namespace kmx
