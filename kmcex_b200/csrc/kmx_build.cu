@@ -320,6 +320,8 @@ cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d
 // =========================================================================================
 constexpr uint32_t kStateShift = 30;
 constexpr uint32_t kAccepted = 1u << kStateShift, kRejected = 2u << kStateShift;
+constexpr uint32_t kNeedShift = 14;                          // status: state(2) | contested(14) | untagged(14)
+constexpr uint32_t kMaskBits = (1u << kNeedShift) - 1;
 constexpr uint32_t kEpochMax = 0x3FFFu;
 constexpr uint32_t kIdTile = 256;                           // ids per reorder tile
 
@@ -380,160 +382,250 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 			uint64_t* dst_kmer = a.buf_kmer[t & 1];
 			uint32_t* dst_occ = a.buf_occ[t & 1];
 
-			// ---------------- reservation iterations ----------------
-			// (a)+(b): check one item against the committed state, reject or reserve
-			auto reserve_item = [&](uint32_t id, uint32_t key_hi) {
-				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-				const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
+			// ---------------- decide every item of the round ----------------
+			// ItemCtx: what every phase recomputes from the item (hashing is cheaper than keeping
+			// n_hash positions per item in memory between phases)
+			struct ItemCtx {
+				uint64_t r;
+				uint64_t pos[HM];
+				uint32_t bin, c;
+				int arr;
+			};
+			auto load_item = [&](uint32_t id, ItemCtx& it) {
+				const uint32_t i = id >> kBucketLog;
+				it.c = id & (kBucket - 1);
+				it.arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
 				const uint64_t v = __ldcg(src_kmer + id);
 				const uint32_t occ = __ldcg(src_occ + id);
-				const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+				it.bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
+				it.r = reverse_bases(v, k);
 				HashPrep p;
-				hash_prepare(reverse_bases(v, k), k, p);
-				uint64_t pos[HM];
+				hash_prepare(it.r, k, p);
+#pragma unroll
+				for (int j = 0; j < HM; j++)
+					if (j < nh) it.pos[j] = fastmod(hash_finish(p, k, m.arr_seed[it.arr][j]), m.arr_mod);
+			};
+			// read the item's cells: conflict with the committed state? which positions are still untagged?
+			auto read_cells = [&](const ItemCtx& it, bool& conflict, uint32_t& untagged) {
 				unsigned long long cell[HM];
 #pragma unroll
-				for (int j = 0; j < HM; j++) {
-					if (j < nh) {
-						pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
-						cell[j] = __ldcg(m.cells[arr] + (pos[j] >> 5));
-					}
-				}
-				bool conflict = false;
-				uint32_t need = 0;
+				for (int j = 0; j < HM; j++)
+					if (j < nh) cell[j] = __ldcg(m.cells[it.arr] + (it.pos[j] >> 5));
+				conflict = false;
+				untagged = 0;
 #pragma unroll
 				for (int j = 0; j < HM; j++) {
 					if (j < nh) {
-						const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
+						const uint32_t sh = ((uint32_t)it.pos[j] & 31u) ^ 7u;
 						const uint32_t val = ((uint32_t)cell[j] >> sh) & 1u, tag = ((uint32_t)(cell[j] >> 32) >> sh) & 1u;
-						const uint32_t want = (bin >> j) & 1u;
-						conflict |= (tag != 0) && (val != want);
-						need |= (tag ^ 1u) << j;
+						conflict |= (tag != 0) && (val != ((it.bin >> j) & 1u));
+						untagged |= (tag ^ 1u) << j;
 					}
-				}
-				if (conflict) {
-					a.status[id] = kRejected;
-					atomicAdd(a.tile_fail + (id / kIdTile), 1u);
-				} else {
-					uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
-#pragma unroll
-					for (int j = 0; j < HM; j++) {
-						if (j < nh && ((need >> j) & 1u)) {
-							const uint32_t want = (bin >> j) & 1u;
-							atomicMin(table + 2 * ((uint32_t)pos[j] & slot_mask) + want, key_hi | c);
-						}
-					}
-					a.status[id] = need;
 				}
 			};
-			// (c): accept the item if nobody smaller contests it; true = still undecided
-			auto commit_item = [&](uint32_t id, uint32_t key_hi) -> bool {
-				const uint32_t need = a.status[id];
-				if (need >> kStateShift) return false;
-				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-				const int arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
-				const uint64_t v = __ldcg(src_kmer + id);
-				const uint32_t occ = __ldcg(src_occ + id);
-				const uint32_t bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
-				const uint64_t r = reverse_bases(v, k);
+			auto reject = [&](uint32_t id) {
+				a.status[id] = kRejected;
+				atomicAdd(a.tile_fail + (id / kIdTile), 1u);
+			};
+			// accept: set tag (+ value) at every position that was untagged, OR the (k-2)-mer into km_back (kmodel.hpp:546-550)
+			auto commit = [&](uint32_t id, const ItemCtx& it, uint32_t untagged) {
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh && ((untagged >> j) & 1u)) {      // tagged positions already hold the wanted value
+						const uint32_t sh = ((uint32_t)it.pos[j] & 31u) ^ 7u;
+						const unsigned long long want = (it.bin >> j) & 1u;
+						atomicOr(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh);
+					}
+				}
 				HashPrep p;
-				hash_prepare(r, k, p);
-				uint64_t pos[HM];
-				const uint32_t* table = a.resv + (size_t)arr * 2 * a.resv_slots;
-				const uint32_t key = key_hi | c;
-				bool ok = true;
-#pragma unroll
-				for (int j = 0; j < HM; j++) {
-					if (j < nh) {
-						pos[j] = fastmod(hash_finish(p, k, m.arr_seed[arr][j]), m.arr_mod);
-						if ((need >> j) & 1u) {
-							const uint32_t want = (bin >> j) & 1u;
-							ok &= __ldcg(table + 2 * ((uint32_t)pos[j] & slot_mask) + (want ^ 1u)) >= key;
-						}
-					}
-				}
-				if (!ok) return true;
-#pragma unroll
-				for (int j = 0; j < HM; j++) {
-					if (j < nh && ((need >> j) & 1u)) {          // positions already tagged hold the wanted value
-						const uint32_t sh = ((uint32_t)pos[j] & 31u) ^ 7u;
-						const unsigned long long want = (bin >> j) & 1u;
-						atomicOr(m.cells[arr] + (pos[j] >> 5), ((1ULL << 32) | want) << sh);
-					}
-				}
-				// accepted: the (k-2)-mer goes to km_back (kmodel.hpp:546-550)
-				hash_prepare(middle_r(r, k), k - 2, p);
+				hash_prepare(middle_r(it.r, k), k - 2, p);
 #pragma unroll
 				for (int j = 0; j < HM - 2; j++)
 					if (j < hk) filter_set(m.km_back, hash_finish(p, k - 2, c_seeds[j]));
 				a.status[id] = kAccepted;
-				return false;
 			};
-			// The first iteration walks every item of the round; what stays undecided is appended
-			// (order is irrelevant, the index travels in the key) to a list that the later
-			// iterations walk instead, so that their cost follows the number of open items.
-			uint32_t iter = 0, n_list = 0;
-			int cur = 0;
+			auto reserve = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) {
+				uint32_t* table = a.resv + (size_t)it.arr * 2 * a.resv_slots;
+#pragma unroll
+				for (int j = 0; j < HM; j++)
+					if (j < nh && ((need >> j) & 1u))
+						atomicMin(table + 2 * ((uint32_t)it.pos[j] & slot_mask) + ((it.bin >> j) & 1u), key_hi | it.c);
+			};
+			auto holds_reservations = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) -> bool {
+				const uint32_t* table = a.resv + (size_t)it.arr * 2 * a.resv_slots;
+				const uint32_t key = key_hi | it.c;
+				bool ok = true;
+#pragma unroll
+				for (int j = 0; j < HM; j++)
+					if (j < nh && ((need >> j) & 1u))
+						ok &= __ldcg(table + 2 * ((uint32_t)it.pos[j] & slot_mask) + (((it.bin >> j) & 1u) ^ 1u)) >= key;
+				return ok;
+			};
+			auto append = [&](uint32_t* list, unsigned int* counter, uint32_t id) {
+				cg::coalesced_group g = cg::coalesced_threads();
+				uint32_t at = 0;
+				if (g.thread_rank() == 0) at = atomicAdd(counter, g.size());
+				at = g.shfl(at, 0);
+				list[at + g.thread_rank()] = id;
+			};
+			// dense walk over the items of the round: x in [0, n_round) -> id
+			uint32_t n_round = 0;
+#pragma unroll
+			for (int i = 0; i < BM; i++) n_round += n_cur[i];
+			auto dense_to_id = [&](uint32_t x) -> uint32_t {
+				uint32_t i = 0;
+#pragma unroll
+				for (int q = 0; q < BM - 1; q++) {
+					if (x >= n_cur[q] && i == (uint32_t)q) {
+						x -= n_cur[q];
+						i++;
+					}
+				}
+				return (i << kBucketLog) | x;
+			};
+			// claim bitmap of this round: sized to the round (about 64 bits per claim), cleared at the end
+			uint32_t claim_log2 = 15;
+			while (claim_log2 < a.claim_log2 && (1u << claim_log2) < 64u * (uint32_t)nh * (n_round / (uint32_t)nb + 1)) claim_log2++;
+			const uint32_t claim_mask = (1u << claim_log2) - 1;
+			const size_t claim_stride = (size_t)1 << (a.claim_log2 - 5);     // words per (array, want) bitmap
+
 			long long tick = clock64();
-			while (true) {
-				const uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
-				const uint32_t* list_cur = a.list[cur];
-				uint32_t* list_next = a.list[cur ^ 1];
-				if (tid == 0) vctl->list_n[cur ^ 1] = 0;
-				if (iter == 0) {
-					for (uint32_t id = tid; id < total_ids; id += T) {
-						if ((id & (kBucket - 1)) >= n_cur[id >> kBucketLog]) continue;
-						reserve_item(id, key_hi);
-					}
+			// ---- first iteration, phase 0: reject on the committed state, or claim (position, wanted value) ----
+			for (uint32_t x = tid; x < n_round; x += T) {
+				const uint32_t id = dense_to_id(x);
+				ItemCtx it;
+				load_item(id, it);
+				bool conflict;
+				uint32_t untagged;
+				read_cells(it, conflict, untagged);
+				if (conflict) {
+					reject(id);
 				} else {
-					for (uint32_t x = tid; x < n_list; x += T) {
-						const uint32_t id = __ldcg(list_cur + x);
-						if (a.status[id] >> kStateShift) continue;
-						reserve_item(id, key_hi);
+					uint32_t* cl = a.claim + (size_t)it.arr * 2 * claim_stride;
+#pragma unroll
+					for (int j = 0; j < HM; j++) {
+						if (j < nh && ((untagged >> j) & 1u)) {
+							const uint32_t bit = (uint32_t)it.pos[j] & claim_mask;
+							atomicOr(cl + ((it.bin >> j) & 1u) * claim_stride + (bit >> 5), 1u << (bit & 31u));
+						}
+					}
+					a.status[id] = untagged;
+				}
+			}
+			grid.sync();
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[0] += (unsigned long long)(now - tick);
+				tick = now;
+				vctl->list_n[0] = 0;
+				vctl->list_n[1] = 0;
+			}
+			// ---- phase 1: an item nobody contests (no live item wants the opposite value at any of its
+			// untagged positions) interacts with nobody and commits at once; the others reserve ----
+			uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
+			for (uint32_t x = tid; x < n_round; x += T) {
+				const uint32_t id = dense_to_id(x);
+				const uint32_t untagged = a.status[id];
+				if (untagged >> kStateShift) continue;
+				ItemCtx it;
+				load_item(id, it);
+				const uint32_t* cl = a.claim + (size_t)it.arr * 2 * claim_stride;
+				uint32_t need = 0;
+#pragma unroll
+				for (int j = 0; j < HM; j++) {
+					if (j < nh && ((untagged >> j) & 1u)) {
+						const uint32_t bit = (uint32_t)it.pos[j] & claim_mask;
+						const uint32_t w = __ldcg(cl + (((it.bin >> j) & 1u) ^ 1u) * claim_stride + (bit >> 5));
+						need |= ((w >> (bit & 31u)) & 1u) << j;
 					}
 				}
-				grid.sync();
-				if (tid == 0) {
-					long long now = clock64();
-					vctl->phase_cycles[iter == 0 ? 0 : 2] += (unsigned long long)(now - tick);
-					tick = now;
+				if (need == 0) {
+					commit(id, it, untagged);
+				} else {
+					reserve(it, need, key_hi);
+					a.status[id] = untagged | (need << kNeedShift);
 				}
-				const uint32_t n_walk = iter == 0 ? total_ids : n_list;
-				for (uint32_t x = tid; x < n_walk; x += T) {
-					uint32_t id = x;
-					if (iter == 0) {
-						if ((id & (kBucket - 1)) >= n_cur[id >> kBucketLog]) continue;
-					} else {
-						id = __ldcg(list_cur + x);
-					}
-					if (commit_item(id, key_hi)) {
-						cg::coalesced_group g = cg::coalesced_threads();
-						uint32_t at = 0;
-						if (g.thread_rank() == 0) at = atomicAdd(&ctl->list_n[cur ^ 1], g.size());
-						at = g.shfl(at, 0);
-						list_next[at + g.thread_rank()] = id;
-					}
-				}
-				grid.sync();
-				if (tid == 0) {
-					long long now = clock64();
-					vctl->phase_cycles[iter == 0 ? 1 : 3] += (unsigned long long)(now - tick);
-					tick = now;
-				}
-				n_list = vctl->list_n[cur ^ 1];
-				cur ^= 1;
-				iter++;
-				epoch++;
+			}
+			grid.sync();
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[1] += (unsigned long long)(now - tick);
+				tick = now;
+			}
+			// ---- phase 2: contested items that hold all their reservations commit, the rest go to the list ----
+			for (uint32_t x = tid; x < n_round; x += T) {
+				const uint32_t id = dense_to_id(x);
+				const uint32_t st = a.status[id];
+				if ((st >> kStateShift) || (st >> kNeedShift) == 0) continue;
+				ItemCtx it;
+				load_item(id, it);
+				if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
+				else append(a.list[0], &ctl->list_n[0], id);
+			}
+			grid.sync();
+			uint32_t n_list = vctl->list_n[0];
+			uint32_t iter = 1;
+			int cur = 0;
+			epoch++;
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[2] += (unsigned long long)(now - tick);
+				tick = now;
+			}
+			// ---- later iterations walk the list of still undecided (contested) items ----
+			while (n_list != 0) {
 				if (epoch >= kEpochMax) {                       // keys can get no smaller: start over
 					for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
 					epoch = 0;
 					grid.sync();
 				}
-				if (n_list == 0) break;
+				key_hi = (kEpochMax - epoch) << kBucketLog;
+				const uint32_t* list_cur = a.list[cur];
+				if (tid == 0) vctl->list_n[cur ^ 1] = 0;
+				for (uint32_t x = tid; x < n_list; x += T) {
+					const uint32_t id = __ldcg(list_cur + x);
+					const uint32_t st = a.status[id];
+					ItemCtx it;
+					load_item(id, it);
+					bool conflict;
+					uint32_t untagged;
+					read_cells(it, conflict, untagged);
+					if (conflict) {
+						reject(id);
+						continue;
+					}
+					const uint32_t need = (st >> kNeedShift) & untagged;     // contested positions that are still open
+					if (need == 0) {
+						commit(id, it, untagged);
+					} else {
+						reserve(it, need, key_hi);
+						a.status[id] = untagged | (need << kNeedShift);
+					}
+				}
+				grid.sync();
+				for (uint32_t x = tid; x < n_list; x += T) {
+					const uint32_t id = __ldcg(list_cur + x);
+					const uint32_t st = a.status[id];
+					if (st >> kStateShift) continue;
+					ItemCtx it;
+					load_item(id, it);
+					if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
+					else append(a.list[cur ^ 1], &ctl->list_n[cur ^ 1], id);
+				}
+				grid.sync();
+				n_list = vctl->list_n[cur ^ 1];
+				cur ^= 1;
+				iter++;
+				epoch++;
 				if (iter >= a.max_iterations) {
 					if (tid == 0) vctl->error = 1;
 					return;                                     // uniform over the grid
 				}
+			}
+			if (tid == 0) {
+				long long now = clock64();
+				vctl->phase_cycles[3] += (unsigned long long)(now - tick);
+				tick = now;
 			}
 
 			// ---------------- reorder_buffer (kmodel.hpp:529-540) in closed form ----------------
@@ -647,6 +739,11 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 				}
 			}
 			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;
+			{   // clear the part of the claim bitmaps this round used
+				const uint32_t words = 1u << (claim_log2 - 5);
+				const uint32_t total = (uint32_t)nb * 2 * words;
+				for (uint32_t x = tid; x < total; x += T) a.claim[(size_t)(x / words) * claim_stride + (x % words)] = 0;
+			}
 			if (tid == 0) {
 				unsigned long long att = 0, fail = 0;
 				for (int i = 0; i < nb; i++) {

@@ -23,7 +23,7 @@ constexpr uint64_t kMurM = 0xc6a4a7935bd1e995ULL;
 constexpr int kBucketLog = 18;                    // kmodel.hpp:276  bucket_size = 1 << 18
 constexpr uint32_t kBucket = 1u << kBucketLog;
 constexpr int kMaxArrays = 8;                     // n_bits supported by this build
-constexpr int kMaxHash = 16;                      // n_hash supported by this build
+constexpr int kMaxHash = 12;                      // n_hash supported by this build (status words hold 14-bit masks)
 constexpr int kMaxBf = 3;                         // kmodel.hpp:50   bf_num is 1 or 3
 
 // ---------------------------------------------------------------------------------------

@@ -891,13 +891,20 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		DA(&a.list[1], batch_items * 4, s);
 		DA(&a.tile_fail, batch_items / 256 * 4, s);
 		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
-		a.resv_slots = 1u << 22;
+		a.resv_slots = 1u << 20;
 		if (const char* e = getenv("KMX_RESV_LOG2")) {
 			int v = atoi(e);
 			if (v >= 10 && v <= 26) a.resv_slots = 1u << v;
 		}
 		DA(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4, s);
 		CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, s));
+		a.claim_log2 = 25;
+		if (const char* e = getenv("KMX_CLAIM_LOG2")) {
+			int v = atoi(e);
+			if (v >= 15 && v <= 30) a.claim_log2 = (uint32_t)v;
+		}
+		DA(&a.claim, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s);
+		CU(cudaMemsetAsync(a.claim, 0, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s));
 		DA(&a.ctl, sizeof(InsertCtl), s);
 		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), s));
 		a.max_iterations = kBucket + 64;
@@ -954,7 +961,7 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		dev_free(a.buf_kmer[b], s);
 		dev_free(a.buf_occ[b], s);
 	}
-	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.ctl, s);
+	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.claim, s); dev_free(a.ctl, s);
 
 	// ---- rest table (rest.hpp:157-161) ----
 	int32_t& groups = m->x->h_pinned->groups;

@@ -74,6 +74,8 @@ struct InsertArgs {
 	uint32_t* list[2];                // [n_bits * kBucket] ids still undecided, ping-pong
 	uint32_t* resv;                   // [n_bits][2 * resv_slots]
 	uint32_t resv_slots;              // power of two
+	uint32_t* claim;                  // [n_bits][2][2^claim_log2 / 32] claim bitmaps (position, wanted value)
+	uint32_t claim_log2;              // bits per bitmap (upper bound; a round uses a prefix sized to its items)
 	uint64_t* rest_kmer;              // survivors of all batches
 	uint32_t* rest_occ;
 	unsigned long long rest_cap;
