@@ -108,6 +108,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch, from profiles/ (ncu --set full)
+NCU_TRAFFIC = {}
+
+
+def random_sector_peaks() -> dict:
+    """GB/s of 32-byte sectors the chip sustains for random access (tools/random_sector_peaks.py, committed under profiles/):
+    mean of the load and atomic figures, for an L2-resident (64 MiB) and an HBM-resident (4 GiB) footprint"""
+    p = os.path.join(ROOT, "profiles", "r1_random_sector_peaks.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        res = json.load(f)["results"]
+    out = {}
+    for name, mb in (("l2", 64), ("hbm", 4096)):
+        v = [r["gb_per_s_32B"] for r in res if r["footprint_mb"] == mb]
+        if v:
+            out[name] = sum(v) / len(v)
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,17 +312,24 @@ def main() -> None:
     qps_e2e = world * per * args.steps / t_qe
     assert bool((out_host.to(dev) == out_dev).all())
 
-    # ---------------- roofline of the dominant kernels ----------------
+    # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peaks()
-    # insert_kernel: each attempt reads n_hash cells (one 32-byte sector each); each accept issues n_hash cell
-    # atomics + (n_hash-2) km_back atomics (one sector each).  DESIGN.md "Algorithmic bytes".
-    ins_bytes = 32.0 * (7 * info["insert_attempts"] + (7 + 5) * info["insert_accepted"])
-    ins_gbs = ins_bytes / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
+    rs_peaks = random_sector_peaks()
+    # insert_kernel (largest share of the step).  Algorithmic traffic, one 32-byte sector per touch
+    # (DESIGN.md section 3): each attempt reads n_hash cells; each accept issues n_hash cell atomics
+    # + (n_hash-2) km_back atomics.  Reservation / claim traffic is implementation overhead, not counted.
+    ins_sectors = 7 * info["insert_attempts"] + (7 + 5) * info["insert_accepted"]
+    ins_gbs = 32.0 * ins_sectors / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
+    model_bytes = info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"]
+    resident = "l2" if model_bytes < (100 << 20) else "hbm"
+    rs_peak = rs_peaks.get(resident)
     roofline = {"kernel": "insert_kernel", "bound": "hbm", "achieved": ins_gbs, "peak": peak, "unit": "GB/s", "frac": ins_gbs / peak,
-                "traffic": None, "peak_source": peak_src, "ms_per_launch": ins_ms,
-                "note": "random 32-byte sectors; arrays of this workload are L2-resident, the kernel is bound by grid-barrier latency"}
-    # query kernel: sectors actually touched per query depend on the path; lower bound counted here is
-    # km_back (5) + Bloom (bf_num*11) for every query that misses the rest table, + 35 cells for those in km_back
+                "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src, "ms_per_launch": ins_ms,
+                "sectors_per_launch": ins_sectors, "residency": resident,
+                "random_sector_peak_gbs": rs_peak, "frac_of_random_sector_peak": (ins_gbs / rs_peak) if rs_peak else None,
+                "note": "random 32-byte sectors: the streaming-copy peak is not reachable by construction; the measured random-sector "
+                        "peak (profiles/r1_random_sector_peaks.json: loads / atomics averaged, L2- or HBM-resident footprint) is the honest bound"}
+    q_sectors_est = None
     line = {
         "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -318,6 +345,7 @@ def main() -> None:
         "roofline": roofline,
         "clocks": clocks,
         "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers", "insert_phase_cycles")},
+        "model_bytes": model_bytes,
     }
 
     # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------

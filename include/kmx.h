@@ -132,6 +132,11 @@ uint64_t kmx_host_fastmod(uint64_t h, uint64_t d);                     /* the de
  * keeps item i; perm[j] = source index of output slot j; returns the new length            */
 int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm);
 
+/* ---- roofline denominators: random 32-byte-sector throughput of the device (diagnostic) ------
+ * kind 0: random 8-byte loads, 1: random 32-bit atomic OR, 2: random 64-bit atomic OR; 7 accesses
+ * per item over `footprint_bytes` of device memory; *ms_out = milliseconds per launch             */
+int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,7 @@ SIGNATURES = {
     "kmx_host_sizes": (None, [C.POINTER(C.c_uint64), C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

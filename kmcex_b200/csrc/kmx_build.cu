@@ -544,6 +544,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 				} else {
 					reserve(it, need, key_hi);
 					a.status[id] = untagged | (need << kNeedShift);
+					append(a.list[1], &ctl->list_n[1], id);
 				}
 			}
 			grid.sync();
@@ -553,10 +554,10 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 				tick = now;
 			}
 			// ---- phase 2: contested items that hold all their reservations commit, the rest go to the list ----
-			for (uint32_t x = tid; x < n_round; x += T) {
-				const uint32_t id = dense_to_id(x);
+			const uint32_t n_contested = vctl->list_n[1];
+			for (uint32_t x = tid; x < n_contested; x += T) {
+				const uint32_t id = __ldcg(a.list[1] + x);
 				const uint32_t st = a.status[id];
-				if ((st >> kStateShift) || (st >> kNeedShift) == 0) continue;
 				ItemCtx it;
 				load_item(id, it);
 				if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
@@ -717,10 +718,11 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 				vctl->phase_cycles[5] += (unsigned long long)(now - tick);
 				tick = now;
 			}
-			for (uint32_t id = tid; id < total_ids; id += T) {
+			for (uint32_t x = tid; x < n_round; x += T) {
+				const uint32_t id = dense_to_id(x);
 				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
 				const uint32_t F = n_next[i];
-				if (c >= n_cur[i] || c < F) continue;
+				if (c < F) continue;
 				if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
 				const uint32_t d = F - __ldcg(a.rank + id) - 1;
 				const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);

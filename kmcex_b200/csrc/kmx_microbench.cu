@@ -1,0 +1,81 @@
+// kmx_microbench.cu -- random-sector microbenchmarks: the roofline denominators of this path.
+// The build and the query are bound by random 32-byte-sector traffic, not
+// by streaming bandwidth; these kernels measure what the chip sustains for the three access
+// kinds the path uses, at a given footprint (L2-resident or HBM-resident):
+//   kind 0: independent random 8-byte loads        (coupled-array probes, ld.global.nc)
+//   kind 1: random 32-bit atomic OR, no return     (Bloom / km_back inserts, red.global.or.b32)
+//   kind 2: random 64-bit atomic OR, no return     (coupled-array commits)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/kmx.h"
+
+namespace {
+
+__device__ __forceinline__ uint64_t mix(uint64_t z) {
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+	return z ^ (z >> 31);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) random_sector_kernel(unsigned long long* buf, uint64_t n_words, uint64_t n_items, unsigned long long* sink) {
+	constexpr int PER = 7;                       // independent accesses per item, as one array probe issues
+	unsigned long long acc = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t h = mix(i * 0x9E3779B97F4A7C15ULL + 12345);
+		unsigned long long v[PER];
+#pragma unroll
+		for (int j = 0; j < PER; j++) {
+			h = mix(h + j);
+			const uint64_t w = h % n_words;
+			if (KIND == 0) v[j] = __ldg(buf + w);
+			else if (KIND == 1) atomicOr((unsigned int*)buf + 2 * w + (j & 1), 1u << (h >> 59));
+			else atomicOr(buf + w, 1ULL << (h >> 58));
+		}
+		if (KIND == 0) {
+#pragma unroll
+			for (int j = 0; j < PER; j++) acc ^= v[j];
+		}
+	}
+	if (KIND == 0 && acc == 0x1234567ULL) *sink = acc;   // keep the loads alive
+}
+
+}  // namespace
+
+// footprint_bytes of device memory are touched at random; n_items * 7 accesses per launch;
+// returns the average milliseconds per launch over `reps` launches (after one warm-up) in *ms_out
+extern "C" int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out) {
+	if (kind < 0 || kind > 2 || footprint_bytes < 4096 || !ms_out || reps < 1) return KMX_EARG;
+	unsigned long long* buf = nullptr;
+	unsigned long long* sink = nullptr;
+	if (cudaMalloc(&buf, footprint_bytes) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) {
+		cudaGetLastError();
+		cudaFree(buf);
+		return KMX_ECUDA;
+	}
+	cudaMemset(buf, 0, footprint_bytes);
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const uint64_t n_words = footprint_bytes / 8;
+	const int grid = sms * 8;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	for (int r = -1; r < reps; r++) {
+		if (r == 0) cudaEventRecord(e0);
+		if (kind == 0) random_sector_kernel<0><<<grid, 256>>>(buf, n_words, n_items, sink);
+		else if (kind == 1) random_sector_kernel<1><<<grid, 256>>>(buf, n_words, n_items, sink);
+		else random_sector_kernel<2><<<grid, 256>>>(buf, n_words, n_items, sink);
+	}
+	cudaEventRecord(e1);
+	cudaError_t e = cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	*ms_out = ms / reps;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(buf);
+	cudaFree(sink);
+	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
+}

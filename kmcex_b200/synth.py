@@ -199,6 +199,8 @@ def write_kmc_db(base: str, kmers: np.ndarray, counts: np.ndarray, k: int = 31, 
     counts = np.ascontiguousarray(counts, dtype=np.uint32)
     n = kmers.size
     suf_bytes = (k - lut_prefix_length) // 4
+    if n >= (1 << 23) and torch.cuda.is_available():
+        return _write_kmc_db_cuda(base, kmers, counts, k, lut_prefix_length, n_bins, counter_size, min_count, max_count, signature_len)
     if n_bins > 1:
         h = (kmers * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
         bins = (h % np.uint64(n_bins)).astype(np.int64)
@@ -221,6 +223,53 @@ def write_kmc_db(base: str, kmers: np.ndarray, counts: np.ndarray, k: int = 31, 
     with open(base + ".kmc_suf", "wb") as f:
         f.write(b"KMCS")
         f.write(rec.tobytes())
+        f.write(b"KMCS")
+    header = struct.pack("<7IQB7x5I I", k, 0, counter_size, lut_prefix_length, signature_len, min_count, max_count,
+                         n, 0, 0, 0, 0, 0, 0, 0x200)
+    with open(base + ".kmc_pre", "wb") as f:
+        f.write(b"KMCP")
+        f.write(lut.tobytes())
+        f.write(np.zeros(4 ** signature_len + 1, dtype=np.uint32).tobytes())
+        f.write(header)
+        f.write(struct.pack("<I", len(header)))
+        f.write(b"KMCP")
+    return n
+
+
+def _write_kmc_db_cuda(base, kmers, counts, k, lut_prefix_length, n_bins, counter_size, min_count, max_count, signature_len) -> int:
+    """same files as write_kmc_db, with the sort and the record packing done by torch on the GPU (large shapes)"""
+    dev = torch.device("cuda")
+    n = kmers.size
+    suf_bytes = (k - lut_prefix_length) // 4
+    km = torch.from_numpy(kmers.view(np.int64)).to(dev)
+    ct = torch.from_numpy(counts.astype(np.int64)).to(dev)
+    if n_bins > 1:
+        h = _lsr(km * _i64(0x9E3779B97F4A7C15), 40)
+        bins = h % n_bins
+    else:
+        bins = torch.zeros(n, dtype=torch.int64, device=dev)
+    order = torch.argsort(km, stable=True)
+    km, ct, bins = km[order], ct[order], bins[order]
+    order = torch.argsort(bins, stable=True)
+    km, ct, bins = km[order], ct[order], bins[order]
+    del order
+    slots = 4 ** lut_prefix_length
+    prefix = _lsr(km, 8 * suf_bytes) if suf_bytes else km
+    per_slot = torch.bincount(bins * slots + prefix, minlength=n_bins * slots)
+    starts = torch.zeros(n_bins * slots + 1, dtype=torch.int64, device=dev)
+    starts[1:] = torch.cumsum(per_slot, 0)
+    lut = starts.cpu().numpy().astype(np.uint64)
+    with open(base + ".kmc_suf", "wb") as f:
+        f.write(b"KMCS")
+        step = 1 << 25
+        for a in range(0, n, step):
+            b = min(n, a + step)
+            rec = torch.empty((b - a, suf_bytes + counter_size), dtype=torch.uint8, device=dev)
+            for j in range(suf_bytes):
+                rec[:, j] = (_lsr(km[a:b], 8 * (suf_bytes - 1 - j)) & 0xFF).to(torch.uint8)
+            for j in range(counter_size):
+                rec[:, suf_bytes + j] = ((ct[a:b] >> (8 * j)) & 0xFF).to(torch.uint8)
+            f.write(rec.cpu().numpy().tobytes())
         f.write(b"KMCS")
     header = struct.pack("<7IQB7x5I I", k, 0, counter_size, lut_prefix_length, signature_len, min_count, max_count,
                          n, 0, 0, 0, 0, 0, 0, 0x200)
