@@ -1,0 +1,60 @@
+"""GPU suite, N > 1 (skipped on a single-GPU box): rank 0 builds on its GPU, the model is
+replicated over NCCL, the query batch is sharded; every rank must see the reference's answers."""
+import hashlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, base, ci, work_dir, q_path):
+    import kmcex_b200 as kx
+    from kmcex_b200 import distributed as kd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    kx._lib.check(kx.lib().kmx_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        def build():
+            m = kx.get_model(ci, cases.MODEL["cs"], cases.MODEL["n_hash"], cases.MODEL["n_bits"])
+            m.init(base)
+            out = os.path.join(work_dir, "built")
+            os.makedirs(out, exist_ok=True)
+            m.save(out)
+            return out
+        sm = kd.ShardedKModel.from_builder(build, work_dir)
+        q = np.fromfile(q_path, dtype=np.uint64)
+        occ = sm.kmer_to_occ(q)
+        np.save(os.path.join(work_dir, f"occ{rank}.npy"), occ)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_ranks_replicated_model_sharded_queries(case_dbs, golden, tmp_path):
+    name = "small_ci2"
+    base, sp = case_dbs(name)
+    q = cases.case_queries(sp)
+    q_path = str(tmp_path / "q.u64")
+    q.tofile(q_path)
+    mp.spawn(_worker, args=(2, _free_port(), base, cases.CASES[name]["ci"], str(tmp_path), q_path), nprocs=2, join=True)
+    for r in range(2):
+        occ = np.load(str(tmp_path / f"occ{r}.npy"))
+        assert hashlib.md5(occ.tobytes()).hexdigest() == golden[name]["occ_md5"]
+        for f in ("header", "km.bin", "rest.bin"):
+            assert cases.md5_file(str(tmp_path / f"replica_rank{r}" / f)) == golden[name]["model_md5"][f]
