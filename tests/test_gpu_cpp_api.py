@@ -1,0 +1,74 @@
+"""GPU suite: the drop-in C++ boundary.  A user program written against the reference's documented
+API (README.md:64-93) is compiled with g++ against include/kmodel.hpp + libkmx.so, and the `kmcEx`
+command line (tools/kmcex_cli.cpp, main.cpp's flags) is run on an existing KMC database; files and
+answers must equal the reference's goldens."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from kmcex_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "kmcex_b200")
+
+
+def _gxx():
+    for c in ("/usr/bin/g++", shutil.which("g++")):
+        if c and os.path.exists(c):
+            return c
+    pytest.skip("g++ not available")
+
+
+def _compile(src, out):
+    cmd = [_gxx(), "-std=c++11", "-O2", "-pthread", "-I" + os.path.join(ROOT, "include"), src, "-L" + LIBDIR, "-lkmx", "-Wl,-rpath," + LIBDIR, "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_reference_style_user_program(case_dbs, golden, tmp_path):
+    name = "small_ci2"
+    base, sp = case_dbs(name)
+    exe = str(tmp_path / "user_program")
+    _compile(os.path.join(ROOT, "tests", "cpp", "user_program.cpp"), exe)
+    q = cases.case_queries(sp)[:20000]
+    qfile, ofile, mdir = str(tmp_path / "q.txt"), str(tmp_path / "o.txt"), str(tmp_path / "model")
+    os.makedirs(mdir)
+    with open(qfile, "w") as f:
+        f.write("\n".join("".join(map(chr, row)) for row in synth.to_ascii(q, 31)) + "\n")
+    r = subprocess.run([exe, base, mdir, qfile, ofile, str(cases.CASES[name]["ci"])], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for f in ("header", "km.bin", "rest.bin"):
+        assert cases.md5_file(os.path.join(mdir, f)) == golden[name]["model_md5"][f], f
+    lines = open(ofile).read().split("\n")
+    got = np.array([int(x) for x in lines[: q.size]], dtype=np.int32)
+    assert got[:64].tolist() == golden[name]["occ_head"]
+    assert lines[q.size] == f"single {got[0]}"
+    # the stdout lines of show_header_info / show_kmodel_info (kmodel.hpp:118-146)
+    assert "KMCEX:" in r.stdout and "kmercount in blommfilter" in r.stdout and "kmercount hash map" in r.stdout
+    assert f"total kmercount                    :     {sp.kmers.size}" in r.stdout
+
+
+def test_kmcex_command_line(case_dbs, golden, tmp_path):
+    name = "tiny_ci1"
+    base, sp = case_dbs(name)
+    exe = str(tmp_path / "kmcEx")
+    _compile(os.path.join(ROOT, "tools", "kmcex_cli.cpp"), exe)
+    work = str(tmp_path / "work")
+    os.makedirs(work)
+    r = subprocess.run([exe, "-k31", "-t4", "-ci1", "-cs1023", "-nh7", "-nb5", "reads.fastq", base, work], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    save_dir = os.path.join(work, os.path.basename(base))          # main.cpp:147: workdir/basename(output)
+    for f in ("header", "km.bin", "rest.bin"):
+        assert cases.md5_file(os.path.join(save_dir, f)) == golden[name]["model_md5"][f], f
+    # too few arguments: usage + non-zero exit (main.cpp:131-134)
+    r = subprocess.run([exe, "-k31"], capture_output=True, text=True)
+    assert r.returncode != 0 and "kmcEx" in r.stdout
+    # unopenable database: message + exit(1) (kmodel.hpp:394-397)
+    r = subprocess.run([exe, "x", str(tmp_path / "nope"), work], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 1 and "can't open the kmer_data_base" in r.stdout

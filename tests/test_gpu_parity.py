@@ -165,6 +165,51 @@ def test_other_geometries_equal_the_oracle(oracle, tmp_path):
         m.close()
 
 
+@pytest.mark.parametrize("k,lut,csz,cs,ci,nh,nb", [(27, 3, 2, 1023, 1, 7, 5), (23, 3, 1, 255, 2, 7, 5), (31, 7, 3, 1023, 2, 6, 4),
+                                                   (19, 3, 2, 1023, 1, 8, 3), (15, 3, 2, 1023, 1, 7, 2)])
+def test_other_k_and_counter_sizes_equal_the_oracle(k, lut, csz, cs, ci, nh, nb, oracle, tmp_path):
+    """k != 31, 1/3-byte counters, cs = 255: record layout, rest prefix length and hash tail all change"""
+    base = str(tmp_path / "db")
+    sp = synth.synth_reads_spectrum(50_000, 30, 100, k=k, seed={27: 11, 23: 12, 31: 13, 19: 14, 15: 16}[k], ci=ci, cs=cs, device="cpu")
+    synth.write_kmc_db(base, sp.kmers, sp.counts, k=k, lut_prefix_length=lut, n_bins=3, counter_size=csz, min_count=ci, max_count=cs)
+    ora, gpu = str(tmp_path / "ora"), str(tmp_path / "gpu")
+    os.makedirs(ora)
+    os.makedirs(gpu)
+    assert oracle.kmxo_build(base.encode(), ci, cs, nh, nb, ora.encode(), None) == 0
+    db = kx.KmcDatabase(base)
+    assert db.info["k"] == k and db.info["counter_size"] == csz
+    kmers, counts = db.list()
+    ok_k = np.zeros(kmers.size, dtype=np.uint64)
+    ok_c = np.zeros(kmers.size, dtype=np.uint32)
+    assert oracle.kmxo_list(base.encode(), ok_k.ctypes.data, ok_c.ctypes.data, kmers.size, None, None) == kmers.size
+    assert (ok_k == kmers).all() and (ok_c == counts).all()
+    m = kx.get_model(ci, cs, nh, nb)
+    m.init(db)
+    m.save(gpu)
+    for f in ("header", "km.bin", "rest.bin"):
+        assert cases.md5_file(os.path.join(gpu, f)) == cases.md5_file(os.path.join(ora, f)), f
+    q = synth.neighbour_rich_queries(sp, 5000, 5000, seed=k)
+    h = oracle.kmxo_load(ora.encode())
+    want = np.zeros(q.size, dtype=np.int32)
+    oracle.kmxo_query_packed(h, q.ctypes.data, q.size, want.ctypes.data)
+    oracle.kmxo_free(h)
+    assert (m.kmer_to_occ(q) == want).all()
+    assert (kx.get_model(gpu).kmer_to_occ(synth.to_ascii(q[:3000], k)) == want[:3000]).all()
+
+
+def test_empty_and_tiny_batches(built):
+    m, out, sp, base = built("tiny_ci1")
+    assert m.kmer_to_occ(np.zeros(0, dtype=np.uint64)).size == 0
+    assert m.kmer_to_occ([]).size == 0
+    one = m.kmer_to_occ(sp.kmers[:1])
+    assert one.shape == (1,)
+    # a batch larger than one pipeline step of the host path (4 Mi queries), uneven tail
+    big = np.resize(sp.kmers, (1 << 22) + 12345)
+    occ = m.kmer_to_occ(big)
+    assert (occ[: sp.kmers.size] == m.kmer_to_occ(sp.kmers)).all()
+    assert (occ[-12345:] == m.kmer_to_occ(big[-12345:])).all()
+
+
 def test_reference_error_corners_are_reported_not_computed(tmp_path):
     # fewer than 8 k-mers in a Bloom class: the reference aborts in new uint8_t[0]{0} (kmodel.hpp:413-417)
     base = str(tmp_path / "db")

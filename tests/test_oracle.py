@@ -59,21 +59,24 @@ def test_oracle_matches_reference_goldens(name, oracle, case_dbs, golden, tmp_pa
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="compiled reference (oracle/_ref) not present")
-def test_oracle_matches_live_reference_on_a_fresh_seed(oracle, tmp_path):
+@pytest.mark.parametrize("k,lut,csz,cs,ci,nh,nb", [(31, 7, 2, 1023, 2, 7, 5), (27, 3, 2, 1023, 1, 7, 5), (23, 3, 1, 255, 2, 7, 5),
+                                                   (19, 3, 3, 1023, 1, 8, 3), (15, 3, 2, 1023, 1, 6, 2)])
+def test_oracle_matches_live_reference_on_a_fresh_seed(k, lut, csz, cs, ci, nh, nb, oracle, tmp_path):
     from kmcex_b200 import synth
     base = str(tmp_path / "db")
-    sp = synth.synth_reads_spectrum(60_000, 25, 100, seed=99, ci=2, device="cpu")
-    synth.write_kmc_db(base, sp.kmers, sp.counts, lut_prefix_length=7, n_bins=2, min_count=2)
+    sp = synth.synth_reads_spectrum(60_000, 25, 100, k=k, seed=99 + k, ci=ci, cs=cs, device="cpu")
+    synth.write_kmc_db(base, sp.kmers, sp.counts, k=k, lut_prefix_length=lut, n_bins=2, counter_size=csz, min_count=ci, max_count=cs)
     ref_dir, ora_dir = str(tmp_path / "ref"), str(tmp_path / "ora")
     os.makedirs(ref_dir)
-    subprocess.run([REF, "build", base, ref_dir, "2", "1023", "7", "5"], check=True, capture_output=True)
-    _oracle_build(oracle, base, dict(ci=2), ora_dir)
+    os.makedirs(ora_dir)
+    subprocess.run([REF, "build", base, ref_dir, str(ci), str(cs), str(nh), str(nb)], check=True, capture_output=True)
+    assert oracle.kmxo_build(base.encode(), ci, cs, nh, nb, ora_dir.encode(), None) == 0
     for f in ("header", "km.bin", "rest.bin"):
         assert cases.md5_file(os.path.join(ref_dir, f)) == cases.md5_file(os.path.join(ora_dir, f)), f
     q = synth.neighbour_rich_queries(sp, 5000, 5000, seed=5)
     qf, of = str(tmp_path / "q.bin"), str(tmp_path / "o.bin")
     q.tofile(qf)
-    subprocess.run([REF, "query", ref_dir, qf, "31", of, "2"], check=True, capture_output=True)
+    subprocess.run([REF, "query", ref_dir, qf, str(k), of, "2"], check=True, capture_output=True)
     ref = np.fromfile(of, dtype=np.int32)
     h = oracle.kmxo_load(ref_dir.encode())
     occ = np.zeros(q.size, dtype=np.int32)
