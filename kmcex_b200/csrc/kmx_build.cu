@@ -43,21 +43,22 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x) {
 	return x;
 }
 
-// exclusive scan of one value per thread over a 256-thread block; *total = block sum
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t x, uint32_t* s_warp /*[9]*/, uint32_t* total) {
+// exclusive scan of one value per thread over a block of NW warps; *total = block sum
+template <int NW>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t x, uint32_t* s_warp /*[NW + 1]*/, uint32_t* total) {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t incl = warp_incl_scan(x);
 	__syncthreads();                      // s_warp may still be read by a previous call
 	if (lane == 31) s_warp[warp] = incl;
 	__syncthreads();
 	if (warp == 0) {
-		uint32_t w = lane < 8 ? s_warp[lane] : 0;
+		uint32_t w = lane < NW ? s_warp[lane] : 0;
 		uint32_t wi = warp_incl_scan(w);
-		if (lane < 8) s_warp[lane] = wi - w;
-		if (lane == 7) s_warp[8] = wi;
+		if (lane < NW) s_warp[lane] = wi - w;
+		if (lane == NW - 1) s_warp[NW] = wi;
 	}
 	__syncthreads();
-	*total = s_warp[8];
+	*total = s_warp[NW];
 	return s_warp[warp] + incl - x;
 }
 
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 			}
 		}
 		uint32_t total;
-		uint32_t rank = block_excl_scan(n_keep, s_warp, &total);
+		uint32_t rank = block_excl_scan<8>(n_keep, s_warp, &total);
 		uint64_t dst = __ldg(tile_off + tile) + rank;
 #pragma unroll
 		for (int j = 0; j < PER; j++) {
@@ -323,10 +324,14 @@ constexpr uint32_t kAccepted = 1u << kStateShift, kRejected = 2u << kStateShift;
 constexpr uint32_t kNeedShift = 14;                          // status: state(2) | contested(14) | untagged(14)
 constexpr uint32_t kMaskBits = (1u << kNeedShift) - 1;
 constexpr uint32_t kEpochMax = 0x3FFFu;
-constexpr uint32_t kIdTile = 256;                           // ids per reorder tile
+#ifndef KMX_INS_THREADS
+#define KMX_INS_THREADS 256
+#endif
+constexpr int kInsThreads = KMX_INS_THREADS;                // threads per block of the persistent insert kernel
+constexpr uint32_t kIdTile = kInsThreads;                   // ids per reorder tile = one block pass
 
 template <int K, int H, int B>
-__global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
+__global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
 	cg::grid_group grid = cg::this_grid();
 	constexpr int HM = H ? H : kMaxHash;
 	constexpr int BM = B ? B : kMaxArrays;
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 	const uint32_t slot_mask = a.resv_slots - 1;
 	InsertCtl* ctl = a.ctl;
 	volatile InsertCtl* vctl = a.ctl;
-	__shared__ uint32_t s_warp[9];
+	__shared__ uint32_t s_warp[kInsThreads / 32 + 1];
 
 	uint32_t epoch = vctl->epoch;
 	grid.sync();                                            // everybody has read ctl->epoch before it is rewritten
@@ -634,20 +639,24 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 			// accepted slots below F ("holes", ascending) are filled by the rejected items at or
 			// above F taken in DESCENDING index order.
 			if ((int)blockIdx.x < nb) {
-				// exclusive scan of this bucket's 1024 tile counters, 4 per thread
+				// exclusive scan of this bucket's tile counters: PER consecutive tiles per thread
 				const uint32_t i = blockIdx.x;
-				uint32_t* tf = a.tile_fail + i * (kBucket / kIdTile);
-				uint32_t x[4], sum = 0;
+				constexpr uint32_t kTilesPerBucket = kBucket / kIdTile;
+				constexpr uint32_t PER = (kTilesPerBucket + kInsThreads - 1) / kInsThreads;
+				uint32_t* tf = a.tile_fail + i * kTilesPerBucket;
+				uint32_t x[PER], sum = 0;
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
-					x[q] = __ldcg(tf + threadIdx.x * 4 + q);
+				for (uint32_t q = 0; q < PER; q++) {
+					const uint32_t at = threadIdx.x * PER + q;
+					x[q] = at < kTilesPerBucket ? __ldcg(tf + at) : 0;
 					sum += x[q];
 				}
 				uint32_t total;
-				uint32_t off = block_excl_scan(sum, s_warp, &total);
+				uint32_t off = block_excl_scan<kInsThreads / 32>(sum, s_warp, &total);
 #pragma unroll
-				for (int q = 0; q < 4; q++) {
-					tf[threadIdx.x * 4 + q] = off;
+				for (uint32_t q = 0; q < PER; q++) {
+					const uint32_t at = threadIdx.x * PER + q;
+					if (at < kTilesPerBucket) tf[at] = off;
 					off += x[q];
 				}
 				if (threadIdx.x == 0) {
@@ -686,7 +695,7 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 				if (tile * kIdTile - (i << kBucketLog) >= n_cur[i]) continue;
 				const bool failed = valid && (__ldcg(a.status + id) >> kStateShift) == 2u;
 				uint32_t total;
-				const uint32_t excl = __ldcg(a.tile_fail + tile) + block_excl_scan(failed ? 1u : 0u, s_warp, &total);
+				const uint32_t excl = __ldcg(a.tile_fail + tile) + block_excl_scan<kInsThreads / 32>(failed ? 1u : 0u, s_warp, &total);
 				const uint32_t F = n_next[i];
 				if (valid) {
 					if (failed) {
@@ -767,10 +776,10 @@ __global__ void __launch_bounds__(256, 4) insert_kernel(const __grid_constant__ 
 
 cudaError_t insert_grid_size(int* blocks_out, int sm_count) {
 	int per_sm = 0;
-	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<31, 7, 5>, 256, 0);
+	cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_kernel<31, 7, 5>, kInsThreads, 0);
 	if (e != cudaSuccess) return e;
 	int per_sm_g = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, insert_kernel<0, 0, 0>, 256, 0);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_g, insert_kernel<0, 0, 0>, kInsThreads, 0);
 	if (e != cudaSuccess) return e;
 	if (per_sm_g < per_sm) per_sm = per_sm_g;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
@@ -782,8 +791,8 @@ cudaError_t launch_insert(const DevModel& m, const InsertArgs& a, int grid_block
 	if (grid_blocks < m.n_bits) return cudaErrorInvalidConfiguration;
 	void* args[2] = { (void*)&m, (void*)&a };
 	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5)
-		return cudaLaunchCooperativeKernel((const void*)insert_kernel<31, 7, 5>, dim3(grid_blocks), dim3(256), args, 0, stream);
-	return cudaLaunchCooperativeKernel((const void*)insert_kernel<0, 0, 0>, dim3(grid_blocks), dim3(256), args, 0, stream);
+		return cudaLaunchCooperativeKernel((const void*)insert_kernel<31, 7, 5>, dim3(grid_blocks), dim3(kInsThreads), args, 0, stream);
+	return cudaLaunchCooperativeKernel((const void*)insert_kernel<0, 0, 0>, dim3(grid_blocks), dim3(kInsThreads), args, 0, stream);
 }
 
 // =========================================================================================

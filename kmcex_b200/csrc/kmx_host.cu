@@ -889,7 +889,7 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 		DA(&a.holepos, batch_items * 4, s);
 		DA(&a.list[0], batch_items * 4, s);
 		DA(&a.list[1], batch_items * 4, s);
-		DA(&a.tile_fail, batch_items / 256 * 4, s);
+		DA(&a.tile_fail, batch_items / 256 * 4, s);      // one counter per reorder tile (a tile is >= 256 ids)
 		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
 		a.resv_slots = 1u << 20;
 		if (const char* e = getenv("KMX_RESV_LOG2")) {
