@@ -132,6 +132,33 @@ uint64_t kmx_host_fastmod(uint64_t h, uint64_t d);                     /* the de
  * keeps item i; perm[j] = source index of output slot j; returns the new length            */
 int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm);
 
+/* ---- multi-GPU build: array-owner decomposition (option A) -------------
+ * One process per GPU.  Every rank calls prepare (decodes the database, fills the Bloom filters,
+ * allocates its exchange buffers and returns their 64-byte CUDA IPC handle), exchanges the handles
+ * (any out-of-band channel), calls connect with the handles of ranks 0..n_active-1 concatenated, then
+ * insert: rank r < n_active owns the coupled arrays a with a % n_active == r, the persistent kernels
+ * pass each bucket's survivors to the next owner through peer memory with a flag barrier per round.
+ * buffers() exposes the device pointers the caller's collectives complete (owned arrays are
+ * broadcast, km_back is OR-merged, survivor lists are concatenated); finish() builds the rest table.
+ * Results are identical to kmx_init_from_db for every n_active.                                   */
+typedef struct kmx_dist_buffers_t {
+	int32_t n_bits;
+	uint64_t cell_bytes;              /* bytes of one coupled array in the device layout          */
+	void* cells[8];                   /* device pointers, array a valid on its owner after insert */
+	void* km_back;
+	uint64_t km_back_bytes;
+	void* rest_kmer;                  /* this rank's survivors: u64 k-mers ...                    */
+	void* rest_occ;                   /* ... and u32 counts                                       */
+	uint64_t rest_n;
+	uint64_t insert_attempts, insert_accepted;
+} kmx_dist_buffers_t;
+int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, void* ipc_handle_out /* 64 bytes */);
+int kmx_dist_connect(kmx_model* m, const void* handles /* n_active * 64 bytes */);
+int kmx_dist_insert(kmx_model* m);
+int kmx_dist_buffers(kmx_model* m, kmx_dist_buffers_t* out);
+int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n,
+                    uint64_t attempts, uint64_t accepted);
+
 /* ---- roofline denominators: random 32-byte-sector throughput of the device (diagnostic) ------
  * kind 0: random 8-byte loads, 1: random 32-bit atomic OR, 2: random 64-bit atomic OR; 7 accesses
  * per item over `footprint_bytes` of device memory; *ms_out = milliseconds per launch             */

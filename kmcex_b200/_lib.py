@@ -42,6 +42,13 @@ class KmxDbInfo(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class KmxDistBuffers(C.Structure):
+    _fields_ = [
+        ("n_bits", C.c_int32), ("cell_bytes", C.c_uint64), ("cells", C.c_void_p * 8), ("km_back", C.c_void_p), ("km_back_bytes", C.c_uint64),
+        ("rest_kmer", C.c_void_p), ("rest_occ", C.c_void_p), ("rest_n", C.c_uint64), ("insert_attempts", C.c_uint64), ("insert_accepted", C.c_uint64),
+    ]
+
+
 # name -> (restype, argtypes); kept in one table so that the CPU test can check it against kmx.h
 SIGNATURES = {
     "kmx_last_error": (C.c_char_p, []),
@@ -74,6 +81,11 @@ SIGNATURES = {
     "kmx_host_sizes": (None, [C.POINTER(C.c_uint64), C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "kmx_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "kmx_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kmx_dist_insert": (C.c_int, [C.c_void_p]),
+    "kmx_dist_buffers": (C.c_int, [C.c_void_p, C.POINTER(KmxDistBuffers)]),
+    "kmx_dist_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 

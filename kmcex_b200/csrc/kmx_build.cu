@@ -349,7 +349,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 	__shared__ uint32_t s_warp[kInsThreads / 32 + 1];
 
 	uint32_t epoch = vctl->epoch;
-	grid.sync();                                            // everybody has read ctl->epoch before it is rewritten
+	uint32_t seq = vctl->seq;
+	grid.sync();                                            // everybody has read ctl->epoch / seq before they are rewritten
 
 	for (unsigned long long batch = a.first_batch; batch < a.first_batch + a.n_batches; batch++) {
 		const unsigned long long base = batch * total_ids;
@@ -384,8 +385,6 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			const bool last_round = (t == nb - 1);
 			const uint64_t* src_kmer = t == 0 ? a.item_kmer + base : a.buf_kmer[(t - 1) & 1];
 			const uint32_t* src_occ = t == 0 ? a.item_occ + base : a.buf_occ[(t - 1) & 1];
-			uint64_t* dst_kmer = a.buf_kmer[t & 1];
-			uint32_t* dst_occ = a.buf_occ[t & 1];
 
 			// ---------------- decide every item of the round ----------------
 			// ItemCtx: what every phase recomputes from the item (hashing is cheaper than keeping
@@ -473,16 +472,23 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				at = g.shfl(at, 0);
 				list[at + g.thread_rank()] = id;
 			};
-			// dense walk over the items of the round: x in [0, n_round) -> id
+			// With several GPUs, array x lives on rank x % n_active: this rank works on the buckets whose
+			// array of this round it owns (all of them on a single GPU).
+			const unsigned int par = (unsigned int)((batch * (unsigned long long)nb + (unsigned long long)t) & 1ULL);
+			uint32_t n_work[BM];
+#pragma unroll
+			for (int i = 0; i < BM; i++)
+				n_work[i] = (i < nb && ((i + t) % nb) % a.n_active == a.rank) ? n_cur[i] : 0;
+			// dense walk over this rank's items of the round: x in [0, n_round) -> id
 			uint32_t n_round = 0;
 #pragma unroll
-			for (int i = 0; i < BM; i++) n_round += n_cur[i];
+			for (int i = 0; i < BM; i++) n_round += n_work[i];
 			auto dense_to_id = [&](uint32_t x) -> uint32_t {
 				uint32_t i = 0;
 #pragma unroll
 				for (int q = 0; q < BM - 1; q++) {
-					if (x >= n_cur[q] && i == (uint32_t)q) {
-						x -= n_cur[q];
+					if (x >= n_work[q] && i == (uint32_t)q) {
+						x -= n_work[q];
 						i++;
 					}
 				}
@@ -638,7 +644,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			// F = number of rejected items.  Rejected items below F stay where they are; the
 			// accepted slots below F ("holes", ascending) are filled by the rejected items at or
 			// above F taken in DESCENDING index order.
-			if ((int)blockIdx.x < nb) {
+			if ((int)blockIdx.x < nb && (((int)blockIdx.x + t) % nb) % a.n_active == a.rank) {
 				// exclusive scan of this bucket's tile counters: PER consecutive tiles per thread
 				const uint32_t i = blockIdx.x;
 				constexpr uint32_t kTilesPerBucket = kBucket / kIdTile;
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					off += x[q];
 				}
 				if (threadIdx.x == 0) {
-					vctl->nfail[i] = total;
+					for (int p = 0; p < a.n_active; p++) ((volatile InsertCtl*)a.peer_ctl[p])->nfail[par][i] = total;   // every rank tracks every bucket
 					if (last_round) {
 						vctl->rest_base[i] = atomicAdd(&ctl->rest_n, (unsigned long long)total);
 						vctl->slot0_valid[i] = total ? 1u : 0u;
@@ -677,8 +683,9 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			unsigned long long rest_base[BM];
 #pragma unroll
 			for (int i = 0; i < BM; i++) {
-				n_next[i] = i < nb ? vctl->nfail[i] : 0;
-				rest_base[i] = (i < nb && last_round) ? vctl->rest_base[i] : 0;
+				const bool mine = i < nb && ((i + t) % nb) % a.n_active == a.rank;
+				n_next[i] = mine ? vctl->nfail[par][i] : 0;              // the other buckets' counts arrive with the round barrier
+				rest_base[i] = (mine && last_round) ? vctl->rest_base[i] : 0;
 			}
 			if (last_round) {
 #pragma unroll
@@ -691,8 +698,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			for (uint32_t tile = blockIdx.x; tile < n_id_tiles; tile += gridDim.x) {
 				const uint32_t id = tile * kIdTile + threadIdx.x;
 				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-				const bool valid = c < n_cur[i];                // uniform over the block: skip empty tiles
-				if (tile * kIdTile - (i << kBucketLog) >= n_cur[i]) continue;
+				const bool valid = c < n_work[i];               // uniform over the block: skip empty tiles
+				if (tile * kIdTile - (i << kBucketLog) >= n_work[i]) continue;
 				const bool failed = valid && (__ldcg(a.status + id) >> kStateShift) == 2u;
 				uint32_t total;
 				const uint32_t excl = __ldcg(a.tile_fail + tile) + block_excl_scan<kInsThreads / 32>(failed ? 1u : 0u, s_warp, &total);
@@ -710,11 +717,12 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 									vctl->slot0_occ[i] = occ;
 								}
 							} else {
-								dst_kmer[id] = v;
-								dst_occ[id] = occ;
+								const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;   // owner of this bucket's next array
+								a.peer_buf_kmer[t & 1][nx][id] = v;
+								a.peer_buf_occ[t & 1][nx][id] = occ;
 							}
 						} else {
-							a.rank[id] = excl;
+							a.excl_rank[id] = excl;
 						}
 					} else if (c < F) {
 						a.holepos[(i << kBucketLog) + (c - excl)] = c;
@@ -733,7 +741,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				const uint32_t F = n_next[i];
 				if (c < F) continue;
 				if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
-				const uint32_t d = F - __ldcg(a.rank + id) - 1;
+				const uint32_t d = F - __ldcg(a.excl_rank + id) - 1;
 				const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
 				const uint64_t v = __ldcg(src_kmer + id);
 				const uint32_t occ = __ldcg(src_occ + id);
@@ -745,8 +753,9 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 						vctl->slot0_occ[i] = occ;
 					}
 				} else {
-					dst_kmer[(i << kBucketLog) + to] = v;
-					dst_occ[(i << kBucketLog) + to] = occ;
+					const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;
+					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = v;
+					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = occ;
 				}
 			}
 			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;
@@ -758,20 +767,46 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			if (tid == 0) {
 				unsigned long long att = 0, fail = 0;
 				for (int i = 0; i < nb; i++) {
-					att += n_cur[i];
+					att += n_work[i];
 					fail += n_next[i];
 				}
 				vctl->attempts += att;
 				vctl->accepted += att - fail;
 				vctl->iterations += iter;
 			}
+			if (a.n_active > 1) __threadfence_system();          // survivors written into a peer's buffers
 			grid.sync();
 			if (tid == 0) vctl->phase_cycles[6] += (unsigned long long)(clock64() - tick);
+			if (a.n_active > 1) {
+				// round barrier across the GPUs: publish "round seq done" on every rank, wait for all of them
+				seq++;
+				if (tid == 0) {
+					__threadfence_system();
+					for (int p = 0; p < a.n_active; p++) ((volatile uint32_t*)a.peer_flags[p])[a.rank] = seq;
+					unsigned long long t0, t1;
+					asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+					for (int q = 0; q < a.n_active; q++) {
+						while ((int)(((volatile uint32_t*)a.peer_flags[a.rank])[q] - seq) < 0) {
+							asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+							if (t1 - t0 > 20000000000ULL) {          // 20 s: a peer died; give up instead of hanging the GPU
+								vctl->error = 3;
+								break;
+							}
+						}
+					}
+					__threadfence_system();
+				}
+				grid.sync();
+				if (vctl->error) return;                            // uniform over the grid
+			}
 #pragma unroll
-			for (int i = 0; i < BM; i++) n_cur[i] = n_next[i];
+			for (int i = 0; i < BM; i++) n_cur[i] = i < nb ? vctl->nfail[par][i] : 0;
 		}
 	}
-	if (tid == 0) vctl->epoch = epoch;
+	if (tid == 0) {
+		vctl->epoch = epoch;
+		vctl->seq = seq;
+	}
 }
 
 cudaError_t insert_grid_size(int* blocks_out, int sm_count) {

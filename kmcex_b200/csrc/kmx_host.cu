@@ -258,6 +258,23 @@ struct RestHost {
 	uint64_t suff_bin_size = 0, count = 0;
 };
 
+// what a build carries from one stage to the next (kmx_init_from_db runs the stages back to back)
+struct BuildState {
+	std::chrono::high_resolution_clock::time_point wall0;
+	uint64_t n_items = 0, n_batches = 0, rest_cap = 0;
+	uint64_t* d_item_kmer = nullptr;
+	uint32_t* d_item_occ = nullptr;
+	InsertArgs a = {};
+	int grid = 0;
+	bool worst_case = true;
+	float ms_upload = 0;
+	// multi-GPU: one cudaMalloc slab with everything peers write into, and the peers' slabs as mapped here
+	void* slab = nullptr;
+	size_t slab_bytes = 0, off[6] = { 0 };
+	uint32_t* flags = nullptr;
+	void* peer_slab[kMaxRanks] = { nullptr };
+};
+
 struct kmx_model {
 	int ci = 1, cs = 1023, n_hash = 7, n_bits = 5, bf_num = 1, k = 0;
 	int device = 0, sm_count = 0;
@@ -284,6 +301,7 @@ struct kmx_model {
 	DevModel dm;
 	kmx_info_t info;
 	DevCtx* x = nullptr;              // borrowed execution context (streams, events, staging)
+	BuildState bs;
 	std::vector<uint16_t> occ2bin16;
 };
 
@@ -455,6 +473,8 @@ extern "C" kmx_model* kmx_create(int ci, int cs, int n_hash, int n_bits) {
 	return m;
 }
 
+static void build_state_free(kmx_model* m);
+
 static int model_attach_device(kmx_model* m) {
 	if (m->x) return KMX_OK;
 	int rc = require_gpu(&m->sm_count);
@@ -477,6 +497,7 @@ extern "C" void kmx_destroy(kmx_model* m) {
 		cudaSetDevice(m->device);
 		cudaStreamSynchronize(m->x->stream);
 		cudaStreamSynchronize(m->x->stream2);
+		build_state_free(m);
 		free_model_device(m);
 		dev_free(m->d_occ2bin, m->x->stream);
 		dev_free(m->d_bin2mean, m->x->stream);
@@ -753,7 +774,8 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 }
 
 // =========================================================================================
-// build: KModel::init (kmodel.hpp:57-86)
+// build: KModel::init (kmodel.hpp:57-86), in stages so that the multi-GPU path can interleave
+// its exchanges:  encode (count + Bloom + item stream)  ->  insert  ->  rest table
 // =========================================================================================
 // bucket index over the top key bits (about one entry per bucket) + the per-prefix false-hit table
 // that reproduces the inclusive upper bound of KRestData::check_kmer (rest.hpp:233-237)
@@ -771,7 +793,7 @@ static int build_rest_side_tables(kmx_model* m) {
 	return KMX_OK;
 }
 
-static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups) {
+static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups) {
 	RestHost& r = m->rest;
 	cudaStream_t s = m->x->stream;
 	r.k = m->k;
@@ -799,17 +821,44 @@ static int build_rest_table(kmx_model* m, uint64_t* d_surv_kmer, uint32_t* d_sur
 	return KMX_OK;
 }
 
-extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
-	if (!m || !db) return fail(KMX_EARG, "null argument");
-	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
-	auto wall0 = std::chrono::high_resolution_clock::now();
+static void build_state_free(kmx_model* m) {
+	BuildState& b = m->bs;
+	if (!m->x) return;
+	cudaStream_t s = m->x->stream;
+	InsertArgs& a = b.a;
+	dev_free(b.d_item_kmer, s);
+	dev_free(b.d_item_occ, s);
+	if (!b.slab) {
+		for (int q = 0; q < 2; q++) {
+			dev_free(a.buf_kmer[q], s);
+			dev_free(a.buf_occ[q], s);
+		}
+		dev_free(a.ctl, s);
+	}
+	dev_free(a.status, s); dev_free(a.excl_rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s);
+	dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.claim, s);
+	dev_free(a.rest_kmer, s); dev_free(a.rest_occ, s);
+	if (b.slab) {
+		cudaStreamSynchronize(s);
+		for (int p = 0; p < kMaxRanks; p++)
+			if (b.peer_slab[p] && b.peer_slab[p] != b.slab) cudaIpcCloseMemHandle(b.peer_slab[p]);
+		cudaFree(b.slab);
+	}
+	b = BuildState();
+}
+
+// stage 1: pass 1 (class histogram, kmodel.hpp:423-434), filter allocation (kmodel.hpp:402-456),
+// pass 2 (Bloom inserts + array-bound stream, kmodel.hpp:68-74)
+static int build_stage_encode(kmx_model* m, kmx_db* db) {
+	BuildState& b = m->bs;
+	b.wall0 = std::chrono::high_resolution_clock::now();
 	int rc = model_attach_device(m);
 	if (rc) return rc;
-	TRACE(wall0, "device attached");
+	TRACE(b.wall0, "device attached");
 	CU(cudaSetDevice(m->device));
 	rc = kmx_db_upload(db);
 	if (rc) return rc;
-	TRACE(wall0, "database on device");
+	TRACE(b.wall0, "database on device");
 	if (db->device != m->device) return fail(KMX_EARG, "database is on device %d, model on device %d", db->device, m->device);
 	m->k = (int)db->info.k;
 	m->total_kmers = db->info.total_kmers;
@@ -819,8 +868,8 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	DevDb d = dev_db(db);
 	cudaStream_t s = m->x->stream;
 	cudaEvent_t* ev = m->x->ev_build;
+	b.ms_upload = db->ms_upload;
 
-	// ---- pass 1: class histogram (kmodel.hpp:423-434) ----
 	uint32_t* d_tile_cnt = nullptr;
 	uint64_t* d_tile_off = nullptr;
 	CountOut* d_count = nullptr;
@@ -834,9 +883,9 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	CountOut& cnt = m->x->h_pinned->count;
 	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, s));
 	CU(cudaEventRecord(ev[1], s));
-	TRACE(wall0, "count pass queued");
+	TRACE(b.wall0, "count pass queued");
 	CU(cudaStreamSynchronize(s));                        // sync 1 of 3: the sizes depend on the counts
-	TRACE(wall0, "count pass done");
+	TRACE(b.wall0, "count pass done");
 	dev_free(d_tile_cnt, s);
 	dev_free(d_count, s);
 	if (cnt.bad_count) {
@@ -859,71 +908,110 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	m->rest.pre_len = rest_prefix_len(m->k);
 	fill_dev_model(m);
 
-	// ---- pass 2: Bloom inserts + array-bound stream (kmodel.hpp:68-74) ----
-	const uint64_t n_items = cnt.array_bound;
-	uint64_t* d_item_kmer = nullptr;
-	uint32_t* d_item_occ = nullptr;
-	DA(&d_item_kmer, (n_items + 1) * 8, s);
-	DA(&d_item_occ, (n_items + 1) * 4, s);
-	CU(launch_encode(d, m->dm, d_tile_off, d_item_kmer, d_item_occ, m->sm_count, s));
+	b.n_items = cnt.array_bound;
+	DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
+	DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
+	CU(launch_encode(d, m->dm, d_tile_off, b.d_item_kmer, b.d_item_occ, m->sm_count, s));
 	dev_free(d_tile_off, s);
 	CU(cudaEventRecord(ev[2], s));
+	return KMX_OK;
+}
 
-	// ---- greedy insert (kmodel.hpp:508-573) ----
-	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
-	const uint64_t n_batches = (n_items + batch_items - 1) / batch_items;
-	InsertArgs a;
+// stage 2a: buffers of the greedy insert (kmodel.hpp:508-573).  shared = true puts the buffers
+// other GPUs write into (survivor ping-pong, control block, barrier flags) in one cudaMalloc
+// slab that can be exported with cudaIpcGetMemHandle.
+static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool shared) {
+	BuildState& b = m->bs;
+	cudaStream_t s = m->x->stream;
+	InsertArgs& a = b.a;
 	memset(&a, 0, sizeof(a));
-	InsertCtl& ctl = m->x->h_pinned->ctl;
-	memset(&ctl, 0, sizeof(ctl));
-	if (n_items > 0) {
-		a.item_kmer = d_item_kmer;
-		a.item_occ = d_item_occ;
-		a.n_items = n_items;
-		for (int b = 0; b < 2; b++) {
-			DA(&a.buf_kmer[b], batch_items * 8, s);
-			DA(&a.buf_occ[b], batch_items * 4, s);
+	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
+	b.n_batches = (b.n_items + batch_items - 1) / batch_items;
+	a.rank = rank;
+	a.n_active = n_active;
+	a.item_kmer = b.d_item_kmer;
+	a.item_occ = b.d_item_occ;
+	a.n_items = b.n_items;
+	if (shared) {
+		auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+		const size_t o_k0 = 0, o_k1 = o_k0 + up(batch_items * 8), o_o0 = o_k1 + up(batch_items * 8), o_o1 = o_o0 + up(batch_items * 4),
+		             o_ctl = o_o1 + up(batch_items * 4), o_flags = o_ctl + up(sizeof(InsertCtl));
+		b.slab_bytes = o_flags + up(kMaxRanks * 4);
+		CU(cudaMalloc(&b.slab, b.slab_bytes));
+		CU(cudaMemsetAsync(b.slab, 0, b.slab_bytes, s));
+		b.off[0] = o_k0; b.off[1] = o_k1; b.off[2] = o_o0; b.off[3] = o_o1; b.off[4] = o_ctl; b.off[5] = o_flags;
+		uint8_t* base = (uint8_t*)b.slab;
+		a.buf_kmer[0] = (uint64_t*)(base + o_k0);
+		a.buf_kmer[1] = (uint64_t*)(base + o_k1);
+		a.buf_occ[0] = (uint32_t*)(base + o_o0);
+		a.buf_occ[1] = (uint32_t*)(base + o_o1);
+		a.ctl = (InsertCtl*)(base + o_ctl);
+		b.flags = (uint32_t*)(base + o_flags);
+		b.peer_slab[rank] = b.slab;
+	} else {
+		for (int q = 0; q < 2; q++) {
+			DA(&a.buf_kmer[q], batch_items * 8, s);
+			DA(&a.buf_occ[q], batch_items * 4, s);
 		}
-		DA(&a.status, batch_items * 4, s);
-		DA(&a.rank, batch_items * 4, s);
-		DA(&a.holepos, batch_items * 4, s);
-		DA(&a.list[0], batch_items * 4, s);
-		DA(&a.list[1], batch_items * 4, s);
-		DA(&a.tile_fail, batch_items / 256 * 4, s);      // one counter per reorder tile (a tile is >= 256 ids)
-		CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
-		a.resv_slots = 1u << 20;
-		if (const char* e = getenv("KMX_RESV_LOG2")) {
-			int v = atoi(e);
-			if (v >= 10 && v <= 26) a.resv_slots = 1u << v;
-		}
-		DA(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4, s);
-		CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, s));
-		a.claim_log2 = 25;
-		if (const char* e = getenv("KMX_CLAIM_LOG2")) {
-			int v = atoi(e);
-			if (v >= 15 && v <= 30) a.claim_log2 = (uint32_t)v;
-		}
-		DA(&a.claim, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s);
-		CU(cudaMemsetAsync(a.claim, 0, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s));
 		DA(&a.ctl, sizeof(InsertCtl), s);
 		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), s));
-		a.max_iterations = kBucket + 64;
-		int grid = 0;
-		CU(insert_grid_size(&grid, m->sm_count));
-		// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
-		// all launches queue without a host round trip; beyond that it grows between launches.
-		const bool worst_case = n_items <= (1ULL << 28);
-		uint64_t rest_cap = worst_case ? n_items + m->n_bits : 0;
-		if (worst_case) {
-			DA(&a.rest_kmer, rest_cap * 8, s);
-			DA(&a.rest_occ, rest_cap * 4, s);
-		}
+	}
+	for (int q = 0; q < 2; q++) {
+		a.peer_buf_kmer[q][rank] = a.buf_kmer[q];
+		a.peer_buf_occ[q][rank] = a.buf_occ[q];
+	}
+	a.peer_ctl[rank] = a.ctl;
+	a.peer_flags[rank] = b.flags;
+	DA(&a.status, batch_items * 4, s);
+	DA(&a.excl_rank, batch_items * 4, s);
+	DA(&a.holepos, batch_items * 4, s);
+	DA(&a.list[0], batch_items * 4, s);
+	DA(&a.list[1], batch_items * 4, s);
+	DA(&a.tile_fail, batch_items / 256 * 4, s);      // one counter per reorder tile (a tile is >= 256 ids)
+	CU(cudaMemsetAsync(a.tile_fail, 0, batch_items / 256 * 4, s));
+	a.resv_slots = 1u << 20;
+	if (const char* e = getenv("KMX_RESV_LOG2")) {
+		int v = atoi(e);
+		if (v >= 10 && v <= 26) a.resv_slots = 1u << v;
+	}
+	DA(&a.resv, (size_t)m->n_bits * 2 * a.resv_slots * 4, s);
+	CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 2 * a.resv_slots * 4, s));
+	a.claim_log2 = 25;
+	if (const char* e = getenv("KMX_CLAIM_LOG2")) {
+		int v = atoi(e);
+		if (v >= 15 && v <= 30) a.claim_log2 = (uint32_t)v;
+	}
+	DA(&a.claim, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s);
+	CU(cudaMemsetAsync(a.claim, 0, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s));
+	a.max_iterations = kBucket + 64;
+	CU(insert_grid_size(&b.grid, m->sm_count));
+	// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
+	// all launches queue without a host round trip; beyond that it grows between launches.
+	b.worst_case = b.n_items <= (1ULL << 28);
+	b.rest_cap = b.worst_case ? b.n_items + m->n_bits : 0;
+	if (b.worst_case) {
+		DA(&a.rest_kmer, b.rest_cap * 8, s);
+		DA(&a.rest_occ, b.rest_cap * 4, s);
+	}
+	return KMX_OK;
+}
+
+// stage 2b: the launches (64 batches each); returns with the control block on the host
+static int build_stage_insert_run(kmx_model* m) {
+	BuildState& b = m->bs;
+	cudaStream_t s = m->x->stream;
+	InsertArgs& a = b.a;
+	InsertCtl& ctl = m->x->h_pinned->ctl;
+	memset(&ctl, 0, sizeof(ctl));
+	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
+	const bool participates = a.rank < a.n_active;
+	if (b.n_items > 0 && participates) {
 		const uint64_t chunk = 64;                         // batches per launch
-		for (uint64_t b0 = 0; b0 < n_batches; b0 += chunk) {
-			const uint64_t nb = std::min<uint64_t>(chunk, n_batches - b0);
+		for (uint64_t b0 = 0; b0 < b.n_batches; b0 += chunk) {
+			const uint64_t nb = std::min<uint64_t>(chunk, b.n_batches - b0);
 			const uint64_t need = ctl.rest_n + nb * batch_items + m->n_bits;
-			if (!worst_case && need > rest_cap) {
-				uint64_t new_cap = std::max<uint64_t>(need, rest_cap * 2);
+			if (!b.worst_case && need > b.rest_cap) {
+				uint64_t new_cap = std::max<uint64_t>(need, b.rest_cap * 2);
 				uint64_t* nk = nullptr;
 				uint32_t* no = nullptr;
 				DA(&nk, new_cap * 8, s);
@@ -936,64 +1024,73 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 				dev_free(a.rest_occ, s);
 				a.rest_kmer = nk;
 				a.rest_occ = no;
-				rest_cap = new_cap;
+				b.rest_cap = new_cap;
 			}
-			a.rest_cap = rest_cap;
+			a.rest_cap = b.rest_cap;
 			a.first_batch = b0;
 			a.n_batches = nb;
-			CU(launch_insert(m->dm, a, grid, s));
-			if (!worst_case) {
+			CU(launch_insert(m->dm, a, b.grid, s));
+			if (!b.worst_case) {
 				CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 				CU(cudaStreamSynchronize(s));
-				if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
+				if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow, 3: peer GPU timed out)", ctl.error);
 			}
 		}
 		CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 	}
-	CU(cudaEventRecord(ev[3], s));
-	TRACE(wall0, "encode + insert queued");
+	CU(cudaEventRecord(m->x->ev_build[3], s));
+	TRACE(b.wall0, "encode + insert queued");
 	CU(cudaStreamSynchronize(s));                        // sync 2 of 3: the sort needs the survivor count
-	TRACE(wall0, "insert done");
-	if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow)", ctl.error);
-	dev_free(d_item_kmer, s);
-	dev_free(d_item_occ, s);
-	for (int b = 0; b < 2; b++) {
-		dev_free(a.buf_kmer[b], s);
-		dev_free(a.buf_occ[b], s);
-	}
-	dev_free(a.status, s); dev_free(a.rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.claim, s); dev_free(a.ctl, s);
+	TRACE(b.wall0, "insert done");
+	if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow, 3: peer GPU timed out)", ctl.error);
+	return KMX_OK;
+}
 
-	// ---- rest table (rest.hpp:157-161) ----
+// stage 3: rest table (rest.hpp:157-161) from the survivors at d_rest_* (n of them), statistics, clean-up
+static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n) {
+	BuildState& b = m->bs;
+	cudaStream_t s = m->x->stream;
+	cudaEvent_t* ev = m->x->ev_build;
+	const InsertCtl ctl = m->x->h_pinned->ctl;
 	int32_t& groups = m->x->h_pinned->groups;
-	rc = build_rest_table(m, a.rest_kmer, a.rest_occ, ctl.rest_n, &groups);
+	int rc = build_rest_table(m, d_rest_kmer, d_rest_occ, rest_n, &groups);
 	if (rc) return rc;
-	dev_free(a.rest_kmer, s);
-	dev_free(a.rest_occ, s);
 	rc = build_rest_side_tables(m);
 	if (rc) return rc;
 	CU(cudaEventRecord(ev[4], s));
-	TRACE(wall0, "rest table queued");
+	TRACE(b.wall0, "rest table queued");
 	CU(cudaStreamSynchronize(s));                        // sync 3 of 3
-	TRACE(wall0, "rest table done");
+	TRACE(b.wall0, "rest table done");
 	m->rest.pre_buffer_size = groups + 1;                 // rest.hpp:119: new int[++pre_buffer_size]
 	fill_dev_model(m);
 	m->built = true;
-
 	kmx_info_t& f = m->info;
 	fill_info(m);
 	f.insert_attempts = ctl.attempts;
 	f.insert_accepted = ctl.accepted;
 	f.insert_iterations = ctl.iterations;
-	f.batches = n_batches;
+	f.batches = b.n_batches;
 	for (int i = 0; i < 8; i++) f.insert_phase_cycles[i] = ctl.phase_cycles[i];
-	f.ms_upload = db->ms_upload;
+	f.ms_upload = b.ms_upload;
 	CU(cudaEventElapsedTime(&f.ms_count, ev[0], ev[1]));
 	CU(cudaEventElapsedTime(&f.ms_encode, ev[1], ev[2]));
 	CU(cudaEventElapsedTime(&f.ms_insert, ev[2], ev[3]));
 	CU(cudaEventElapsedTime(&f.ms_rest, ev[3], ev[4]));
 	CU(cudaEventElapsedTime(&f.ms_total_device, ev[0], ev[4]));
-	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - wall0).count();
+	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - b.wall0).count();
+	build_state_free(m);
 	return KMX_OK;
+}
+
+extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
+	if (!m || !db) return fail(KMX_EARG, "null argument");
+	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
+	int rc = build_stage_encode(m, db);
+	if (!rc) rc = build_stage_insert_setup(m, 0, 1, false);
+	if (!rc) rc = build_stage_insert_run(m);
+	if (!rc) rc = build_stage_finish(m, m->bs.a.rest_kmer, m->bs.a.rest_occ, m->x->h_pinned->ctl.rest_n);
+	if (rc) build_state_free(m);
+	return rc;
 }
 
 extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
@@ -1006,6 +1103,83 @@ extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
 	kmx_db_close(db);
 	return rc;
 }
+
+// ---- multi-GPU build, array-owner decomposition (option A) ----------------------
+// Every rank decodes the database and fills the Bloom filters (replicated: order-free and cheap);
+// the coupled arrays are split by ownership -- array a lives on rank a % n_active -- and the
+// persistent insert kernels of the ranks hand each bucket's survivors to the next owner through
+// peer-mapped buffers, with a flag barrier per round.  The caller (kmcex_b200/distributed.py)
+// moves IPC handles and, afterwards, the finished pieces with torch.distributed.
+extern "C" int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, void* ipc_handle_out) {
+	if (!m || !db || !ipc_handle_out) return fail(KMX_EARG, "null argument");
+	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
+	if (n_active < 1 || n_active > kMaxRanks || n_active > m->n_bits || rank < 0) return fail(KMX_EARG, "n_active must be in 1..min(%d, n_bits)", kMaxRanks);
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+	int rc = build_stage_encode(m, db);
+	if (!rc) rc = build_stage_insert_setup(m, rank, n_active, true);
+	if (!rc) {
+		CU(cudaStreamSynchronize(m->x->stream));         // the slab is zeroed before anybody maps it
+		CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle_out, m->bs.slab));
+	}
+	if (rc) build_state_free(m);
+	return rc;
+}
+
+extern "C" int kmx_dist_connect(kmx_model* m, const void* handles) {
+	if (!m || !handles || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
+	BuildState& b = m->bs;
+	InsertArgs& a = b.a;
+	for (int p = 0; p < a.n_active; p++) {
+		if (p != a.rank || a.rank >= a.n_active) {
+			if (a.rank >= a.n_active) break;               // an idle rank maps nothing
+			cudaIpcMemHandle_t h;
+			memcpy(&h, (const uint8_t*)handles + 64 * p, 64);
+			CU(cudaIpcOpenMemHandle(&b.peer_slab[p], h, cudaIpcMemLazyEnablePeerAccess));
+		}
+		uint8_t* base = (uint8_t*)b.peer_slab[p];
+		a.peer_buf_kmer[0][p] = (uint64_t*)(base + b.off[0]);
+		a.peer_buf_kmer[1][p] = (uint64_t*)(base + b.off[1]);
+		a.peer_buf_occ[0][p] = (uint32_t*)(base + b.off[2]);
+		a.peer_buf_occ[1][p] = (uint32_t*)(base + b.off[3]);
+		a.peer_ctl[p] = (InsertCtl*)(base + b.off[4]);
+		a.peer_flags[p] = (uint32_t*)(base + b.off[5]);
+	}
+	return KMX_OK;
+}
+
+extern "C" int kmx_dist_insert(kmx_model* m) {
+	if (!m || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
+	return build_stage_insert_run(m);
+}
+
+extern "C" int kmx_dist_buffers(kmx_model* m, kmx_dist_buffers_t* out) {
+	if (!m || !out || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
+	memset(out, 0, sizeof(*out));
+	out->n_bits = m->n_bits;
+	out->cell_bytes = (cell_words(m->bytes[6]) + 1) * 8;
+	for (int i = 0; i < m->n_bits; i++) out->cells[i] = m->d_cells[i];
+	out->km_back = m->d_km_back;
+	out->km_back_bytes = pad8(m->bytes[7]);
+	out->rest_kmer = m->bs.a.rest_kmer;
+	out->rest_occ = m->bs.a.rest_occ;
+	out->rest_n = m->x->h_pinned->ctl.rest_n;
+	out->insert_attempts = m->x->h_pinned->ctl.attempts;
+	out->insert_accepted = m->x->h_pinned->ctl.accepted;
+	return KMX_OK;
+}
+
+extern "C" int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n,
+                               uint64_t attempts, uint64_t accepted) {
+	if (!m || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
+	if (rest_n && (!d_rest_kmer || !d_rest_occ)) return fail(KMX_EARG, "null survivor list");
+	m->x->h_pinned->ctl.attempts = attempts;
+	m->x->h_pinned->ctl.accepted = accepted;
+	CU(cudaDeviceSynchronize());                         // the caller's collectives ran on its own streams
+	int rc = build_stage_finish(m, d_rest_kmer, d_rest_occ, rest_n);
+	if (rc) build_state_free(m);
+	return rc;
+}
+
 // =========================================================================================
 // save / load (kmodel.hpp:173-235, rest.hpp:163-221)
 // =========================================================================================

@@ -47,13 +47,16 @@ cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d
 cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream);
 
 // greedy coupled-array insert: persistent cooperative kernel over batches [first, first+count)
+constexpr int kMaxRanks = 8;
+
 struct InsertCtl {                    // lives in device memory, survives across launches
 	unsigned long long rest_n;        // survivors appended to the rest list so far
 	unsigned long long attempts, accepted, iterations;
 	unsigned int list_n[2];           // entries of the two undecided-item lists
 	unsigned int epoch;               // reservation epoch (keys of newer epochs are smaller)
 	unsigned int error;               // non-zero: iteration cap hit / rest overflow
-	unsigned int nfail[kMaxArrays];   // survivors of each bucket after the current round
+	unsigned int nfail[2][kMaxArrays];   // survivors of each bucket after a round, by round parity (peers write it too)
+	unsigned int seq;                 // rounds completed: the cross-GPU barrier counts with it
 	unsigned long long rest_base[kMaxArrays];
 	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
 	unsigned int slot0_occ[kMaxArrays];
@@ -68,7 +71,7 @@ struct InsertArgs {
 	uint64_t* buf_kmer[2];            // [n_bits * kBucket] ping-pong survivor buffers
 	uint32_t* buf_occ[2];
 	uint32_t* status;                 // [n_bits * kBucket] state<<30 | reserve mask
-	uint32_t* rank;                   // [n_bits * kBucket]
+	uint32_t* excl_rank;              // [n_bits * kBucket]
 	uint32_t* holepos;                // [n_bits * kBucket]
 	uint32_t* tile_fail;              // [n_bits * kBucket / 256]
 	uint32_t* list[2];                // [n_bits * kBucket] ids still undecided, ping-pong
@@ -80,6 +83,13 @@ struct InsertArgs {
 	uint32_t* rest_occ;
 	unsigned long long rest_cap;
 	InsertCtl* ctl;
+	// array-owner decomposition over GPUs (SURVEY.md 8e option A): array a lives on active rank a % n_active;
+	// the peer_* pointers are this device's views of every active rank's exchange buffers (index = rank)
+	int rank, n_active;
+	uint64_t* peer_buf_kmer[2][kMaxRanks];
+	uint32_t* peer_buf_occ[2][kMaxRanks];
+	InsertCtl* peer_ctl[kMaxRanks];
+	uint32_t* peer_flags[kMaxRanks];  // peer_flags[p][r]: rounds rank r has completed, as visible on rank p
 	unsigned long long first_batch, n_batches;
 	unsigned int max_iterations;      // safety cap per round
 };

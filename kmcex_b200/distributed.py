@@ -79,6 +79,92 @@ def sharded_kmer_to_occ(answer: Callable[[np.ndarray], np.ndarray], kmers: np.nd
     return out
 
 
+class _DeviceBytes:
+    """a raw device allocation of libkmx.so as something torch can wrap without copying"""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def _view(ptr: int, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
+    t = torch.as_tensor(_DeviceBytes(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+    return t.view(dtype)
+
+
+def or_merge_(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """bitwise OR of `buf` over all ranks, in place (NCCL has no OR reduction: all-gather + local OR)"""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return buf
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    acc = parts[0]
+    for p in parts[1:]:
+        acc |= p
+    buf.copy_(acc)
+    return buf
+
+
+def concat_ranks(local: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
+    """concatenation over ranks (rank order) of the first n_local elements of `local`; every rank gets the whole"""
+    world = dist.get_world_size(group)
+    dev = local.device
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[dist.get_rank(group)] = n_local
+    dist.all_reduce(counts, group=group)
+    counts = counts.tolist()
+    width = max(max(counts), 1)
+    send = torch.zeros(width, dtype=local.dtype, device=dev)
+    send[:n_local] = local[:n_local]
+    parts = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(parts, send, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)]) if sum(counts) else torch.zeros(0, dtype=local.dtype, device=dev)
+
+
+def owner_of_array(a: int, n_active: int) -> int:
+    """array-owner decomposition: coupled array a lives on rank a % n_active"""
+    return a % n_active
+
+
+def build_array_owner(model, db, group=None, n_active: Optional[int] = None) -> None:
+    """KModel::init over the GPUs of one node, exactly (SURVEY.md section 8e, option A).
+
+    Every rank decodes the database and fills the Bloom filters; the coupled arrays are owned
+    round-robin by ranks 0..n_active-1 (n_active <= n_bits), whose insert kernels pass survivors to
+    the next owner through peer-mapped memory.  Afterwards the owned arrays are broadcast, km_back
+    is OR-merged and the survivor lists are concatenated, so that every rank holds the complete
+    model -- byte-identical to a single-GPU build."""
+    from ._lib import KmxDistBuffers, check, lib
+    import ctypes as C
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_bits = model.info["n_bits"]
+    n_active = min(world, n_bits, 8) if n_active is None else n_active
+    dev = torch.device("cuda", torch.cuda.current_device())
+    handle = (C.c_ubyte * 64)()
+    check(lib().kmx_dist_prepare(model._h, db._h, rank, n_active, handle))
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    blob = bytes(torch.cat(allh[:n_active]).cpu().numpy().tobytes())
+    check(lib().kmx_dist_connect(model._h, blob))
+    dist.barrier(group=group)                      # every rank has mapped its peers before any kernel writes
+    check(lib().kmx_dist_insert(model._h))
+    bufs = KmxDistBuffers()
+    check(lib().kmx_dist_buffers(model._h, C.byref(bufs)))
+    for a in range(n_bits):                        # owners publish their arrays
+        dist.broadcast(_view(bufs.cells[a], bufs.cell_bytes), src=owner_of_array(a, n_active), group=group)
+    or_merge_(_view(bufs.km_back, bufs.km_back_bytes, torch.int64), group)
+    n_local = int(bufs.rest_n)
+    cap = max(n_local, 1)
+    rest_k = concat_ranks(_view(bufs.rest_kmer, cap * 8, torch.int64) if bufs.rest_kmer else torch.zeros(1, dtype=torch.int64, device=dev), n_local, group)
+    rest_o = concat_ranks(_view(bufs.rest_occ, cap * 4, torch.int32) if bufs.rest_occ else torch.zeros(1, dtype=torch.int32, device=dev), n_local, group)
+    stats = torch.tensor([bufs.insert_attempts, bufs.insert_accepted], dtype=torch.int64, device=dev)
+    dist.all_reduce(stats, group=group)
+    torch.cuda.synchronize()
+    check(lib().kmx_dist_finish(model._h, rest_k.data_ptr() if rest_k.numel() else None, rest_o.data_ptr() if rest_o.numel() else None,
+                                rest_k.numel(), int(stats[0]), int(stats[1])))
+
+
 class ShardedKModel:
     """A KModel replica on this rank's GPU + the sharded batch query on top of it."""
 

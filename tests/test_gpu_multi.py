@@ -58,3 +58,42 @@ def test_two_ranks_replicated_model_sharded_queries(case_dbs, golden, tmp_path):
         assert hashlib.md5(occ.tobytes()).hexdigest() == golden[name]["occ_md5"]
         for f in ("header", "km.bin", "rest.bin"):
             assert cases.md5_file(str(tmp_path / f"replica_rank{r}" / f)) == golden[name]["model_md5"][f]
+
+
+def _owner_worker(rank, world, port, base, ci, work_dir, q_path):
+    import kmcex_b200 as kx
+    from kmcex_b200 import distributed as kd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    kx._lib.check(kx.lib().kmx_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m = kx.get_model(ci, cases.MODEL["cs"], cases.MODEL["n_hash"], cases.MODEL["n_bits"])
+        db = kx.KmcDatabase(base)
+        kd.build_array_owner(m, db)
+        out = os.path.join(work_dir, f"owner_rank{rank}")
+        os.makedirs(out, exist_ok=True)
+        m.save(out)
+        q = np.fromfile(q_path, dtype=np.uint64)
+        np.save(os.path.join(work_dir, f"owner_occ{rank}.npy"), kd.ShardedKModel(m).kmer_to_occ(q))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name", ["small_ci2", "multi_ci1"])
+def test_array_owner_build_is_byte_identical(name, case_dbs, golden, tmp_path):
+    """the coupled arrays split over the GPUs by ownership, survivors handed over through peer memory:
+    every rank must end with the reference's files, whatever the number of ranks"""
+    base, sp = case_dbs(name)
+    q = cases.case_queries(sp)
+    q_path = str(tmp_path / "q.u64")
+    q.tofile(q_path)
+    world = min(torch.cuda.device_count(), 5)
+    mp.spawn(_owner_worker, args=(world, _free_port(), base, cases.CASES[name]["ci"], str(tmp_path), q_path), nprocs=world, join=True)
+    for r in range(world):
+        for f in ("header", "km.bin", "rest.bin"):
+            assert cases.md5_file(str(tmp_path / f"owner_rank{r}" / f)) == golden[name]["model_md5"][f], (r, f)
+        occ = np.load(str(tmp_path / f"owner_occ{r}.npy"))
+        assert hashlib.md5(occ.tobytes()).hexdigest() == golden[name]["occ_md5"]
