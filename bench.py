@@ -192,6 +192,9 @@ def main() -> None:
     ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
     ap.add_argument("--workload", default="rs", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "array-owner"],
+                    help="N > 1 build: independent whole builds per rank (weak scaling) or ONE build with the coupled arrays owned by "
+                         "different GPUs (kmcex_b200.distributed.build_array_owner, strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -233,6 +236,9 @@ def main() -> None:
         return float(t.item())
 
     # ---------------- build, database resident in HBM ----------------
+    from kmcex_b200 import distributed as kd
+    owner_mode = world > 1 and args.parallelism == "array-owner"
+    builds_per_step = 1 if owner_mode else world          # array-owner: all ranks build ONE model together
     db = kx.KmcDatabase(meta["db"]).upload()
     infos, wall = [], []
     sampler = ClockSampler(local_rank)
@@ -243,7 +249,10 @@ def main() -> None:
         barrier()
         t0 = time.perf_counter()
         m = kx.get_model(meta["ci"], 1023, 7, 5)
-        m.init(db)
+        if owner_mode:
+            kd.build_array_owner(m, db)
+        else:
+            m.init(db)
         m.sync()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -255,7 +264,7 @@ def main() -> None:
     clocks = sampler.stop()
     t_build = max_over_ranks(sum(wall))
     ms_per_step = 1e3 * t_build / args.steps
-    value = world * n_kmers * args.steps / t_build            # every rank builds one model per step (replicas)
+    value = builds_per_step * n_kmers * args.steps / t_build
     info = infos[-1]
     dev_ms = float(np.mean([i["ms_total_device"] for i in infos]))
     ins_ms = float(np.mean([i["ms_insert"] for i in infos]))
@@ -268,14 +277,19 @@ def main() -> None:
         barrier()
         t0 = time.perf_counter()
         m2 = kx.get_model(meta["ci"], 1023, 7, 5)
-        m2.init(meta["db"])
+        if owner_mode:
+            db2 = kx.KmcDatabase(meta["db"])
+            kd.build_array_owner(m2, db2)
+            db2.close()
+        else:
+            m2.init(meta["db"])
         m2.sync()
         dt = time.perf_counter() - t0
         if step >= 2:
             e2e_wall.append(dt)
         m2.close()
     t_e2e = max_over_ranks(sum(e2e_wall))
-    e2e_value = world * n_kmers * args.steps / t_e2e
+    e2e_value = builds_per_step * n_kmers * args.steps / t_e2e
 
     # ---------------- retrieval ----------------
     q_all = np.fromfile(meta["queries"], dtype=np.uint64)
@@ -332,9 +346,9 @@ def main() -> None:
     q_sectors_est = None
     line = {
         "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if owner_mode else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": n_kmers, "k": 31, "n_hash": 7, "n_bits": 5, "ci": meta["ci"], "cs": 1023,
-                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": "replicas" if world > 1 else "single"},
+                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": (args.parallelism if world > 1 else "single")},
         "device_ms_per_step": dev_ms, "wall_ms_steps": [round(1e3 * w, 3) for w in wall], "e2e_wall_ms_steps": [round(1e3 * w, 3) for w in e2e_wall],
         "stage_ms": {k: float(np.mean([i[k] for i in infos])) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
         "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": meta["suffix_bytes"] + meta["prefix_bytes"], "d2h_bytes_per_step": 256,

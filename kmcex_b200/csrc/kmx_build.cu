@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				// round barrier across the GPUs: publish "round seq done" on every rank, wait for all of them
 				seq++;
 				if (tid == 0) {
+					const long long wait0 = clock64();
 					__threadfence_system();
 					for (int p = 0; p < a.n_active; p++) ((volatile uint32_t*)a.peer_flags[p])[a.rank] = seq;
 					unsigned long long t0, t1;
@@ -795,6 +796,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 						}
 					}
 					__threadfence_system();
+					vctl->phase_cycles[7] += (unsigned long long)(clock64() - wait0);
 				}
 				grid.sync();
 				if (vctl->error) return;                            // uniform over the grid

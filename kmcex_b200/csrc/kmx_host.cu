@@ -17,6 +17,7 @@
 #include <sys/stat.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -187,7 +188,7 @@ struct DevCtx {
 	cudaStream_t stream = nullptr, stream2 = nullptr;
 	cudaStream_t reader[4] = { nullptr, nullptr, nullptr, nullptr };
 	cudaEvent_t reader_ev[4][2] = {};
-	cudaEvent_t ev_build[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t ev_build[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
 		CountOut count;
 		InsertCtl ctl;
@@ -821,6 +822,19 @@ static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uin
 	return KMX_OK;
 }
 
+// Exchange slabs and peer mappings are kept for the life of the process: cudaMalloc / cudaFree and
+// cudaIpcOpenMemHandle cost milliseconds each, a rebuild with the same geometry reuses them.
+namespace {
+struct CachedSlab {
+	void* ptr;
+	size_t bytes;
+	int device;
+};
+std::mutex g_slab_mu;
+std::vector<CachedSlab> g_slab_free;
+std::map<std::string, void*> g_ipc_open;             // 64 handle bytes -> mapping in this process
+}  // namespace
+
 static void build_state_free(kmx_model* m) {
 	BuildState& b = m->bs;
 	if (!m->x) return;
@@ -840,9 +854,8 @@ static void build_state_free(kmx_model* m) {
 	dev_free(a.rest_kmer, s); dev_free(a.rest_occ, s);
 	if (b.slab) {
 		cudaStreamSynchronize(s);
-		for (int p = 0; p < kMaxRanks; p++)
-			if (b.peer_slab[p] && b.peer_slab[p] != b.slab) cudaIpcCloseMemHandle(b.peer_slab[p]);
-		cudaFree(b.slab);
+		std::lock_guard<std::mutex> lock(g_slab_mu);
+		g_slab_free.push_back(CachedSlab{ b.slab, b.slab_bytes, m->device });
 	}
 	b = BuildState();
 }
@@ -937,8 +950,18 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 		const size_t o_k0 = 0, o_k1 = o_k0 + up(batch_items * 8), o_o0 = o_k1 + up(batch_items * 8), o_o1 = o_o0 + up(batch_items * 4),
 		             o_ctl = o_o1 + up(batch_items * 4), o_flags = o_ctl + up(sizeof(InsertCtl));
 		b.slab_bytes = o_flags + up(kMaxRanks * 4);
-		CU(cudaMalloc(&b.slab, b.slab_bytes));
-		CU(cudaMemsetAsync(b.slab, 0, b.slab_bytes, s));
+		{
+			std::lock_guard<std::mutex> lock(g_slab_mu);
+			for (size_t q = 0; q < g_slab_free.size(); q++) {
+				if (g_slab_free[q].device == m->device && g_slab_free[q].bytes == b.slab_bytes) {
+					b.slab = g_slab_free[q].ptr;
+					g_slab_free.erase(g_slab_free.begin() + q);
+					break;
+				}
+			}
+		}
+		if (!b.slab) CU(cudaMalloc(&b.slab, b.slab_bytes));
+		CU(cudaMemsetAsync((uint8_t*)b.slab + o_ctl, 0, b.slab_bytes - o_ctl, s));   // control block + barrier flags start at zero
 		b.off[0] = o_k0; b.off[1] = o_k1; b.off[2] = o_o0; b.off[3] = o_o1; b.off[4] = o_ctl; b.off[5] = o_flags;
 		uint8_t* base = (uint8_t*)b.slab;
 		a.buf_kmer[0] = (uint64_t*)(base + o_k0);
@@ -1005,6 +1028,7 @@ static int build_stage_insert_run(kmx_model* m) {
 	memset(&ctl, 0, sizeof(ctl));
 	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
 	const bool participates = a.rank < a.n_active;
+	CU(cudaEventRecord(m->x->ev_build[5], s));           // the multi-GPU path spends host time between encode and here
 	if (b.n_items > 0 && participates) {
 		const uint64_t chunk = 64;                         // batches per launch
 		for (uint64_t b0 = 0; b0 < b.n_batches; b0 += chunk) {
@@ -1074,7 +1098,7 @@ static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const u
 	f.ms_upload = b.ms_upload;
 	CU(cudaEventElapsedTime(&f.ms_count, ev[0], ev[1]));
 	CU(cudaEventElapsedTime(&f.ms_encode, ev[1], ev[2]));
-	CU(cudaEventElapsedTime(&f.ms_insert, ev[2], ev[3]));
+	CU(cudaEventElapsedTime(&f.ms_insert, ev[5], ev[3]));
 	CU(cudaEventElapsedTime(&f.ms_rest, ev[3], ev[4]));
 	CU(cudaEventElapsedTime(&f.ms_total_device, ev[0], ev[4]));
 	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - b.wall0).count();
@@ -1134,7 +1158,15 @@ extern "C" int kmx_dist_connect(kmx_model* m, const void* handles) {
 			if (a.rank >= a.n_active) break;               // an idle rank maps nothing
 			cudaIpcMemHandle_t h;
 			memcpy(&h, (const uint8_t*)handles + 64 * p, 64);
-			CU(cudaIpcOpenMemHandle(&b.peer_slab[p], h, cudaIpcMemLazyEnablePeerAccess));
+			std::string key((const char*)&h, 64);
+			std::lock_guard<std::mutex> lock(g_slab_mu);
+			auto it = g_ipc_open.find(key);
+			if (it == g_ipc_open.end()) {
+				void* mapped = nullptr;
+				CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+				it = g_ipc_open.emplace(key, mapped).first;
+			}
+			b.peer_slab[p] = it->second;
 		}
 		uint8_t* base = (uint8_t*)b.peer_slab[p];
 		a.peer_buf_kmer[0][p] = (uint64_t*)(base + b.off[0]);
