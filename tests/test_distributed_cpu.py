@@ -42,6 +42,47 @@ def _load_oracle():
     return lib
 
 
+def _collective_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # OR-merge of a filter every rank filled partially (km_back in the array-owner build)
+        rng = np.random.default_rng(100 + rank)
+        part = torch.from_numpy(rng.integers(0, 1 << 62, 4096, dtype=np.int64) & rng.integers(0, 1 << 62, 4096, dtype=np.int64))
+        np.save(os.path.join(out_dir, f"part{rank}.npy"), part.numpy())
+        merged = kd.or_merge_(part.clone())
+        np.save(os.path.join(out_dir, f"merged{rank}.npy"), merged.numpy())
+        # concatenation of survivor lists of different lengths (rank order)
+        n_local = 5 + 7 * rank
+        local = torch.arange(100 * rank, 100 * rank + 64, dtype=torch.int64)
+        cat = kd.concat_ranks(local, n_local)
+        np.save(os.path.join(out_dir, f"cat{rank}.npy"), cat.numpy())
+        empty = kd.concat_ranks(torch.zeros(1, dtype=torch.int32), 0)
+        assert empty.numel() == 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_or_merge_and_concat_world2(tmp_path):
+    world = 2
+    mp.spawn(_collective_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(str(tmp_path / f"part{r}.npy")) for r in range(world)]
+    want = parts[0] | parts[1]
+    for r in range(world):
+        assert (np.load(str(tmp_path / f"merged{r}.npy")) == want).all()
+        cat = np.load(str(tmp_path / f"cat{r}.npy"))
+        assert cat.tolist() == list(range(0, 5)) + list(range(100, 112))
+
+
+def test_array_ownership_covers_every_array_once():
+    for n_bits in (1, 2, 5, 8):
+        for n_active in range(1, n_bits + 1):
+            owners = [kd.owner_of_array(a, n_active) for a in range(n_bits)]
+            assert set(owners) == set(range(n_active))            # every active rank owns something
+            assert max(owners.count(r) for r in range(n_active)) - min(owners.count(r) for r in range(n_active)) <= 1
+
+
 def _worker(rank, world, port, model_dir, work_dir, q_path, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
