@@ -109,7 +109,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch, from profiles/ (ncu --set full)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"rs": 1.618e9}        # profiles/r1_e_ncu_full_bench_rs.txt
 
 
 def random_sector_peaks() -> dict:
