@@ -132,6 +132,15 @@ uint64_t kmx_host_fastmod(uint64_t h, uint64_t d);                     /* the de
  * keeps item i; perm[j] = source index of output slot j; returns the new length            */
 int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm);
 
+/* ---- k-mer counting: the stage the reference delegates to the external `kmc` binary (main.cpp:136-140)
+ * Plain-text 4-line FASTQ files -> <out_base>.kmc_pre/.kmc_suf (KMC 2/3 layout, one bin): canonical k-mers, windows
+ * with a non-ACGT base skipped, k-mers seen fewer than ci times dropped, counters saturated at cs.            */
+typedef struct kmx_count_info_t {
+	uint64_t n_reads, n_windows, n_unique, n_kept;
+	uint32_t lut_prefix_length, counter_size;
+} kmx_count_info_t;
+int kmx_count_fastq(const char* const* fastq_paths, int n_files, int k, int ci, int cs, const char* out_base, kmx_count_info_t* info);
+
 /* ---- multi-GPU build: array-owner decomposition (option A) -------------
  * One process per GPU.  Every rank calls prepare (decodes the database, fills the Bloom filters,
  * allocates its exchange buffers and returns their 64-byte CUDA IPC handle), exchanges the handles

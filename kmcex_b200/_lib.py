@@ -42,6 +42,11 @@ class KmxDbInfo(C.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class KmxCountInfo(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_windows", C.c_uint64), ("n_unique", C.c_uint64), ("n_kept", C.c_uint64),
+                ("lut_prefix_length", C.c_uint32), ("counter_size", C.c_uint32)]
+
+
 class KmxDistBuffers(C.Structure):
     _fields_ = [
         ("n_bits", C.c_int32), ("cell_bytes", C.c_uint64), ("cells", C.c_void_p * 8), ("km_back", C.c_void_p), ("km_back_bytes", C.c_uint64),
@@ -81,6 +86,7 @@ SIGNATURES = {
     "kmx_host_sizes": (None, [C.POINTER(C.c_uint64), C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "kmx_count_fastq": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(KmxCountInfo)]),
     "kmx_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "kmx_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmx_dist_insert": (C.c_int, [C.c_void_p]),

@@ -55,6 +55,17 @@ static int fail(int code, const char* fmt, ...) {
 	return code;
 }
 
+namespace kmx {
+// error reporting for the other translation units of the library
+int set_error(int code, const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+}  // namespace kmx
+
 #define CU(call)                                                                                         \
 	do {                                                                                                 \
 		cudaError_t e__ = (call);                                                                        \

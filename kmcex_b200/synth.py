@@ -333,3 +333,45 @@ def make_db(base: str, shape: str, seed: int = 1, ci: int = 1, cs: int = 1023, l
     write_kmc_db(base, sp.kmers, sp.counts, k=sp.k, lut_prefix_length=lut_prefix_length, n_bins=n_bins,
                  min_count=ci, max_count=cs)
     return sp
+
+
+def synth_fastq(path: str, genome_bp: int = 20_000, coverage: float = 20.0, read_len: int = 100, k: int = 31, seed: int = 1,
+                err_rate: float = 0.01, n_rate: float = 0.002, crlf: bool = False):
+    """Write a small 4-line FASTQ file of simulated reads (substitution errors, a few N, random case is NOT
+    used) and return the canonical k-mer spectrum a counter must find in it: (kmers uint64 sorted, counts int64).
+    Pure numpy: meant for tests of the k-mer counting stage."""
+    rng = np.random.default_rng(seed)
+    genome = rng.integers(0, 4, genome_bp, dtype=np.uint8)
+    n_reads = int(genome_bp * coverage / read_len)
+    starts = rng.integers(0, genome_bp - read_len + 1, n_reads)
+    lens = np.where(rng.random(n_reads) < 0.05, rng.integers(k - 5, read_len, n_reads), read_len)      # a few short reads
+    reads = []
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    eol = "\r\n" if crlf else "\n"
+    all_k, mask = [], np.uint64((1 << (2 * k)) - 1)
+    with open(path, "w", newline="") as f:
+        for r in range(n_reads):
+            codes = genome[starts[r]:starts[r] + lens[r]].copy()
+            if rng.random() < 0.5:                       # reverse strand
+                codes = (3 - codes)[::-1]
+            err = rng.random(codes.size) < err_rate
+            codes[err] = (codes[err] + rng.integers(1, 4, int(err.sum()))) % 4
+            seq = alphabet[codes].copy()
+            isn = rng.random(codes.size) < n_rate
+            seq[isn] = ord("N")
+            f.write(f"@read{r}{eol}{seq.tobytes().decode()}{eol}+{eol}{'I' * codes.size}{eol}")
+            # expected k-mers of this read
+            if codes.size >= k:
+                valid = ~isn
+                v = np.zeros(codes.size - k + 1, dtype=np.uint64)
+                ok = np.ones(codes.size - k + 1, dtype=bool)
+                for j in range(k):
+                    v = (v << np.uint64(2)) | codes[j:j + v.size].astype(np.uint64)
+                    ok &= valid[j:j + v.size]
+                v = v[ok] & mask
+                if v.size:
+                    rc = revcomp_packed(torch.from_numpy(v.astype(np.int64)), k).numpy().astype(np.uint64)
+                    all_k.append(np.minimum(v, rc))
+    allk = np.concatenate(all_k) if all_k else np.zeros(0, dtype=np.uint64)
+    u, c = np.unique(allk, return_counts=True)
+    return u, c.astype(np.int64), n_reads

@@ -66,6 +66,13 @@ def test_kmcex_command_line(case_dbs, golden, tmp_path):
     save_dir = os.path.join(work, os.path.basename(base))          # main.cpp:147: workdir/basename(output)
     for f in ("header", "km.bin", "rest.bin"):
         assert cases.md5_file(os.path.join(save_dir, f)) == golden[name]["model_md5"][f], f
+    # no database yet: the FASTQ input is counted on the GPU, then the model is built from it
+    fq = str(tmp_path / "reads.fastq")
+    want_k, want_c, _ = synth.synth_fastq(fq, genome_bp=20_000, coverage=20, read_len=100, k=31, seed=4)
+    r = subprocess.run([exe, "-k31", "-ci2", fq, str(tmp_path / "counted"), work], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"kept {int((want_c >= 2).sum())}" in r.stdout
+    assert os.path.exists(os.path.join(work, "counted", "km.bin"))
     # too few arguments: usage + non-zero exit (main.cpp:131-134)
     r = subprocess.run([exe, "-k31"], capture_output=True, text=True)
     assert r.returncode != 0 and "kmcEx" in r.stdout

@@ -1,13 +1,15 @@
 // kmcex_cli.cpp -- the `kmcEx` command line on top of include/kmodel.hpp (row N2 of SURVEY.md 8f).
 // Same positional arguments, options, defaults and stdout lines as the reference driver
 // (main.cpp:16-150).  The counting stage is the external `kmc` binary (main.cpp:136-140), which
-// is not part of this repository: it is invoked when ./kmc_api/kmc exists, and otherwise an
-// existing <output_file_name>.kmc_pre/.kmc_suf database is used as it is.
+// is not part of this repository: it is invoked when ./kmc_api/kmc exists; otherwise an existing
+// <output_file_name>.kmc_pre/.kmc_suf database is used as it is, and if there is none the FASTQ
+// input is counted on the GPU (kmx_count_fastq).
 //
 //   g++ -std=c++11 -O2 -Iinclude tools/kmcex_cli.cpp -Lkmcex_b200 -lkmx -Wl,-rpath,$PWD/kmcex_b200 -o kmcEx
 #include <sys/stat.h>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include "kmodel.hpp"
 
 struct Options {
@@ -58,8 +60,34 @@ int main(int argc, char** argv) {
 		std::cout << cmd << std::endl;
 		if (system(cmd) != 0) std::cout << "kmc returned a non-zero status" << std::endl;
 		std::cout << std::endl;
-	} else {
+	} else if (stat((o.output + ".kmc_pre").c_str(), &st) == 0) {
 		std::cout << "./kmc_api/kmc not found: using the existing database " << o.output << std::endl;
+	} else {
+		// the counting stage on the GPU (kmx_count_fastq): plain-text FASTQ, or @file listing one path per line
+		std::vector<std::string> files;
+		if (!o.input.empty() && o.input[0] == '@') {
+			std::ifstream lst(o.input.substr(1));
+			std::string line;
+			while (std::getline(lst, line))
+				if (!line.empty()) files.push_back(line);
+		} else {
+			files.push_back(o.input);
+		}
+		std::vector<const char*> paths;
+		for (auto& f : files)
+			if (stat(f.c_str(), &st) == 0) paths.push_back(f.c_str());
+		if (paths.size() != files.size() || paths.empty()) {
+			// like a failed kmc run in the reference: carry on, KModel::init reports the missing database
+			std::cout << "input file(s) not found, no k-mer database produced" << std::endl;
+			paths.clear();
+		}
+		std::cout << "./kmc_api/kmc not found: counting " << files.size() << " FASTQ file(s) on the GPU" << std::endl;
+		kmx_count_info_t ci = {};
+		if (!paths.empty() && kmx_count_fastq(paths.data(), (int)paths.size(), o.k, o.ci, o.cs, o.output.c_str(), &ci) != KMX_OK) {
+			std::cout << kmx_last_error() << std::endl;
+			return 1;
+		}
+		if (!paths.empty()) std::cout << "   reads " << ci.n_reads << ", k-mers " << ci.n_windows << ", unique " << ci.n_unique << ", kept " << ci.n_kept << std::endl;
 	}
 	KModel* kmodel = get_model(o.ci, o.cs, o.num_hash, o.num_bit);
 	kmodel->init(o.output);
