@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmx.so")
+LIB_PATH = os.environ.get("KMX_LIB_PATH", os.path.join(_HERE, "libkmx.so"))   # override: A/B builds of the kernels
 
 
 class KmxInfo(C.Structure):

@@ -395,12 +395,10 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				uint32_t bin, c;
 				int arr;
 			};
-			auto load_item = [&](uint32_t id, ItemCtx& it) {
+			auto prepare_item = [&](uint32_t id, uint64_t v, uint32_t occ, ItemCtx& it) {
 				const uint32_t i = id >> kBucketLog;
 				it.c = id & (kBucket - 1);
 				it.arr = (int)((i + (uint32_t)t) % (uint32_t)nb);
-				const uint64_t v = __ldcg(src_kmer + id);
-				const uint32_t occ = __ldcg(src_occ + id);
 				it.bin = __ldg(m.occ2bin + (occ > (uint32_t)m.cs ? (uint32_t)m.cs : occ));
 				it.r = reverse_bases(v, k);
 				HashPrep p;
@@ -409,6 +407,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				for (int j = 0; j < HM; j++)
 					if (j < nh) it.pos[j] = fastmod(hash_finish(p, k, m.arr_seed[it.arr][j]), m.arr_mod);
 			};
+			auto load_item = [&](uint32_t id, ItemCtx& it) { prepare_item(id, __ldcg(src_kmer + id), __ldcg(src_occ + id), it); };
 			// read the item's cells: conflict with the committed state? which positions are still untagged?
 			auto read_cells = [&](const ItemCtx& it, bool& conflict, uint32_t& untagged) {
 				unsigned long long cell[HM];
@@ -500,12 +499,28 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			const uint32_t claim_mask = (1u << claim_log2) - 1;
 			const size_t claim_stride = (size_t)1 << (a.claim_log2 - 5);     // words per (array, want) bitmap
 
+			if (epoch + 2 >= kEpochMax) {                      // reservation keys can get no smaller: start the epochs over
+				for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
+				epoch = 0;
+				grid.sync();
+			}
 			long long tick = clock64();
 			// ---- first iteration, phase 0: reject on the committed state, or claim (position, wanted value) ----
+			// (the next item's k-mer and count are fetched while the current one is hashed and probed)
+			uint32_t id_n = tid < n_round ? dense_to_id(tid) : 0;
+			uint64_t v_n = tid < n_round ? __ldcg(src_kmer + id_n) : 0;
+			uint32_t occ_n = tid < n_round ? __ldcg(src_occ + id_n) : 0;
 			for (uint32_t x = tid; x < n_round; x += T) {
-				const uint32_t id = dense_to_id(x);
+				const uint32_t id = id_n;
+				const uint64_t v_c = v_n;
+				const uint32_t occ_c = occ_n;
+				if (x + T < n_round) {
+					id_n = dense_to_id(x + T);
+					v_n = __ldcg(src_kmer + id_n);
+					occ_n = __ldcg(src_occ + id_n);
+				}
 				ItemCtx it;
-				load_item(id, it);
+				prepare_item(id, v_c, occ_c, it);
 				bool conflict;
 				uint32_t untagged;
 				read_cells(it, conflict, untagged);
@@ -586,7 +601,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			}
 			// ---- later iterations walk the list of still undecided (contested) items ----
 			while (n_list != 0) {
-				if (epoch >= kEpochMax) {                       // keys can get no smaller: start over
+				if (epoch + 1 >= kEpochMax) {                   // keys can get no smaller: start over
 					for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
 					epoch = 0;
 					grid.sync();

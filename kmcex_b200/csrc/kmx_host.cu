@@ -197,8 +197,8 @@ static int rest_prefix_len(int k) {              // rest.hpp:78-83
 struct DevCtx {
 	int device = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaStream_t reader[4] = { nullptr, nullptr, nullptr, nullptr };
-	cudaEvent_t reader_ev[4][2] = {};
+	cudaStream_t reader[8] = {};
+	cudaEvent_t reader_ev[8][2] = {};
 	cudaEvent_t ev_build[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
 		CountOut count;
@@ -641,7 +641,7 @@ extern "C" void kmx_db_info(const kmx_db* db, kmx_db_info_t* info) {
 // Process-wide pinned bounce buffers for file -> device streaming (allocated once, kept).
 namespace {
 constexpr size_t kChunk = 8u << 20;
-constexpr int kReaders = 4, kSlotsPerReader = 2;
+constexpr int kReaders = 8, kSlotsPerReader = 2;
 struct Bounce {
 	std::mutex mu;
 	uint8_t* buf[kReaders][kSlotsPerReader] = {};
@@ -683,7 +683,9 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 	CU(cudaStreamSynchronize(x->stream));                // the allocation is usable from the reader streams now
 	TRACE(t0, "upload: buffers ready");
 	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
-	const int n_thr = (int)std::min<uint64_t>(kReaders, n_chunks);
+	int want_thr = 4;
+	if (const char* e = getenv("KMX_READERS")) want_thr = std::max(1, std::min(kReaders, atoi(e)));
+	const int n_thr = (int)std::min<uint64_t>(want_thr, n_chunks);
 	std::vector<int> status(kReaders, KMX_OK);
 	auto work = [&](int t) {
 		cudaSetDevice(db->device);
@@ -990,6 +992,11 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 		DA(&a.ctl, sizeof(InsertCtl), s);
 		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), s));
 	}
+	if (const char* e = getenv("KMX_TEST_EPOCH_START")) {    // lets a small test cross the epoch wrap-around
+		const unsigned int start = (unsigned int)atoi(e);
+		CU(cudaMemcpyAsync(&a.ctl->epoch, &start, sizeof(start), cudaMemcpyHostToDevice, s));
+		CU(cudaStreamSynchronize(s));
+	}
 	for (int q = 0; q < 2; q++) {
 		a.peer_buf_kmer[q][rank] = a.buf_kmer[q];
 		a.peer_buf_occ[q][rank] = a.buf_occ[q];
@@ -1021,7 +1028,7 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	CU(insert_grid_size(&b.grid, m->sm_count));
 	// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
 	// all launches queue without a host round trip; beyond that it grows between launches.
-	b.worst_case = b.n_items <= (1ULL << 28);
+	b.worst_case = b.n_items <= (1ULL << 28) && !getenv("KMX_TEST_GROW_REST");   // the env var lets a small test take the growing path
 	b.rest_cap = b.worst_case ? b.n_items + m->n_bits : 0;
 	if (b.worst_case) {
 		DA(&a.rest_kmer, b.rest_cap * 8, s);

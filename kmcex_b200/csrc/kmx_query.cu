@@ -295,8 +295,11 @@ __device__ __forceinline__ uint64_t encode_ascii(const char* s, int k) {
 	return v;
 }
 
+#ifndef KMX_QUERY_BLOCKS
+#define KMX_QUERY_BLOCKS 2
+#endif
 template <int K, int H, int B, bool ASCII>
-__global__ void __launch_bounds__(256, 2) query_fast_kernel(const __grid_constant__ DevModel m, const void* __restrict__ input, size_t stride,
+__global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const __grid_constant__ DevModel m, const void* __restrict__ input, size_t stride,
                                                             size_t n, int32_t* __restrict__ out, int32_t* __restrict__ path_out,
                                                             DeferredQuery* __restrict__ defer, unsigned int* __restrict__ defer_n) {
 	const int k = K ? K : m.k;

@@ -210,6 +210,24 @@ def test_empty_and_tiny_batches(built):
     assert (occ[-12345:] == m.kmer_to_occ(big[-12345:])).all()
 
 
+@pytest.mark.parametrize("env", [{"KMX_TEST_EPOCH_START": "16370"}, {"KMX_TEST_GROW_REST": "1"}, {"KMX_RESV_LOG2": "12", "KMX_CLAIM_LOG2": "15"}])
+def test_rare_paths_keep_parity(env, case_dbs, golden, tmp_path, monkeypatch):
+    """paths that only large inputs reach: reservation-epoch wrap-around, survivor list grown between launches,
+    and heavily aliased reservation / claim tables (aliasing may only delay decisions, never change them)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("small_ci2", "multi_ci1"):
+        base, sp = case_dbs(name)
+        m = kx.get_model(cases.CASES[name]["ci"], cases.MODEL["cs"], cases.MODEL["n_hash"], cases.MODEL["n_bits"])
+        m.init(base)
+        out = str(tmp_path / (name + "_".join(env)))
+        os.makedirs(out)
+        m.save(out)
+        for f in ("header", "km.bin", "rest.bin"):
+            assert cases.md5_file(os.path.join(out, f)) == golden[name]["model_md5"][f], (env, name, f)
+        m.close()
+
+
 def test_reference_error_corners_are_reported_not_computed(tmp_path):
     # fewer than 8 k-mers in a Bloom class: the reference aborts in new uint8_t[0]{0} (kmodel.hpp:413-417)
     base = str(tmp_path / "db")
