@@ -36,6 +36,7 @@ WORKLOADS = {
     "cfg1": ("cfg1", 1, 3, 8, "configs[0]: 1M-read 100bp, ci1"),
     "rs": ("rs", 2, 7, 16, "configs[1]: GAGE-RS-shaped synthetic (4.6 Mbp, 100x, 101bp) k31 nh7 nb5 ci2"),
     "hc14": ("hc14", 1, 7, 64, "configs[2]: GAGE-HC14-shaped synthetic (88 Mbp, 40x) k31 nh7 nb5 ci1"),
+    "wgs350": ("wgs350", 2, 7, 128, "scale check towards configs[3]: 350 Mbp synthetic genome, 30x, k31 nh7 nb5 ci2"),
 }
 CACHE = os.environ.get("KMX_BENCH_CACHE", "/tmp/kmx_bench")
 
@@ -109,7 +110,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch, from profiles/ (ncu --set full)
-NCU_TRAFFIC = {"rs": 1.618e9}        # profiles/r1_e_ncu_full_bench_rs.txt
+NCU_TRAFFIC = {"rs": 1.587e9}        # profiles/r1_e_ncu_full_bench_rs.txt
 
 
 def random_sector_peaks() -> dict:
@@ -268,7 +269,8 @@ def main() -> None:
     info = infos[-1]
     dev_ms = float(np.mean([i["ms_total_device"] for i in infos]))
     ins_ms = float(np.mean([i["ms_insert"] for i in infos]))
-    launches_per_step = 1 + 1 + 1 + (info["batches"] + 63) // 64 + 6     # count, scan, encode, insert launches, rest sort/index
+    # our kernels per build: count, tile scan, encode, one insert launch per 64 batches, rest first/index/fine/quirk (the CUB sort launches are not counted)
+    launches_per_step = 3 + (info["batches"] + 63) // 64 + 4
 
     # ---------------- build, end to end from the files (host buffers) ----------------
     e2e_wall = []

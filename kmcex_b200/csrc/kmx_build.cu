@@ -521,9 +521,14 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				}
 				ItemCtx it;
 				prepare_item(id, v_c, occ_c, it);
-				bool conflict;
-				uint32_t untagged;
-				read_cells(it, conflict, untagged);
+				bool conflict = false;
+				uint32_t untagged = (1u << nh) - 1u;
+				// claim_first (models that do not fit the L2): claim every position without looking at the cells, so that
+				// phase 1 reads a cell and commits to it back to back while its sector is still in the L2 -- one
+				// DRAM round trip per sector instead of a read here and a read-modify-write there.  Claims on
+				// tagged positions and claims of items that turn out rejected are harmless: a claim can only
+				// send somebody through the reservation path.
+				if (!a.claim_first) read_cells(it, conflict, untagged);
 				if (conflict) {
 					reject(id);
 				} else {
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 							atomicOr(cl + ((it.bin >> j) & 1u) * claim_stride + (bit >> 5), 1u << (bit & 31u));
 						}
 					}
-					a.status[id] = untagged;
+					if (!a.claim_first) a.status[id] = untagged;
 				}
 			}
 			grid.sync();
@@ -551,10 +556,18 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
 			for (uint32_t x = tid; x < n_round; x += T) {
 				const uint32_t id = dense_to_id(x);
-				const uint32_t untagged = a.status[id];
+				uint32_t untagged = a.claim_first ? 0u : a.status[id];
 				if (untagged >> kStateShift) continue;
 				ItemCtx it;
 				load_item(id, it);
+				if (a.claim_first) {
+					bool conflict;
+					read_cells(it, conflict, untagged);
+					if (conflict) {
+						reject(id);
+						continue;
+					}
+				}
 				const uint32_t* cl = a.claim + (size_t)it.arr * 2 * claim_stride;
 				uint32_t need = 0;
 #pragma unroll

@@ -1024,6 +1024,10 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	}
 	DA(&a.claim, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s);
 	CU(cudaMemsetAsync(a.claim, 0, (size_t)m->n_bits * 2 * ((size_t)1 << (a.claim_log2 - 5)) * 4, s));
+	// claim_first merges the cell read with the commit (see insert_kernel phase 0).  Measured on B200 it is a wash
+	// for HBM-resident models (hc14 shape: 187 ms against 186 ms) and slower for L2-resident ones, so it stays off.
+	a.claim_first = 0;
+	if (const char* e = getenv("KMX_CLAIM_FIRST")) a.claim_first = atoi(e) ? 1 : 0;
 	a.max_iterations = kBucket + 64;
 	CU(insert_grid_size(&b.grid, m->sm_count));
 	// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets

@@ -322,6 +322,7 @@ def make_db(base: str, shape: str, seed: int = 1, ci: int = 1, cs: int = 1023, l
         "cfg1": (2_000_000, 50, 100, "reads"),          # 1 M reads x 100 bp
         "rs": (4_600_000, 100, 101, "reads"),          # GAGE R. sphaeroides shaped
         "hc14": (88_000_000, 40, 101, "direct"),
+        "wgs350": (350_000_000, 30, 101, "direct"),     # a quarter-gigabase genome: > 2^28 array k-mers, HBM-resident everything
         "na12878": (3_100_000_000, 30, 101, "direct"),
     }
     g, c, l, mode = shapes[shape]
