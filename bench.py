@@ -327,6 +327,23 @@ def main() -> None:
     t_qe = max_over_ranks(sum(q_e2e))
     qps_e2e = world * per * args.steps / t_qe
     assert bool((out_host.to(dev) == out_dev).all())
+    # the reference-facing form of the call: ASCII strings (kmer_to_occ(vector<string>)), flattened at stride k
+    from kmcex_b200 import synth as _synth
+    n_a = min(per, 1 << 22)
+    a_host = torch.from_numpy(_synth.to_ascii(q_all[rank * per: rank * per + n_a], 31)).pin_memory()
+    a_out = torch.empty(n_a, dtype=torch.int32).pin_memory()
+    q_asc = []
+    for step in range(2 + args.steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        kx._lib.check(kx.lib().kmx_query_ascii(m._h, a_host.data_ptr(), 31, n_a, a_out.data_ptr()))
+        dt = time.perf_counter() - t0
+        if step >= 2:
+            q_asc.append(dt)
+    t_qa = max_over_ranks(sum(q_asc))
+    qps_ascii = world * n_a * args.steps / t_qa
+    assert bool((a_out == out_host[:n_a]).all())
 
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peaks()
@@ -356,7 +373,9 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": meta["suffix_bytes"] + meta["prefix_bytes"], "d2h_bytes_per_step": 256,
                 "ms_per_step": 1e3 * t_e2e / args.steps},
         "query": {"value": qps, "unit": "queries/s", "batch": per, "ms_per_batch": 1e3 * t_q / args.steps,
-                  "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": per * 4}},
+                  "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": per * 4},
+                  "e2e_ascii": {"value": qps_ascii, "unit": "queries/s", "batch": n_a, "h2d_bytes_per_step": n_a * 31, "d2h_bytes_per_step": n_a * 4,
+                                "note": "kmx_query_ascii: 31-character strings at stride 31, encoded to 2 bits on the device"}},
         "gpu_launches": int(launches_per_step * args.steps),
         "roofline": roofline,
         "clocks": clocks,

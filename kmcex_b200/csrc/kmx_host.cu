@@ -210,10 +210,12 @@ struct DevCtx {
 	int32_t* h_out[2] = { nullptr, nullptr };
 	void* d_in[2] = { nullptr, nullptr };
 	int32_t* d_out[2] = { nullptr, nullptr };
+	uint64_t* d_pack[2] = { nullptr, nullptr };
 	DeferredQuery* d_defer[2] = { nullptr, nullptr };
 	unsigned int* d_defer_n[2] = { nullptr, nullptr };
 	size_t stage_bytes = 0, stage_items = 0;
 	cudaEvent_t ev_done[2] = { nullptr, nullptr };
+	std::mutex query_mu;              // host-pointer queries share the staging slots: one batch at a time per model
 };
 
 namespace {
@@ -1469,15 +1471,18 @@ static int query_device(kmx_model* m, const void* d_in, size_t stride, size_t n,
 	const size_t step = 1u << 24;
 	DeferredQuery* d_defer = nullptr;
 	unsigned int* d_defer_n = nullptr;
+	uint64_t* d_packed = nullptr;
 	DA(&d_defer, std::min(n, step) * sizeof(DeferredQuery), s);
 	DA(&d_defer_n, sizeof(unsigned int), s);
+	if (ASCII) DA(&d_packed, std::min(n, step) * 8, s);
 	for (size_t off = 0; off < n; off += step) {
 		const size_t cnt = std::min(step, n - off);
-		if (ASCII) CU(launch_query_ascii(m->dm, (const char*)d_in + off * stride, stride, cnt, d_out + off, d_defer, d_defer_n, m->sm_count, s));
+		if (ASCII) CU(launch_query_ascii(m->dm, (const char*)d_in + off * stride, stride, cnt, d_out + off, d_packed, d_defer, d_defer_n, m->sm_count, s));
 		else CU(launch_query_packed(m->dm, (const uint64_t*)d_in + off, cnt, d_out + off, nullptr, d_defer, d_defer_n, m->sm_count, s));
 	}
 	dev_free(d_defer, s);
 	dev_free(d_defer_n, s);
+	dev_free(d_packed, s);
 	return KMX_OK;
 }
 
@@ -1510,6 +1515,7 @@ static int ensure_staging(kmx_model* m, size_t item_bytes, bool need_h_in, bool 
 		if (need_h_out && !x->h_out[s]) CU(cudaMallocHost((void**)&x->h_out[s], items * 4));
 		if (!x->d_out[s]) {
 			DA(&x->d_out[s], items * 4, x->stream);
+			DA(&x->d_pack[s], items * 8, x->stream);
 			DA(&x->d_defer[s], items * sizeof(DeferredQuery), x->stream);
 			DA(&x->d_defer_n[s], sizeof(unsigned int), x->stream);
 			fresh = true;
@@ -1536,6 +1542,7 @@ static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t st
 	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
 	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
 	if (n == 0) return KMX_OK;
+	std::lock_guard<std::mutex> lock(m->x->query_mu);       // kmer_to_occ may be called from several threads (kmodel.hpp:90-98 is read-only)
 	CU(cudaSetDevice(m->device));
 	int32_t* res = path ? path : out;
 	const bool in_pinned = is_pinned(in), out_pinned = is_pinned(res);
@@ -1558,7 +1565,7 @@ static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t st
 			h_src = m->x->h_in[slot];
 		}
 		CU(cudaMemcpyAsync(m->x->d_in[slot], h_src, cnt * item_bytes, cudaMemcpyHostToDevice, st[slot]));
-		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->x->d_in[slot], stride, cnt, m->x->d_out[slot], m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
+		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->x->d_in[slot], stride, cnt, m->x->d_out[slot], m->x->d_pack[slot], m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
 		else CU(launch_query_packed(m->dm, (const uint64_t*)m->x->d_in[slot], cnt, path ? nullptr : m->x->d_out[slot], path ? m->x->d_out[slot] : nullptr,
 		                            m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
 		CU(cudaMemcpyAsync(out_pinned ? (void*)(res + off) : (void*)m->x->h_out[slot], m->x->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st[slot]));

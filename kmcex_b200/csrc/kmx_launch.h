@@ -16,8 +16,8 @@ struct DeferredQuery {               // a query whose answer needs its 8 neighbo
 // d_defer needs room for n entries (worst case: every query is deferred); d_defer_n is one counter
 cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
                                 DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream);
-cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, DeferredQuery* d_defer,
-                               unsigned int* d_defer_n, int sm_count, cudaStream_t stream);
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, uint64_t* d_packed,
+                               DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream);
 // bucket index + false-hit table of the rest table (R.keys/hash2index/pre_buffer/fine_bits set)
 cudaError_t launch_rest_side_tables(const DevRest& R, int map_size, uint32_t* d_fine, uint64_t* d_quirk_suffix, uint32_t* d_quirk_index,
                                     cudaStream_t stream);

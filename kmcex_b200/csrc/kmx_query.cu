@@ -284,27 +284,63 @@ __device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uin
 	}
 }
 
-// 2-bit encode of an ASCII k-mer (tools.hpp:63-76: bytes other than C/G/T encode as A)
-__device__ __forceinline__ uint64_t encode_ascii(const char* s, int k) {
-	uint64_t v = 0;
-	for (int i = 0; i < k; i++) {
-		const char ch = s[i];
-		const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
-		v = (v << 2) | code;
+// 2-bit encode of ASCII k-mers (tools.hpp:63-76: bytes other than C/G/T encode as A).  A block stages the
+// contiguous bytes of its 256 k-mers in shared memory with coalesced 16-byte loads (a thread reading its own
+// k-mer straight from global memory would issue k byte loads at a stride of `stride` bytes across the warp).
+constexpr int kPackMaxStride = 64;
+__global__ void __launch_bounds__(256) ascii_pack_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed) {
+	__shared__ uint4 s_buf[256 * kPackMaxStride / 16 + 1];
+	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_buf);
+	for (size_t base = (size_t)blockIdx.x * 256; base < n; base += (size_t)gridDim.x * 256) {
+		const size_t cnt = min((size_t)256, n - base);
+		const size_t byte0 = base * stride, bytes = cnt * stride;
+		const size_t head = (size_t)(reinterpret_cast<uintptr_t>(flat + byte0) & 15);   // the aligned window starts `head` bytes earlier
+		const uint4* src = reinterpret_cast<const uint4*>(flat + byte0 - head);         // (inside the same allocation)
+		const size_t n_full = (head + bytes) >> 4;               // whole 16-byte vectors; the tail goes byte by byte
+		__syncthreads();
+		for (size_t i = threadIdx.x; i < n_full; i += 256) s_buf[i] = __ldg(src + i);
+		{
+			uint8_t* s_w = reinterpret_cast<uint8_t*>(s_buf);
+			for (size_t i = (n_full << 4) + threadIdx.x; i < head + bytes; i += 256) s_w[i] = (uint8_t)flat[byte0 - head + i];
+		}
+		__syncthreads();
+		if (threadIdx.x < cnt) {
+			const uint8_t* p = s_bytes + head + threadIdx.x * stride;
+			uint64_t v = 0;
+			for (int i = 0; i < k; i++) {
+				const uint8_t ch = p[i];
+				const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
+				v = (v << 2) | code;
+			}
+			packed[base + threadIdx.x] = v;
+		}
 	}
-	return v;
+}
+
+// fallback for strides beyond the staging buffer: one thread per k-mer, straight from global memory
+__global__ void ascii_pack_wide_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const char* p = flat + i * stride;
+		uint64_t v = 0;
+		for (int j = 0; j < k; j++) {
+			const char ch = p[j];
+			const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
+			v = (v << 2) | code;
+		}
+		packed[i] = v;
+	}
 }
 
 #ifndef KMX_QUERY_BLOCKS
 #define KMX_QUERY_BLOCKS 2
 #endif
-template <int K, int H, int B, bool ASCII>
-__global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const __grid_constant__ DevModel m, const void* __restrict__ input, size_t stride,
+template <int K, int H, int B>
+__global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const __grid_constant__ DevModel m, const uint64_t* __restrict__ input,
                                                             size_t n, int32_t* __restrict__ out, int32_t* __restrict__ path_out,
                                                             DeferredQuery* __restrict__ defer, unsigned int* __restrict__ defer_n) {
 	const int k = K ? K : m.k;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		const uint64_t raw = ASCII ? encode_ascii((const char*)input + i * stride, k) : ((const uint64_t*)input)[i];
+		const uint64_t raw = input[i];
 		uint64_t r;
 		const uint64_t v = canonical(raw & mask2(k), k, &r);
 		Primary P;
@@ -442,8 +478,7 @@ static int query_grid(size_t n, int sm_count) {
 	return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
-template <bool ASCII>
-static cudaError_t launch_query(const DevModel& m, const void* d_in, size_t stride, size_t n, int32_t* d_out, int32_t* d_path,
+cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
                                 DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	cudaError_t e = cudaMemsetAsync(d_defer_n, 0, sizeof(unsigned int), stream);
@@ -451,23 +486,25 @@ static cudaError_t launch_query(const DevModel& m, const void* d_in, size_t stri
 	const int grid = query_grid(n, sm_count);
 	const int slow_grid = sm_count * 2;
 	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5) {
-		query_fast_kernel<31, 7, 5, ASCII><<<grid, 256, 0, stream>>>(m, d_in, stride, n, d_out, d_path, d_defer, d_defer_n);
+		query_fast_kernel<31, 7, 5><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
 		if (d_out) query_slow_kernel<31, 7, 5><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
 	} else {
-		query_fast_kernel<0, 0, 0, ASCII><<<grid, 256, 0, stream>>>(m, d_in, stride, n, d_out, d_path, d_defer, d_defer_n);
+		query_fast_kernel<0, 0, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
 		if (d_out) query_slow_kernel<0, 0, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
 	}
 	return cudaGetLastError();
 }
 
-cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
-                                DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
-	return launch_query<false>(m, d_kmers, 8, n, d_out, d_path, d_defer, d_defer_n, sm_count, stream);
-}
-
-cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, DeferredQuery* d_defer,
-                               unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
-	return launch_query<true>(m, d_flat, stride, n, d_out, nullptr, d_defer, d_defer_n, sm_count, stream);
+// ASCII batches are 2-bit encoded into d_packed (room for n words) and then take the packed path
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, uint64_t* d_packed,
+                               DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	const int grid = query_grid(n, sm_count);
+	if (stride <= (size_t)kPackMaxStride) ascii_pack_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed);
+	else ascii_pack_wide_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	return launch_query_packed(m, d_packed, n, d_out, nullptr, d_defer, d_defer_n, sm_count, stream);
 }
 
 }  // namespace kmx
