@@ -37,7 +37,11 @@ WORKLOADS = {
     "rs": ("rs", 2, 7, 16, "configs[1]: GAGE-RS-shaped synthetic (4.6 Mbp, 100x, 101bp) k31 nh7 nb5 ci2"),
     "hc14": ("hc14", 1, 7, 64, "configs[2]: GAGE-HC14-shaped synthetic (88 Mbp, 40x) k31 nh7 nb5 ci1"),
     "wgs350": ("wgs350", 2, 7, 128, "scale check towards configs[3]: 350 Mbp synthetic genome, 30x, k31 nh7 nb5 ci2"),
+    "na12878": ("na12878", 2, 7, 512, "configs[3]: NA12878-shaped synthetic (3.1 Gbp, 30x, 101bp) k31 nh7 nb5 ci2"),
 }
+# shapes generated bin group by bin group on the GPU (kmcex_b200.synth.make_db_streamed): (genome_bp, coverage, read_len)
+STREAMED = {"na12878": (3_100_000_000, 30, 101)}
+SWEEP_POOL = 100_000_000          # distinct queries behind the configs[4] sweep
 CACHE = os.environ.get("KMX_BENCH_CACHE", "/tmp/kmx_bench")
 
 
@@ -56,6 +60,24 @@ def ensure_db(workload: str, seed: int = 1):
         with open(meta_path) as f:
             return json.load(f)
     os.makedirs(d, exist_ok=True)
+    if workload in STREAMED:
+        import shutil
+        import torch
+        g, cov, rl = STREAMED[workload]
+        need = int(g * 1.4 * 8) + (8 << 30)
+        if shutil.disk_usage(d).free < need:
+            raise SystemExit(f"{workload}: {need >> 30} GiB of scratch space needed under {CACHE} (set KMX_BENCH_CACHE)")
+        r = synth.make_db_streamed(base, g, cov, rl, seed=seed, ci=ci, lut_prefix_length=lut, n_bins=bins, n_present=SWEEP_POOL // 2)
+        torch.cuda.empty_cache()
+        q = synth.mixed_queries(r["present"], SWEEP_POOL, seed=seed + 100)
+        q.tofile(os.path.join(d, "queries.u64"))
+        meta = {"db": base, "queries": os.path.join(d, "queries.u64"), "n_kmers": int(r["n_kmers"]), "n_queries": int(q.size), "ci": ci,
+                "suffix_bytes": os.path.getsize(base + ".kmc_suf"), "prefix_bytes": os.path.getsize(base + ".kmc_pre")}
+        tmp = meta_path + f".{os.getpid()}"
+        with open(tmp, "w") as f:
+            json.dump(meta, f)
+        os.replace(tmp, meta_path)
+        return meta
     sp = synth.make_db(base, shape, seed=seed, ci=ci, lut_prefix_length=lut, n_bins=bins)
     # query set: 50 % present (random strand) / 50 % absent + neighbours, BASELINE.json configs[4] mix
     n_q = 1 << 24
@@ -193,6 +215,9 @@ def main() -> None:
     ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
     ap.add_argument("--workload", default="rs", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--query-sweep", action="store_true",
+                    help="BASELINE.json configs[4]: 1e9 kmer_to_occ lookups against the built model in batches of 1e5 .. 1e8 "
+                         "(device-resident and host->host), reported under \"query_sweep\"")
     ap.add_argument("--parallelism", default="replicas", choices=["replicas", "array-owner"],
                     help="N > 1 build: independent whole builds per rank (weak scaling) or ONE build with the coupled arrays owned by "
                          "different GPUs (kmcex_b200.distributed.build_array_owner, strong scaling)")
@@ -295,7 +320,7 @@ def main() -> None:
 
     # ---------------- retrieval ----------------
     q_all = np.fromfile(meta["queries"], dtype=np.uint64)
-    per = q_all.size // world
+    per = min(q_all.size // world, 1 << 24)
     q_host = torch.from_numpy(q_all[rank * per:(rank + 1) * per].astype(np.int64)).pin_memory()
     q_dev = q_host.to(dev)
     out_dev = torch.empty(per, dtype=torch.int32, device=dev)
@@ -345,6 +370,43 @@ def main() -> None:
     qps_ascii = world * n_a * args.steps / t_qa
     assert bool((a_out == out_host[:n_a]).all())
 
+    # ---------------- configs[4]: 1e9 lookups in batches of 1e5 .. 1e8 ----------------
+    sweep = None
+    if args.query_sweep:
+        pool_n = q_all.size // world
+        lookups = 1_000_000_000 // world                     # per rank; the batch is sharded over the ranks
+        pool_host = torch.from_numpy(q_all[rank * pool_n:(rank + 1) * pool_n].astype(np.int64)).pin_memory()
+        pool_dev = pool_host.to(dev)
+        big = max(b for b in (100_000, 1_000_000, 10_000_000, 100_000_000) if b <= pool_n)
+        s_out_dev = torch.empty(big, dtype=torch.int32, device=dev)
+        s_out_host = torch.empty(big, dtype=torch.int32).pin_memory()
+        sweep = []
+        for B in (100_000, 1_000_000, 10_000_000, 100_000_000):
+            if B > pool_n:
+                continue
+            n_b = max(1, lookups // B)
+            span = pool_n - B + 1
+            offs = [(i * B) % span for i in range(n_b)]
+            barrier()
+            stream.wait_stream(torch.cuda.current_stream())
+            for o in offs[:2]:                               # warm-up
+                m.query_device(pool_dev.data_ptr() + 8 * o, B, s_out_dev.data_ptr(), stream.cuda_stream)
+            ev[0].record(stream)
+            for o in offs:
+                m.query_device(pool_dev.data_ptr() + 8 * o, B, s_out_dev.data_ptr(), stream.cuda_stream)
+            ev[1].record(stream)
+            torch.cuda.synchronize()
+            t_dev = max_over_ranks(ev[0].elapsed_time(ev[1]) / 1e3)
+            n_e = min(n_b, 2000)                             # host->host: bounded number of calls for the small batches
+            barrier()
+            t0 = time.perf_counter()
+            for o in offs[:n_e]:
+                kx._lib.check(kx.lib().kmx_query_packed(m._h, pool_host.data_ptr() + 8 * o, B, s_out_host.data_ptr()))
+            t_host = max_over_ranks(time.perf_counter() - t0)
+            sweep.append({"batch": B, "batches": n_b, "lookups": n_b * B * world, "device_qps": world * n_b * B / t_dev,
+                          "host_batches": n_e, "host_qps": world * n_e * B / t_host})
+        del pool_dev, s_out_dev
+
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = measured_peaks()
     rs_peaks = random_sector_peaks()
@@ -382,6 +444,10 @@ def main() -> None:
         "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers", "insert_phase_cycles")},
         "model_bytes": model_bytes,
     }
+    if sweep is not None:
+        line["query_sweep"] = {"note": "BASELINE.json configs[4]: 50 % present / 37.5 % absent / 12.5 % neighbours, pool of "
+                               f"{q_all.size} distinct queries walked cyclically; the model is far larger than the L2", "unit": "queries/s",
+                               "results": sweep}
 
     # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 template <bool LIST, int K, int H>
 __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ DevDb db, const __grid_constant__ DevModel m,
                                                      const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out_kmer,
-                                                     uint32_t* __restrict__ out_occ) {
+                                                     uint32_t* __restrict__ out_occ, uint64_t bloom_lo, uint64_t bloom_hi,
+                                                     uint64_t tile_first, uint64_t tile_end) {
 	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint64_t s_slot[2];
@@ -212,10 +213,10 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 	const int k = K ? K : db.k;
 	const int nh = H ? H : m.n_hash;
 	constexpr int PER = kTile / 256;
-	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x) {
 		const uint64_t s0 = tile * kTile;
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
+		const bool bloom_tile = LIST || (tile >= bloom_lo && tile < bloom_hi);   // this launch's share of the Bloom inserts
 		__syncthreads();
 		stage_tile(db, s0, n_rec, s_stage);
 		if (threadIdx.x < 2) {
@@ -235,12 +236,13 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 				uint32_t c = decode_count(db, rec);
 				cnt[j] = c;
 				if (c >= db.min_count && c <= db.max_count) {
-					kmer[j] = decode_kmer(db, rec, lut_slot(db.lut, slot_lo, slot_hi, s0 + t));
-					bool to_stream = LIST ? true : (c >= (uint32_t)(m.ci + m.bf_num));
+					const bool to_stream = LIST ? true : (c >= (uint32_t)(m.ci + m.bf_num));
+					if (to_stream ? (out_kmer != nullptr) : bloom_tile)
+						kmer[j] = decode_kmer(db, rec, lut_slot(db.lut, slot_lo, slot_hi, s0 + t));
 					if (to_stream) {
 						keep |= 1u << j;
 						n_keep++;
-					} else if (c >= (uint32_t)m.ci) {
+					} else if (bloom_tile && c >= (uint32_t)m.ci) {
 						const int f = (int)c - m.ci;
 						uint64_t r = reverse_bases(kmer[j], k);
 						HashPrep p;
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 				}
 			}
 		}
+		if (out_kmer == nullptr) continue;                   // Bloom share only (uniform over the grid)
 		uint32_t total;
 		uint32_t rank = block_excl_scan<8>(n_keep, s_warp, &total);
 		uint64_t dst = __ldg(tile_off + tile) + rank;
@@ -296,14 +299,19 @@ cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint6
 }
 
 cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, uint64_t* d_item_kmer,
-                          uint32_t* d_item_occ, int sm_count, cudaStream_t stream) {
+                          uint32_t* d_item_occ, uint64_t bloom_tile_lo, uint64_t bloom_tile_hi, bool stream_items, int sm_count,
+                          cudaStream_t stream) {
 	if (db.total == 0) return cudaSuccess;
-	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	int grid = stream_grid(n_tiles, sm_count, 8);
+	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	if (bloom_tile_hi > n_tiles) bloom_tile_hi = n_tiles;
+	const uint64_t first = stream_items ? 0 : bloom_tile_lo, end = stream_items ? n_tiles : bloom_tile_hi;
+	if (end <= first) return cudaSuccess;
+	if (!stream_items) d_item_kmer = nullptr;
+	int grid = stream_grid(end - first, sm_count, 8);
 	if (db.k == 31 && m.n_hash == 7)
-		encode_kernel<false, 31, 7><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ);
+		encode_kernel<false, 31, 7><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ, bloom_tile_lo, bloom_tile_hi, first, end);
 	else
-		encode_kernel<false, 0, 0><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ);
+		encode_kernel<false, 0, 0><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ, bloom_tile_lo, bloom_tile_hi, first, end);
 	return cudaGetLastError();
 }
 
@@ -312,7 +320,7 @@ cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d
 	if (db.total == 0) return cudaSuccess;
 	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
 	DevModel dummy = {};
-	encode_kernel<true, 0, 0><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, dummy, d_tile_off, d_kmers, d_counts);
+	encode_kernel<true, 0, 0><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, dummy, d_tile_off, d_kmers, d_counts, 0, n_tiles, 0, n_tiles);
 	return cudaGetLastError();
 }
 

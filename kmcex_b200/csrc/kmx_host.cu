@@ -287,6 +287,13 @@ struct BuildState {
 	size_t slab_bytes = 0, off[6] = { 0 };
 	uint32_t* flags = nullptr;
 	void* peer_slab[kMaxRanks] = { nullptr };
+	// multi-GPU: the Bloom filters and km_back live in a second cudaMalloc slab that every rank maps, so that the
+	// partial filters can be OR-ed through peer memory (kmx_dist.cu).  Layout: [Bloom filters | km_back | flags | error]
+	void* fslab = nullptr;
+	size_t fslab_bytes = 0, f_bloom_bytes = 0, f_kmback_off = 0, f_kmback_bytes = 0, f_flags_off = 0;
+	void* peer_fslab[kMaxRanks] = { nullptr };
+	uint32_t fseq = 0;
+	int world = 1, dist_rank = 0;
 };
 
 struct kmx_model {
@@ -350,8 +357,11 @@ static void free_model_device(kmx_model* m) {
 	m->d_rest_counts = nullptr;
 }
 
-// allocate + zero every filter of the model from m->kmer_counts / m->km_kmers (kmodel.hpp:402-456)
-static int alloc_filters(kmx_model* m) {
+static int slab_acquire(void** out, size_t bytes, int device);
+
+// allocate + zero every filter of the model from m->kmer_counts / m->km_kmers (kmodel.hpp:402-456);
+// in_slab: Bloom filters and km_back are carved from one exportable cudaMalloc block (multi-GPU build)
+static int alloc_filters(kmx_model* m, bool in_slab = false) {
 	model_sizes(m->kmer_counts, m->bf_num, m->km_kmers, m->n_hash, m->bytes);
 	for (int i = 0; i < m->bf_num; i++) {
 		if (m->bytes[i] == 0 || m->bytes[3 + i] == 0)
@@ -361,14 +371,39 @@ static int alloc_filters(kmx_model* m) {
 	if (m->bytes[6] == 0 || m->bytes[7] == 0)
 		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays: the reference aborts on zero-length arrays (kmodel.hpp:443-447)",
 		            (unsigned long long)m->km_kmers);
-	for (int i = 0; i < m->bf_num; i++) {
-		DA(&m->d_bf[i], pad8(m->bytes[i]), m->x->stream);
-		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->x->stream));
-		DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->x->stream);
-		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->x->stream));
+	if (in_slab) {
+		BuildState& b = m->bs;
+		auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+		size_t off = 0, o_bf[3] = { 0, 0, 0 }, o_bb[3] = { 0, 0, 0 };
+		for (int i = 0; i < m->bf_num; i++) {
+			o_bf[i] = off; off += up(pad8(m->bytes[i]));
+			o_bb[i] = off; off += up(pad8(m->bytes[3 + i]));
+		}
+		b.f_bloom_bytes = off;
+		b.f_kmback_off = off;
+		b.f_kmback_bytes = up(pad8(m->bytes[7]));
+		off += b.f_kmback_bytes;
+		b.f_flags_off = off;
+		b.fslab_bytes = off + 256;                           // kMaxRanks barrier counters + the error word
+		int rc = slab_acquire(&b.fslab, b.fslab_bytes, m->device);
+		if (rc) return rc;
+		CU(cudaMemsetAsync(b.fslab, 0, b.fslab_bytes, m->x->stream));
+		uint8_t* base = (uint8_t*)b.fslab;
+		for (int i = 0; i < m->bf_num; i++) {
+			m->d_bf[i] = (uint32_t*)(base + o_bf[i]);
+			m->d_bf_back[i] = (uint32_t*)(base + o_bb[i]);
+		}
+		m->d_km_back = (uint32_t*)(base + b.f_kmback_off);
+	} else {
+		for (int i = 0; i < m->bf_num; i++) {
+			DA(&m->d_bf[i], pad8(m->bytes[i]), m->x->stream);
+			CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->x->stream));
+			DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->x->stream);
+			CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->x->stream));
+		}
+		DA(&m->d_km_back, pad8(m->bytes[7]), m->x->stream);
+		CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->x->stream));
 	}
-	DA(&m->d_km_back, pad8(m->bytes[7]), m->x->stream);
-	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->x->stream));
 	const uint64_t words = cell_words(m->bytes[6]);
 	for (int i = 0; i < m->n_bits; i++) {
 		DA(&m->d_cells[i], (words + 1) * 8, m->x->stream);
@@ -850,11 +885,64 @@ std::vector<CachedSlab> g_slab_free;
 std::map<std::string, void*> g_ipc_open;             // 64 handle bytes -> mapping in this process
 }  // namespace
 
+static int slab_acquire(void** out, size_t bytes, int device) {
+	{
+		std::lock_guard<std::mutex> lock(g_slab_mu);
+		for (size_t q = 0; q < g_slab_free.size(); q++) {
+			if (g_slab_free[q].device == device && g_slab_free[q].bytes == bytes) {
+				*out = g_slab_free[q].ptr;
+				g_slab_free.erase(g_slab_free.begin() + q);
+				return KMX_OK;
+			}
+		}
+	}
+	CU(cudaMalloc(out, bytes));
+	return KMX_OK;
+}
+
+static void slab_release(void* ptr, size_t bytes, int device) {
+	std::lock_guard<std::mutex> lock(g_slab_mu);
+	g_slab_free.push_back(CachedSlab{ ptr, bytes, device });
+}
+
+// the filters move from the exchange slab into allocations of their own (the slab goes back to the cache)
+static int filters_leave_slab(kmx_model* m) {
+	BuildState& b = m->bs;
+	if (!b.fslab) return KMX_OK;
+	cudaStream_t s = m->x->stream;
+	auto move = [&](uint32_t** p, uint64_t bytes) -> int {
+		uint32_t* fresh = nullptr;
+		DA(&fresh, pad8(bytes), s);
+		CU(cudaMemcpyAsync(fresh, *p, pad8(bytes), cudaMemcpyDeviceToDevice, s));
+		*p = fresh;
+		return KMX_OK;
+	};
+	for (int i = 0; i < m->bf_num; i++) {
+		int rc = move(&m->d_bf[i], m->bytes[i]);
+		if (!rc) rc = move(&m->d_bf_back[i], m->bytes[3 + i]);
+		if (rc) return rc;
+	}
+	int rc = move(&m->d_km_back, m->bytes[7]);
+	if (rc) return rc;
+	CU(cudaStreamSynchronize(s));
+	slab_release(b.fslab, b.fslab_bytes, m->device);
+	b.fslab = nullptr;
+	fill_dev_model(m);
+	return KMX_OK;
+}
+
 static void build_state_free(kmx_model* m) {
 	BuildState& b = m->bs;
 	if (!m->x) return;
 	cudaStream_t s = m->x->stream;
 	InsertArgs& a = b.a;
+	if (b.fslab) {                                        // a build that failed half-way: the filters still point into the slab
+		cudaStreamSynchronize(s);
+		for (int i = 0; i < 3; i++) m->d_bf[i] = m->d_bf_back[i] = nullptr;
+		m->d_km_back = nullptr;
+		slab_release(b.fslab, b.fslab_bytes, m->device);
+		b.fslab = nullptr;
+	}
 	dev_free(b.d_item_kmer, s);
 	dev_free(b.d_item_occ, s);
 	if (!b.slab) {
@@ -869,17 +957,20 @@ static void build_state_free(kmx_model* m) {
 	dev_free(a.rest_kmer, s); dev_free(a.rest_occ, s);
 	if (b.slab) {
 		cudaStreamSynchronize(s);
-		std::lock_guard<std::mutex> lock(g_slab_mu);
-		g_slab_free.push_back(CachedSlab{ b.slab, b.slab_bytes, m->device });
+		slab_release(b.slab, b.slab_bytes, m->device);
 	}
 	b = BuildState();
 }
 
 // stage 1: pass 1 (class histogram, kmodel.hpp:423-434), filter allocation (kmodel.hpp:402-456),
 // pass 2 (Bloom inserts + array-bound stream, kmodel.hpp:68-74)
-static int build_stage_encode(kmx_model* m, kmx_db* db) {
+// dist_world > 1: this rank inserts the Bloom-bound records of its share of the tiles only (the partial filters are OR-ed
+// afterwards, kmx_dist_merge) and writes the item stream only if stream_items (ranks that own a coupled array)
+static int build_stage_encode(kmx_model* m, kmx_db* db, int dist_rank = 0, int dist_world = 1, bool stream_items = true) {
 	BuildState& b = m->bs;
 	b.wall0 = std::chrono::high_resolution_clock::now();
+	b.world = dist_world;
+	b.dist_rank = dist_rank;
 	int rc = model_attach_device(m);
 	if (rc) return rc;
 	TRACE(b.wall0, "device attached");
@@ -927,7 +1018,7 @@ static int build_stage_encode(kmx_model* m, kmx_db* db) {
 		bf_kmers += cnt.class_count[i];
 	}
 	m->km_kmers = total - bf_kmers;                       // kmodel.hpp:433: header total, not the listed count
-	rc = alloc_filters(m);
+	rc = alloc_filters(m, dist_world > 1);
 	if (rc) {
 		dev_free(d_tile_off, s);
 		return rc;
@@ -935,11 +1026,15 @@ static int build_stage_encode(kmx_model* m, kmx_db* db) {
 	m->rest.k = m->k;
 	m->rest.pre_len = rest_prefix_len(m->k);
 	fill_dev_model(m);
+	if (dist_world > 1) CU(cudaStreamSynchronize(s));     // the filter slab is zeroed before its handle leaves this process
 
 	b.n_items = cnt.array_bound;
-	DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
-	DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
-	CU(launch_encode(d, m->dm, d_tile_off, b.d_item_kmer, b.d_item_occ, m->sm_count, s));
+	if (stream_items) {
+		DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
+		DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
+	}
+	const uint64_t tile_lo = n_tiles * (uint64_t)dist_rank / (uint64_t)dist_world, tile_hi = n_tiles * (uint64_t)(dist_rank + 1) / (uint64_t)dist_world;
+	CU(launch_encode(d, m->dm, d_tile_off, b.d_item_kmer, b.d_item_occ, tile_lo, tile_hi, stream_items, m->sm_count, s));
 	dev_free(d_tile_off, s);
 	CU(cudaEventRecord(ev[2], s));
 	return KMX_OK;
@@ -966,16 +1061,9 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 		             o_ctl = o_o1 + up(batch_items * 4), o_flags = o_ctl + up(sizeof(InsertCtl));
 		b.slab_bytes = o_flags + up(kMaxRanks * 4);
 		{
-			std::lock_guard<std::mutex> lock(g_slab_mu);
-			for (size_t q = 0; q < g_slab_free.size(); q++) {
-				if (g_slab_free[q].device == m->device && g_slab_free[q].bytes == b.slab_bytes) {
-					b.slab = g_slab_free[q].ptr;
-					g_slab_free.erase(g_slab_free.begin() + q);
-					break;
-				}
-			}
+			int rc = slab_acquire(&b.slab, b.slab_bytes, m->device);
+			if (rc) return rc;
 		}
-		if (!b.slab) CU(cudaMalloc(&b.slab, b.slab_bytes));
 		CU(cudaMemsetAsync((uint8_t*)b.slab + o_ctl, 0, b.slab_bytes - o_ctl, s));   // control block + barrier flags start at zero
 		b.off[0] = o_k0; b.off[1] = o_k1; b.off[2] = o_o0; b.off[3] = o_o1; b.off[4] = o_ctl; b.off[5] = o_flags;
 		uint8_t* base = (uint8_t*)b.slab;
@@ -1158,48 +1246,91 @@ extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
 // persistent insert kernels of the ranks hand each bucket's survivors to the next owner through
 // peer-mapped buffers, with a flag barrier per round.  The caller (kmcex_b200/distributed.py)
 // moves IPC handles and, afterwards, the finished pieces with torch.distributed.
-extern "C" int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, void* ipc_handle_out) {
-	if (!m || !db || !ipc_handle_out) return fail(KMX_EARG, "null argument");
+extern "C" int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, int world, void* ipc_handles_out) {
+	if (!m || !db || !ipc_handles_out) return fail(KMX_EARG, "null argument");
 	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
 	if (n_active < 1 || n_active > kMaxRanks || n_active > m->n_bits || rank < 0) return fail(KMX_EARG, "n_active must be in 1..min(%d, n_bits)", kMaxRanks);
+	if (world < n_active || world > kMaxRanks || rank >= world) return fail(KMX_EARG, "world must be in n_active..%d and rank below it", kMaxRanks);
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
-	int rc = build_stage_encode(m, db);
+	int rc = build_stage_encode(m, db, rank, world, rank < n_active);
 	if (!rc) rc = build_stage_insert_setup(m, rank, n_active, true);
 	if (!rc) {
-		CU(cudaStreamSynchronize(m->x->stream));         // the slab is zeroed before anybody maps it
-		CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handle_out, m->bs.slab));
+		CU(cudaStreamSynchronize(m->x->stream));         // the slabs are zeroed before anybody maps them
+		CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handles_out, m->bs.slab));
+		memset((uint8_t*)ipc_handles_out + 64, 0, 64);
+		if (m->bs.fslab) CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)((uint8_t*)ipc_handles_out + 64), m->bs.fslab));
 	}
 	if (rc) build_state_free(m);
 	return rc;
+}
+
+static int ipc_map(const void* handle64, void** out) {
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	std::string key((const char*)&h, 64);
+	std::lock_guard<std::mutex> lock(g_slab_mu);
+	auto it = g_ipc_open.find(key);
+	if (it == g_ipc_open.end()) {
+		void* mapped = nullptr;
+		CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+		it = g_ipc_open.emplace(key, mapped).first;
+	}
+	*out = it->second;
+	return KMX_OK;
 }
 
 extern "C" int kmx_dist_connect(kmx_model* m, const void* handles) {
 	if (!m || !handles || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
 	BuildState& b = m->bs;
 	InsertArgs& a = b.a;
-	for (int p = 0; p < a.n_active; p++) {
-		if (p != a.rank || a.rank >= a.n_active) {
-			if (a.rank >= a.n_active) break;               // an idle rank maps nothing
-			cudaIpcMemHandle_t h;
-			memcpy(&h, (const uint8_t*)handles + 64 * p, 64);
-			std::string key((const char*)&h, 64);
-			std::lock_guard<std::mutex> lock(g_slab_mu);
-			auto it = g_ipc_open.find(key);
-			if (it == g_ipc_open.end()) {
-				void* mapped = nullptr;
-				CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
-				it = g_ipc_open.emplace(key, mapped).first;
+	const uint8_t* hs = (const uint8_t*)handles;
+	if (a.rank < a.n_active) {                             // an idle rank takes no part in the survivor exchange
+		for (int p = 0; p < a.n_active; p++) {
+			if (p != a.rank) {
+				int rc = ipc_map(hs + 128 * p, &b.peer_slab[p]);
+				if (rc) return rc;
 			}
-			b.peer_slab[p] = it->second;
+			uint8_t* base = (uint8_t*)b.peer_slab[p];
+			a.peer_buf_kmer[0][p] = (uint64_t*)(base + b.off[0]);
+			a.peer_buf_kmer[1][p] = (uint64_t*)(base + b.off[1]);
+			a.peer_buf_occ[0][p] = (uint32_t*)(base + b.off[2]);
+			a.peer_buf_occ[1][p] = (uint32_t*)(base + b.off[3]);
+			a.peer_ctl[p] = (InsertCtl*)(base + b.off[4]);
+			a.peer_flags[p] = (uint32_t*)(base + b.off[5]);
 		}
-		uint8_t* base = (uint8_t*)b.peer_slab[p];
-		a.peer_buf_kmer[0][p] = (uint64_t*)(base + b.off[0]);
-		a.peer_buf_kmer[1][p] = (uint64_t*)(base + b.off[1]);
-		a.peer_buf_occ[0][p] = (uint32_t*)(base + b.off[2]);
-		a.peer_buf_occ[1][p] = (uint32_t*)(base + b.off[3]);
-		a.peer_ctl[p] = (InsertCtl*)(base + b.off[4]);
-		a.peer_flags[p] = (uint32_t*)(base + b.off[5]);
 	}
+	if (b.fslab) {                                         // every rank takes part in the filter merges
+		for (int p = 0; p < b.world; p++) {
+			if (p == b.dist_rank) b.peer_fslab[p] = b.fslab;
+			else {
+				int rc = ipc_map(hs + 128 * p + 64, &b.peer_fslab[p]);
+				if (rc) return rc;
+			}
+		}
+	}
+	return KMX_OK;
+}
+
+// OR all-reduce over the ranks of the Bloom filters (which = 0, after kmx_dist_prepare) or of km_back (which = 1, after
+// kmx_dist_insert): one kernel per rank, exchanges through peer memory, asynchronous on the model's stream
+extern "C" int kmx_dist_merge(kmx_model* m, int which) {
+	if (!m || !m->bs.fslab || !m->bs.peer_fslab[0]) return fail(KMX_ESTATE, "kmx_dist_prepare / kmx_dist_connect first");
+	BuildState& b = m->bs;
+	OrReduceArgs r;
+	memset(&r, 0, sizeof(r));
+	r.rank = b.dist_rank;
+	r.world = b.world;
+	const size_t off = which == 0 ? 0 : b.f_kmback_off, bytes = which == 0 ? b.f_bloom_bytes : b.f_kmback_bytes;
+	r.n_vec = bytes / 16;
+	for (int p = 0; p < b.world; p++) {
+		r.base[p] = (uint4*)((uint8_t*)b.peer_fslab[p] + off);
+		r.flags[p] = (uint32_t*)((uint8_t*)b.peer_fslab[p] + b.f_flags_off);
+	}
+	r.seq = b.fseq;
+	r.error = (unsigned int*)((uint8_t*)b.fslab + b.f_flags_off + 128);
+	b.fseq += 2;
+	CU(cudaSetDevice(m->device));
+	CU(launch_or_allreduce(r, m->sm_count, m->x->stream));
 	return KMX_OK;
 }
 
@@ -1231,7 +1362,16 @@ extern "C" int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const 
 	m->x->h_pinned->ctl.attempts = attempts;
 	m->x->h_pinned->ctl.accepted = accepted;
 	CU(cudaDeviceSynchronize());                         // the caller's collectives ran on its own streams
-	int rc = build_stage_finish(m, d_rest_kmer, d_rest_occ, rest_n);
+	if (m->bs.fslab) {
+		unsigned int err = 0;
+		CU(cudaMemcpy(&err, (uint8_t*)m->bs.fslab + m->bs.f_flags_off + 128, 4, cudaMemcpyDeviceToHost));
+		if (err) {
+			build_state_free(m);
+			return fail(KMX_ECUDA, "filter merge stopped: a peer GPU did not reach the barrier within 20 s");
+		}
+	}
+	int rc = filters_leave_slab(m);
+	if (!rc) rc = build_stage_finish(m, d_rest_kmer, d_rest_occ, rest_n);
 	if (rc) build_state_free(m);
 	return rc;
 }

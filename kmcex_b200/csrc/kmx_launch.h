@@ -39,8 +39,11 @@ cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* 
 cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint64_t* d_tile_off, cudaStream_t stream);
 // pass 2: decode again; Bloom-bound k-mers are OR-ed into their filters, array-bound k-mers are
 // written (file order preserved) to the item stream
+// bloom_tile_lo/hi: the tiles whose Bloom-bound records this launch inserts (multi-GPU: the record range is split
+// over the ranks and the partial filters are OR-ed, kmx_dist.cu); stream = false skips the item stream altogether
 cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, uint64_t* d_item_kmer,
-                          uint32_t* d_item_occ, int sm_count, cudaStream_t stream);
+                          uint32_t* d_item_occ, uint64_t bloom_tile_lo, uint64_t bloom_tile_hi, bool stream_items, int sm_count,
+                          cudaStream_t stream);
 // plain listing (kmx_db_list): every listed record, file order, compacted
 cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d_kmers, uint32_t* d_counts, int sm_count,
                         cudaStream_t stream);
@@ -94,6 +97,17 @@ struct InsertArgs {
 	unsigned long long first_batch, n_batches;
 	unsigned int max_iterations;      // safety cap per round
 };
+
+// bitwise-OR all-reduce of a filter region over peer-mapped copies (kmx_dist.cu)
+struct OrReduceArgs {
+	int rank, world;
+	unsigned long long n_vec;         // 16-byte vectors in the region
+	uint4* base[kMaxRanks];           // every rank's copy of the region as mapped on this device (index = rank)
+	uint32_t* flags[kMaxRanks];       // flags[p][r]: barriers rank r has entered, as visible on rank p
+	uint32_t seq;                     // barriers completed before this launch (it uses two more)
+	unsigned int* error;              // local word, set to 3 when a peer does not show up
+};
+cudaError_t launch_or_allreduce(const OrReduceArgs& a, int sm_count, cudaStream_t stream);
 
 cudaError_t insert_grid_size(int* blocks_out, int sm_count);
 cudaError_t launch_insert(const DevModel& m, const InsertArgs& a, int grid_blocks, cudaStream_t stream);

@@ -283,6 +283,168 @@ def _write_kmc_db_cuda(base, kmers, counts, k, lut_prefix_length, n_bins, counte
     return n
 
 
+def _kmers_at(genome: torch.Tensor, a: int, b: int, k: int) -> torch.Tensor:
+    """packed forward k-mers starting at genome positions [a, b) (genome = uint8 codes)"""
+    g = genome[a:b + k - 1].to(torch.int64)
+    n = b - a
+    out = torch.zeros(n, dtype=torch.int64, device=g.device)
+    for j in range(k):
+        out |= g[j:j + n] << (2 * (k - 1 - j))
+    return out
+
+
+def make_db_streamed(base: str, genome_bp: int, coverage: float, read_len: int, k: int = 31, err_frac: float = 0.3, seed: int = 1,
+                     ci: int = 2, cs: int = 1023, lut_prefix_length: int = 7, n_bins: int = 512, n_groups: int = 16,
+                     chunk: int = 1 << 26, n_present: int = 0, device: str | None = None) -> dict:
+    """Genome-derived spectrum for shapes too large for the in-memory generators (NA12878-shaped: 3.1 Gbp).
+
+    Every genomic k-mer gets a count around coverage*(L-k+1)/L; a fraction err_frac of the positions
+    also contributes a single-substitution neighbour with a short low-count tail.  The (k-mer, count)
+    pairs stay on the device (10 bytes each); the database is written bin group by bin group (sort,
+    merge duplicates, -ci filter, pack records, append to .kmc_suf), so neither the host nor the
+    device ever holds more than one group besides the pair buffer.  Returns a dict with the record
+    count and, if n_present > 0, `present`: that many k-mers sampled uniformly from the records."""
+    dev = torch.device(device or ("cuda" if torch.cuda.is_available() else "cpu"))
+    G = int(genome_bp)
+    assert (k - lut_prefix_length) % 4 == 0 and k <= 31 and n_bins % n_groups == 0
+    genome = torch.empty(G, dtype=torch.uint8, device=dev)
+    for a in range(0, G, chunk):
+        b = min(G, a + chunk)
+        genome[a:b] = (splitmix64(torch.arange(a, b, dtype=torch.int64, device=dev), seed, 1) & 3).to(torch.uint8)
+    n_pos = G - k + 1
+    lam = coverage * (read_len - k + 1) / read_len
+    thr = int(err_frac * 65536)
+    cap = n_pos + int(n_pos * err_frac * 1.02) + 4096 * (n_pos // chunk + 1)
+    allk = torch.empty(cap, dtype=torch.int64, device=dev)
+    allc = torch.empty(cap, dtype=torch.int16, device=dev)
+    n_all = 0
+    for a in range(0, n_pos, chunk):
+        b = min(n_pos, a + chunk)
+        idx = torch.arange(a, b, dtype=torch.int64, device=dev)
+        gk = _kmers_at(genome, a, b, k)
+        r = splitmix64(idx, seed, 10)
+        # four 16-bit uniforms: Irwin-Hall(4), mean 2, variance 1/3 -> roughly normal around lam, sd sqrt(lam)
+        s4 = ((r & 0xFFFF) + (_lsr(r, 16) & 0xFFFF) + (_lsr(r, 32) & 0xFFFF) + _lsr(r, 48)).to(torch.float32) / 65536.0
+        solid_c = torch.clamp((lam + (s4 - 2.0) * (3.0 * lam) ** 0.5).round().to(torch.int64), min=1, max=cs)
+        r2 = splitmix64(idx, seed, 20)
+        has_err = (r2 & 0xFFFF) < thr
+        src = gk[has_err]
+        r2 = r2[has_err]
+        epos = (_lsr(r2, 16) & 0xFFFF) % k
+        ed = (_lsr(r2, 32) & 0xFFFF) % 3 + 1
+        err = src ^ (ed << (2 * epos))
+        u = (_lsr(r2, 40) & 0xFFFFFF).to(torch.float32) / float(1 << 24)
+        err_c = torch.clamp((torch.log(1 - u) / float(np.log(0.45))).floor().to(torch.int64) + 1, min=1, max=8)
+        m = gk.numel() + err.numel()
+        assert n_all + m <= cap
+        allk[n_all:n_all + m] = canonical_packed(torch.cat([gk, err]), k)
+        allc[n_all:n_all + m] = torch.cat([solid_c, err_c]).to(torch.int16)
+        n_all += m
+        del gk, r, s4, solid_c, r2, has_err, src, epos, ed, err, u, err_c, idx
+    del genome
+    allk, allc = allk[:n_all], allc[:n_all]
+    bins = torch.empty(n_all, dtype=torch.int16, device=dev)
+    for a in range(0, n_all, chunk):
+        b = min(n_all, a + chunk)
+        bins[a:b] = (_lsr(allk[a:b] * _i64(0x9E3779B97F4A7C15), 40) % n_bins).to(torch.int16)
+    suf_bytes = (k - lut_prefix_length) // 4
+    counter_size = 2
+    slots = 4 ** lut_prefix_length
+    per_slot = torch.zeros(n_bins * slots, dtype=torch.int64, device=dev)
+    per_group = n_bins // n_groups
+    total = 0
+    present = []
+    os.makedirs(os.path.dirname(os.path.abspath(base)), exist_ok=True)
+    with open(base + ".kmc_suf", "wb") as f:
+        f.write(b"KMCS")
+        for g in range(n_groups):
+            pk, pc, pb = [], [], []
+            for a in range(0, n_all, 1 << 28):                 # selection in pieces: index tensors stay below 2^31 elements
+                b = min(n_all, a + (1 << 28))
+                bsl = bins[a:b]
+                msk = (bsl >= g * per_group) & (bsl < (g + 1) * per_group)
+                pk.append(allk[a:b][msk])
+                pc.append(allc[a:b][msk])
+                pb.append(bsl[msk])
+                del msk, bsl
+            km, ct, bn = torch.cat(pk), torch.cat(pc).to(torch.int64), torch.cat(pb).to(torch.int64)
+            del pk, pc, pb
+            km, order = torch.sort(km, stable=True)
+            ct, bn = ct[order], bn[order]
+            del order
+            km, inv = torch.unique_consecutive(km, return_inverse=True)
+            if km.numel() != ct.numel():
+                cc = torch.zeros(km.numel(), dtype=torch.int64, device=dev)
+                cc.index_add_(0, inv, ct)
+                first = torch.ones_like(inv, dtype=torch.bool)
+                first[1:] = inv[1:] != inv[:-1]
+                ct, bn = cc, bn[first]
+                del cc, first
+            del inv
+            ct = torch.clamp(ct, max=cs)
+            keep = ct >= ci
+            km, ct, bn = km[keep], ct[keep], bn[keep]
+            del keep
+            bn, order = torch.sort(bn, stable=True)            # records sorted by k-mer within each bin
+            km, ct = km[order], ct[order]
+            del order
+            n = km.numel()
+            prefix = _lsr(km, 8 * suf_bytes)
+            per_slot += torch.bincount(bn * slots + prefix, minlength=n_bins * slots)
+            del prefix, bn
+            if n_present:
+                want = (n_present + n_groups - 1) // n_groups
+                pick = _uniform_int(torch.arange(want, dtype=torch.int64, device=dev), seed, 40 + g, max(n, 1))
+                present.append(km[pick])
+            step = 1 << 25
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                rec = torch.empty((b - a, suf_bytes + counter_size), dtype=torch.uint8, device=dev)
+                for j in range(suf_bytes):
+                    rec[:, j] = (_lsr(km[a:b], 8 * (suf_bytes - 1 - j)) & 0xFF).to(torch.uint8)
+                for j in range(counter_size):
+                    rec[:, suf_bytes + j] = ((ct[a:b] >> (8 * j)) & 0xFF).to(torch.uint8)
+                f.write(rec.cpu().numpy().tobytes())
+                del rec
+            total += n
+            del km, ct
+        f.write(b"KMCS")
+    starts = torch.zeros(n_bins * slots + 1, dtype=torch.int64, device=dev)
+    starts[1:] = torch.cumsum(per_slot, 0)
+    lut = starts.cpu().numpy().astype(np.uint64)
+    header = struct.pack("<7IQB7x5I I", k, 0, counter_size, lut_prefix_length, 7, ci, cs, total, 0, 0, 0, 0, 0, 0, 0x200)
+    with open(base + ".kmc_pre", "wb") as f:
+        f.write(b"KMCP")
+        f.write(lut.tobytes())
+        f.write(np.zeros(4 ** 7 + 1, dtype=np.uint32).tobytes())
+        f.write(header)
+        f.write(struct.pack("<I", len(header)))
+        f.write(b"KMCP")
+    out = {"n_kmers": int(total), "k": k}
+    if n_present:
+        out["present"] = torch.cat(present)[:n_present].cpu().numpy().astype(np.uint64)
+    return out
+
+
+def mixed_queries(present: np.ndarray, n_total: int, k: int = 31, seed: int = 7) -> np.ndarray:
+    """BASELINE.json configs[4] mix: 50 % present k-mers (random strand), 37.5 % uniform random k-mers
+    (absent w.p. ~1), 12.5 % single-base neighbours of present k-mers (the disambiguation path)."""
+    rng = np.random.default_rng(seed)
+    mask = np.uint64((1 << (2 * k)) - 1)
+    n_p = n_total // 2
+    n_nb = n_total // 8
+    n_a = n_total - n_p - n_nb
+    pres = present[rng.integers(0, present.size, n_p)]
+    rc = revcomp_packed(torch.from_numpy(pres.astype(np.int64)), k).numpy().astype(np.uint64)
+    pres = np.where(rng.integers(0, 2, n_p).astype(bool), rc, pres)
+    absent = rng.integers(0, 1 << 62, n_a, dtype=np.uint64) & mask
+    nb_src = present[rng.integers(0, present.size, n_nb)]
+    nb = ((nb_src << np.uint64(2)) & mask) | rng.integers(0, 4, n_nb).astype(np.uint64)
+    q = np.concatenate([pres, absent, nb])
+    rng.shuffle(q)
+    return q.astype(np.uint64)
+
+
 def neighbour_rich_queries(sp: Spectrum, n_present: int, n_absent: int, seed: int = 7) -> np.ndarray:
     """Query set: present k-mers (random strand), uniform random k-mers (absent w.p. ~1) and
     single-base neighbours of present k-mers (drives the disambiguation slow path)."""
