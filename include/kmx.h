@@ -142,14 +142,17 @@ typedef struct kmx_count_info_t {
 int kmx_count_fastq(const char* const* fastq_paths, int n_files, int k, int ci, int cs, const char* out_base, kmx_count_info_t* info);
 
 /* ---- multi-GPU build: array-owner decomposition (option A) -------------
- * One process per GPU.  Every rank calls prepare (decodes the database, fills the Bloom filters,
- * allocates its exchange buffers and returns their 64-byte CUDA IPC handle), exchanges the handles
- * (any out-of-band channel), calls connect with the handles of ranks 0..n_active-1 concatenated, then
- * insert: rank r < n_active owns the coupled arrays a with a % n_active == r, the persistent kernels
- * pass each bucket's survivors to the next owner through peer memory with a flag barrier per round.
- * buffers() exposes the device pointers the caller's collectives complete (owned arrays are
- * broadcast, km_back is OR-merged, survivor lists are concatenated); finish() builds the rest table.
- * Results are identical to kmx_init_from_db for every n_active.                                   */
+ * One process per GPU, `world` of them.  Every rank calls prepare: it runs the counting pass, inserts the
+ * Bloom-bound records of ITS share of the database (record range rank/world) into its copy of the filters,
+ * writes the item stream if it owns a coupled array (rank < n_active), allocates its exchange buffers and
+ * returns two 64-byte CUDA IPC handles (survivor exchange slab, filter slab).  The ranks exchange the handles
+ * (any out-of-band channel) and call connect with the handles of ranks 0..world-1 concatenated (128 bytes
+ * each).  merge(0) ORs the partial Bloom filters over the ranks through peer memory (one kernel: reduce-scatter
+ * + all-gather with flag barriers, no NCCL); insert: rank r < n_active owns the coupled arrays a with
+ * a % n_active == r, the persistent kernels pass each bucket's survivors to the next owner through peer memory
+ * with a flag barrier per round; merge(1) ORs km_back.  buffers() exposes the device pointers the caller's
+ * collectives complete (owned arrays are broadcast, survivor lists are concatenated); finish() builds the rest
+ * table.  Results are identical to kmx_init_from_db for every world / n_active.                       */
 typedef struct kmx_dist_buffers_t {
 	int32_t n_bits;
 	uint64_t cell_bytes;              /* bytes of one coupled array in the device layout          */
@@ -161,8 +164,9 @@ typedef struct kmx_dist_buffers_t {
 	uint64_t rest_n;
 	uint64_t insert_attempts, insert_accepted;
 } kmx_dist_buffers_t;
-int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, void* ipc_handle_out /* 64 bytes */);
-int kmx_dist_connect(kmx_model* m, const void* handles /* n_active * 64 bytes */);
+int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, int world, void* ipc_handles_out /* 128 bytes */);
+int kmx_dist_connect(kmx_model* m, const void* handles /* world * 128 bytes */);
+int kmx_dist_merge(kmx_model* m, int which /* 0: Bloom filters, 1: km_back */);
 int kmx_dist_insert(kmx_model* m);
 int kmx_dist_buffers(kmx_model* m, kmx_dist_buffers_t* out);
 int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n,
@@ -172,6 +176,8 @@ int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d
  * kind 0: random 8-byte loads, 1: random 32-bit atomic OR, 2: random 64-bit atomic OR; 7 accesses
  * per item over `footprint_bytes` of device memory; *ms_out = milliseconds per launch             */
 int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out);
+/* the same with locality: the accesses of items that run together fall into one window of window_bytes (0 = none) */
+int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -87,12 +87,14 @@ SIGNATURES = {
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "kmx_count_fastq": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(KmxCountInfo)]),
-    "kmx_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "kmx_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "kmx_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kmx_dist_merge": (C.c_int, [C.c_void_p, C.c_int]),
     "kmx_dist_insert": (C.c_int, [C.c_void_p]),
     "kmx_dist_buffers": (C.c_int, [C.c_void_p, C.POINTER(KmxDistBuffers)]),
     "kmx_dist_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
+    "kmx_microbench_windowed": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None

@@ -17,17 +17,22 @@ __device__ __forceinline__ uint64_t mix(uint64_t z) {
 	return z ^ (z >> 31);
 }
 
+// window_words != 0: the accesses of item i fall into window (i * n_windows / n_items) of the buffer, i.e. threads that
+// run together touch the same window_words * 8 bytes (what binning the probes by address range would give)
 template <int KIND>
-__global__ void __launch_bounds__(256) random_sector_kernel(unsigned long long* buf, uint64_t n_words, uint64_t n_items, unsigned long long* sink) {
+__global__ void __launch_bounds__(256) random_sector_kernel(unsigned long long* buf, uint64_t n_words, uint64_t n_items, unsigned long long* sink,
+                                                            uint64_t window_words) {
 	constexpr int PER = 7;                       // independent accesses per item, as one array probe issues
 	unsigned long long acc = 0;
+	const uint64_t n_windows = window_words ? n_words / window_words : 1;
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t h = mix(i * 0x9E3779B97F4A7C15ULL + 12345);
+		const uint64_t wbase = window_words ? (uint64_t)(((unsigned __int128)i * n_windows) / n_items) * window_words : 0;
 		unsigned long long v[PER];
 #pragma unroll
 		for (int j = 0; j < PER; j++) {
 			h = mix(h + j);
-			const uint64_t w = h % n_words;
+			const uint64_t w = window_words ? wbase + h % window_words : h % n_words;
 			if (KIND == 0) v[j] = __ldg(buf + w);
 			else if (KIND == 1) atomicOr((unsigned int*)buf + 2 * w + (j & 1), 1u << (h >> 59));
 			else atomicOr(buf + w, 1ULL << (h >> 58));
@@ -44,8 +49,14 @@ __global__ void __launch_bounds__(256) random_sector_kernel(unsigned long long* 
 
 // footprint_bytes of device memory are touched at random; n_items * 7 accesses per launch;
 // returns the average milliseconds per launch over `reps` launches (after one warm-up) in *ms_out
+extern "C" int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out);
 extern "C" int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out) {
-	if (kind < 0 || kind > 2 || footprint_bytes < 4096 || !ms_out || reps < 1) return KMX_EARG;
+	return kmx_microbench_windowed(kind, footprint_bytes, 0, n_items, reps, ms_out);
+}
+
+extern "C" int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out) {
+	if (kind < 0 || kind > 2 || footprint_bytes < 4096 || !ms_out || reps < 1 || (window_bytes && window_bytes > footprint_bytes)) return KMX_EARG;
+	const uint64_t window_words = window_bytes / 8;
 	unsigned long long* buf = nullptr;
 	unsigned long long* sink = nullptr;
 	if (cudaMalloc(&buf, footprint_bytes) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) {
@@ -64,9 +75,9 @@ extern "C" int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_
 	cudaEventCreate(&e1);
 	for (int r = -1; r < reps; r++) {
 		if (r == 0) cudaEventRecord(e0);
-		if (kind == 0) random_sector_kernel<0><<<grid, 256>>>(buf, n_words, n_items, sink);
-		else if (kind == 1) random_sector_kernel<1><<<grid, 256>>>(buf, n_words, n_items, sink);
-		else random_sector_kernel<2><<<grid, 256>>>(buf, n_words, n_items, sink);
+		if (kind == 0) random_sector_kernel<0><<<grid, 256>>>(buf, n_words, n_items, sink, window_words);
+		else if (kind == 1) random_sector_kernel<1><<<grid, 256>>>(buf, n_words, n_items, sink, window_words);
+		else random_sector_kernel<2><<<grid, 256>>>(buf, n_words, n_items, sink, window_words);
 	}
 	cudaEventRecord(e1);
 	cudaError_t e = cudaEventSynchronize(e1);

@@ -129,31 +129,35 @@ def owner_of_array(a: int, n_active: int) -> int:
 def build_array_owner(model, db, group=None, n_active: Optional[int] = None) -> None:
     """KModel::init over the GPUs of one node, exactly (SURVEY.md section 8e, option A).
 
-    Every rank decodes the database and fills the Bloom filters; the coupled arrays are owned
-    round-robin by ranks 0..n_active-1 (n_active <= n_bits), whose insert kernels pass survivors to
-    the next owner through peer-mapped memory.  Afterwards the owned arrays are broadcast, km_back
-    is OR-merged and the survivor lists are concatenated, so that every rank holds the complete
-    model -- byte-identical to a single-GPU build."""
+    Every rank runs the counting pass and inserts the Bloom-bound records of its share of the
+    database; the partial Bloom filters are OR-ed over all ranks through peer memory (libkmx's own
+    kernel, kmx_dist_merge).  The coupled arrays are owned round-robin by ranks 0..n_active-1
+    (n_active <= n_bits), whose insert kernels pass survivors to the next owner through peer-mapped
+    memory; km_back is OR-ed the same way as the filters.  Afterwards the owned arrays are broadcast
+    and the survivor lists are concatenated, so that every rank holds the complete model --
+    byte-identical to a single-GPU build."""
     from ._lib import KmxDistBuffers, check, lib
     import ctypes as C
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n_bits = model.info["n_bits"]
     n_active = min(world, n_bits, 8) if n_active is None else n_active
     dev = torch.device("cuda", torch.cuda.current_device())
-    handle = (C.c_ubyte * 64)()
-    check(lib().kmx_dist_prepare(model._h, db._h, rank, n_active, handle))
-    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    handles = (C.c_ubyte * 128)()
+    check(lib().kmx_dist_prepare(model._h, db._h, rank, n_active, world, handles))
+    mine = torch.tensor(list(handles), dtype=torch.uint8, device=dev)
     allh = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allh, mine, group=group)
-    blob = bytes(torch.cat(allh[:n_active]).cpu().numpy().tobytes())
+    blob = bytes(torch.cat(allh).cpu().numpy().tobytes())
     check(lib().kmx_dist_connect(model._h, blob))
     dist.barrier(group=group)                      # every rank has mapped its peers before any kernel writes
+    check(lib().kmx_dist_merge(model._h, 0))       # Bloom filters: OR of the ranks' shares
     check(lib().kmx_dist_insert(model._h))
+    check(lib().kmx_dist_merge(model._h, 1))       # km_back: OR of what every array owner accepted
     bufs = KmxDistBuffers()
     check(lib().kmx_dist_buffers(model._h, C.byref(bufs)))
+    check(lib().kmx_model_sync(model._h))          # the collectives below run on torch's stream
     for a in range(n_bits):                        # owners publish their arrays
         dist.broadcast(_view(bufs.cells[a], bufs.cell_bytes), src=owner_of_array(a, n_active), group=group)
-    or_merge_(_view(bufs.km_back, bufs.km_back_bytes, torch.int64), group)
     n_local = int(bufs.rest_n)
     cap = max(n_local, 1)
     rest_k = concat_ranks(_view(bufs.rest_kmer, cap * 8, torch.int64) if bufs.rest_kmer else torch.zeros(1, dtype=torch.int64, device=dev), n_local, group)
