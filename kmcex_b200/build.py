@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "kmcex_b200", "csrc")
 LIB = os.path.join(ROOT, "kmcex_b200", "libkmx.so")
 SOURCES = ["kmx_host.cu", "kmx_build.cu", "kmx_query.cu", "kmx_microbench.cu", "kmx_count.cu", "kmx_dist.cu"]
-HEADERS = ["kmx_core.cuh", "kmx_device.cuh", "kmx_launch.h", os.path.join(ROOT, "include", "kmx.h")]
+HEADERS = ["kmx_core.cuh", "kmx_device.cuh", "kmx_launch.h", "kmx_gridbar.cuh", os.path.join(ROOT, "include", "kmx.h")]
 NVCC_FLAGS = ["--threads", "4", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "-shared", "-cudart", "static"]
 
@@ -31,19 +31,21 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: libkmx.so cannot be built (there is no CPU fallback)")
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, out: str | None = None, defines: list[str] | None = None) -> str:
+    """out / defines: A/B builds of the kernels (e.g. defines=["KMX_INS_THREADS=512"]), loaded with KMX_LIB_PATH"""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
-    if not force and _newer(LIB, deps):
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    target = out or LIB
+    if not force and _newer(target, deps):
+        return target
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in (defines or [])] + ["-o", target] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libkmx.so")
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return target
 
 
 def build_oracle() -> None:

@@ -25,6 +25,12 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "kmx_device.cuh"
 #include "kmx_launch.h"
+#include "kmx_gridbar.cuh"
+
+// grid-wide barrier of the persistent insert kernel: 0 = cooperative_groups grid.sync(), 1 = the counter barrier of kmx_gridbar.cuh
+#ifndef KMX_GRIDBAR
+#define KMX_GRIDBAR 1
+#endif
 
 namespace cg = cooperative_groups;
 
@@ -336,7 +342,7 @@ constexpr uint32_t kEpochMax = 0x3FFFu;
 #define KMX_INS_THREADS 256
 #endif
 constexpr int kInsThreads = KMX_INS_THREADS;                // threads per block of the persistent insert kernel
-constexpr uint32_t kIdTile = kInsThreads;                   // ids per reorder tile = one block pass
+constexpr uint32_t kIdTile = 256;                           // ids per reorder tile (one warp of the place pass takes a tile)
 
 template <int K, int H, int B>
 __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel(const __grid_constant__ DevModel m, const __grid_constant__ InsertArgs a) {
@@ -358,7 +364,35 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 
 	uint32_t epoch = vctl->epoch;
 	uint32_t seq = vctl->seq;
-	grid.sync();                                            // everybody has read ctl->epoch / seq before they are rewritten
+#if KMX_GRIDBAR
+	GridBarrier gbar;
+	gbar.init(&ctl->bar);
+#define GSYNC() gbar.sync()
+#else
+#define GSYNC() grid.sync()
+#endif
+	// Control words every thread needs after a barrier (list lengths, error flag, survivor counts) are fetched ONCE per
+	// block, by the thread that waited at the barrier, and handed out through shared memory: a word read by every warp of
+	// the grid is several thousand requests to one L2 slice, microseconds per word and barrier.
+	__shared__ uint32_t s_hot[12];                        // list_n[0], list_n[1], epoch, error, nfail[parity][0..7]
+	auto gsync_fetch = [&](unsigned int parity) {
+#if KMX_GRIDBAR
+		gbar.arrive_wait();
+#else
+		grid.sync();
+#endif
+		if (threadIdx.x == 0) {
+			uint4 h, n0, n1;
+			asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "l"(&ctl->list_n[0]) : "memory");
+			asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n0.x), "=r"(n0.y), "=r"(n0.z), "=r"(n0.w) : "l"(&ctl->nfail[parity][0]) : "memory");
+			asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(n1.x), "=r"(n1.y), "=r"(n1.z), "=r"(n1.w) : "l"(&ctl->nfail[parity][4]) : "memory");
+			s_hot[0] = h.x; s_hot[1] = h.y; s_hot[2] = h.z; s_hot[3] = h.w;
+			s_hot[4] = n0.x; s_hot[5] = n0.y; s_hot[6] = n0.z; s_hot[7] = n0.w;
+			s_hot[8] = n1.x; s_hot[9] = n1.y; s_hot[10] = n1.z; s_hot[11] = n1.w;
+		}
+		__syncthreads();
+	};
+	grid.sync();                                            // everybody has read ctl->epoch / seq / bar before they are rewritten
 
 	for (unsigned long long batch = a.first_batch; batch < a.first_batch + a.n_batches; batch++) {
 		const unsigned long long base = batch * total_ids;
@@ -502,17 +536,24 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				return (i << kBucketLog) | x;
 			};
 			// claim bitmap of this round: sized to the round (about 64 bits per claim), cleared at the end
+			uint32_t n_arr_max = 0;                             // items offered to one array this round
+#pragma unroll
+			for (int i = 0; i < BM; i++) n_arr_max = n_work[i] > n_arr_max ? n_work[i] : n_arr_max;
 			uint32_t claim_log2 = 15;
-			while (claim_log2 < a.claim_log2 && (1u << claim_log2) < 64u * (uint32_t)nh * (n_round / (uint32_t)nb + 1)) claim_log2++;
+			while (claim_log2 < a.claim_log2 && (1u << claim_log2) < 64u * (uint32_t)nh * (n_arr_max + 1)) claim_log2++;
 			const uint32_t claim_mask = (1u << claim_log2) - 1;
 			const size_t claim_stride = (size_t)1 << (a.claim_log2 - 5);     // words per (array, want) bitmap
 
 			if (epoch + 2 >= kEpochMax) {                      // reservation keys can get no smaller: start the epochs over
 				for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
 				epoch = 0;
-				grid.sync();
+				GSYNC();
 			}
 			long long tick = clock64();
+			if (tid == 0) {                                     // nobody touches the lists during phase 0
+				vctl->list_n[0] = 0;
+				vctl->list_n[1] = 0;
+			}
 			// ---- first iteration, phase 0: reject on the committed state, or claim (position, wanted value) ----
 			// (the next item's k-mer and count are fetched while the current one is hashed and probed)
 			uint32_t id_n = tid < n_round ? dense_to_id(tid) : 0;
@@ -551,13 +592,11 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					if (!a.claim_first) a.status[id] = untagged;
 				}
 			}
-			grid.sync();
+			GSYNC();
 			if (tid == 0) {
 				long long now = clock64();
 				vctl->phase_cycles[0] += (unsigned long long)(now - tick);
 				tick = now;
-				vctl->list_n[0] = 0;
-				vctl->list_n[1] = 0;
 			}
 			// ---- phase 1: an item nobody contests (no live item wants the opposite value at any of its
 			// untagged positions) interacts with nobody and commits at once; the others reserve ----
@@ -594,14 +633,14 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					append(a.list[1], &ctl->list_n[1], id);
 				}
 			}
-			grid.sync();
+			gsync_fetch(par);
 			if (tid == 0) {
 				long long now = clock64();
 				vctl->phase_cycles[1] += (unsigned long long)(now - tick);
 				tick = now;
 			}
 			// ---- phase 2: contested items that hold all their reservations commit, the rest go to the list ----
-			const uint32_t n_contested = vctl->list_n[1];
+			const uint32_t n_contested = s_hot[1];
 			for (uint32_t x = tid; x < n_contested; x += T) {
 				const uint32_t id = __ldcg(a.list[1] + x);
 				const uint32_t st = a.status[id];
@@ -610,8 +649,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
 				else append(a.list[0], &ctl->list_n[0], id);
 			}
-			grid.sync();
-			uint32_t n_list = vctl->list_n[0];
+			gsync_fetch(par);
+			uint32_t n_list = s_hot[0];
 			uint32_t iter = 1;
 			int cur = 0;
 			epoch++;
@@ -625,7 +664,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				if (epoch + 1 >= kEpochMax) {                   // keys can get no smaller: start over
 					for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
 					epoch = 0;
-					grid.sync();
+					GSYNC();
 				}
 				key_hi = (kEpochMax - epoch) << kBucketLog;
 				const uint32_t* list_cur = a.list[cur];
@@ -650,7 +689,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 						a.status[id] = untagged | (need << kNeedShift);
 					}
 				}
-				grid.sync();
+				GSYNC();
 				for (uint32_t x = tid; x < n_list; x += T) {
 					const uint32_t id = __ldcg(list_cur + x);
 					const uint32_t st = a.status[id];
@@ -660,8 +699,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
 					else append(a.list[cur ^ 1], &ctl->list_n[cur ^ 1], id);
 				}
-				grid.sync();
-				n_list = vctl->list_n[cur ^ 1];
+				gsync_fetch(par);
+				n_list = s_hot[cur ^ 1];
 				cur ^= 1;
 				iter++;
 				epoch++;
@@ -680,125 +719,140 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			// F = number of rejected items.  Rejected items below F stay where they are; the
 			// accepted slots below F ("holes", ascending) are filled by the rejected items at or
 			// above F taken in DESCENDING index order.
-			if ((int)blockIdx.x < nb && (((int)blockIdx.x + t) % nb) % a.n_active == a.rank) {
-				// exclusive scan of this bucket's tile counters: PER consecutive tiles per thread
-				const uint32_t i = blockIdx.x;
-				constexpr uint32_t kTilesPerBucket = kBucket / kIdTile;
-				constexpr uint32_t PER = (kTilesPerBucket + kInsThreads - 1) / kInsThreads;
-				uint32_t* tf = a.tile_fail + i * kTilesPerBucket;
-				uint32_t x[PER], sum = 0;
-#pragma unroll
-				for (uint32_t q = 0; q < PER; q++) {
-					const uint32_t at = threadIdx.x * PER + q;
-					x[q] = at < kTilesPerBucket ? __ldcg(tf + at) : 0;
-					sum += x[q];
+			//
+			// Place pass, one WARP per tile of 256 ids (lane l takes ids l, l + 32, ...: every access is coalesced).  The
+			// warp sums the per-tile reject counters of its bucket (<= 1024 words, L2-resident) into the number of rejects
+			// before its tile and the bucket total F -- there is no separate scan phase.  In the last round every survivor
+			// goes to the rest list, whose order does not matter (it is sorted afterwards): a tile takes its range with one
+			// atomicAdd and the round needs no move pass; only buffer slot 0 (kmodel.hpp:520-540) is tracked.
+			constexpr uint32_t kTilesPerBucket = kBucket / kIdTile;
+			static_assert(kIdTile == 256 && kTilesPerBucket == 1024, "the place pass gives a tile of 256 ids to a warp");
+			if (tid == 0) {                                     // empty buckets of this rank: nobody visits their tiles
+				for (int i = 0; i < nb; i++) {
+					if (((i + t) % nb) % a.n_active == a.rank && n_work[i] == 0) {
+						for (int p = 0; p < a.n_active; p++) ((volatile InsertCtl*)a.peer_ctl[p])->nfail[par][i] = 0;
+						if (last_round) vctl->slot0_valid[i] = 0u;
+					}
 				}
-				uint32_t total;
-				uint32_t off = block_excl_scan<kInsThreads / 32>(sum, s_warp, &total);
+			}
+			{
+				const uint32_t lane = threadIdx.x & 31u;
+				const uint32_t warp_g = tid >> 5, n_warps = T >> 5;
+				for (uint32_t tile = warp_g; tile < n_id_tiles; tile += n_warps) {
+					const uint32_t id_base = tile * kIdTile;
+					const uint32_t i = id_base >> kBucketLog, c_base = id_base & (kBucket - 1);
+					const uint32_t nw = n_work[i];
+					if (c_base >= nw) continue;                    // uniform over the warp: empty tile
+					uint32_t st[8];
 #pragma unroll
-				for (uint32_t q = 0; q < PER; q++) {
-					const uint32_t at = threadIdx.x * PER + q;
-					if (at < kTilesPerBucket) tf[at] = off;
-					off += x[q];
-				}
-				if (threadIdx.x == 0) {
-					for (int p = 0; p < a.n_active; p++) ((volatile InsertCtl*)a.peer_ctl[p])->nfail[par][i] = total;   // every rank tracks every bucket
+					for (int q = 0; q < 8; q++) st[q] = __ldcg(a.status + id_base + q * 32u + lane);
+					const uint32_t tb = c_base / kIdTile, tiles_used = (nw + kIdTile - 1) / kIdTile;
+					const uint32_t* tf = a.tile_fail + i * kTilesPerBucket;
+					uint32_t before = 0, F = 0;
+					for (uint32_t k = lane; k < tiles_used; k += 32u) {
+						const uint32_t v = __ldcg(tf + k);
+						F += v;
+						before += k < tb ? v : 0u;
+					}
+#pragma unroll
+					for (int d = 16; d > 0; d >>= 1) {
+						F += __shfl_xor_sync(0xffffffffu, F, d);
+						before += __shfl_xor_sync(0xffffffffu, before, d);
+					}
+					if (tb == 0 && lane == 0) {
+						for (int p = 0; p < a.n_active; p++) ((volatile InsertCtl*)a.peer_ctl[p])->nfail[par][i] = F;   // every rank tracks every bucket
+						if (last_round) vctl->slot0_valid[i] = F ? 1u : 0u;
+					}
+					unsigned long long rest_at = 0;
+					bool first_accepted = false;
 					if (last_round) {
-						vctl->rest_base[i] = atomicAdd(&ctl->rest_n, (unsigned long long)total);
-						vctl->slot0_valid[i] = total ? 1u : 0u;
+						const uint32_t mine_cnt = __ldcg(tf + tb);
+						if (lane == 0 && mine_cnt) {
+							rest_at = atomicAdd(&ctl->rest_n, (unsigned long long)mine_cnt);
+							if (rest_at + mine_cnt > a.rest_cap) vctl->error = 2;
+						}
+						rest_at = __shfl_sync(0xffffffffu, rest_at, 0);
+						if (rest_at + mine_cnt > a.rest_cap) continue;          // uniform over the warp; the grid stops after the barrier
+						first_accepted = (__ldcg(a.status + (i << kBucketLog)) >> kStateShift) != 2u;
 					}
-				}
-			}
-			grid.sync();
-			if (tid == 0) {
-				long long now = clock64();
-				vctl->phase_cycles[4] += (unsigned long long)(now - tick);
-				tick = now;
-			}
-			uint32_t n_next[BM];
-			unsigned long long rest_base[BM];
+					uint32_t excl = before;
 #pragma unroll
-			for (int i = 0; i < BM; i++) {
-				const bool mine = i < nb && ((i + t) % nb) % a.n_active == a.rank;
-				n_next[i] = mine ? vctl->nfail[par][i] : 0;              // the other buckets' counts arrive with the round barrier
-				rest_base[i] = (mine && last_round) ? vctl->rest_base[i] : 0;
-			}
-			if (last_round) {
-#pragma unroll
-				for (int i = 0; i < BM; i++)
-					if (i < nb && rest_base[i] + n_next[i] > a.rest_cap) {
-						if (tid == 0) vctl->error = 2;
-						return;                                 // uniform over the grid
-					}
-			}
-			for (uint32_t tile = blockIdx.x; tile < n_id_tiles; tile += gridDim.x) {
-				const uint32_t id = tile * kIdTile + threadIdx.x;
-				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-				const bool valid = c < n_work[i];               // uniform over the block: skip empty tiles
-				if (tile * kIdTile - (i << kBucketLog) >= n_work[i]) continue;
-				const bool failed = valid && (__ldcg(a.status + id) >> kStateShift) == 2u;
-				uint32_t total;
-				const uint32_t excl = __ldcg(a.tile_fail + tile) + block_excl_scan<kInsThreads / 32>(failed ? 1u : 0u, s_warp, &total);
-				const uint32_t F = n_next[i];
-				if (valid) {
-					if (failed) {
-						if (c < F) {
-							const uint64_t v = __ldcg(src_kmer + id);
-							const uint32_t occ = __ldcg(src_occ + id);
+					for (int q = 0; q < 8; q++) {
+						const uint32_t c = c_base + q * 32u + lane, id = id_base + q * 32u + lane;
+						const bool valid = c < nw;
+						const bool failed = valid && (st[q] >> kStateShift) == 2u;
+						const uint32_t ball = __ballot_sync(0xffffffffu, failed);
+						const uint32_t mine = excl + __popc(ball & ((1u << lane) - 1u));
+						excl += __popc(ball);
+						if (!valid) continue;
+						if (failed) {
 							if (last_round) {
-								a.rest_kmer[rest_base[i] + c] = v;
-								a.rest_occ[rest_base[i] + c] = occ;
-								if (c == 0) {
+								const uint64_t v = __ldcg(src_kmer + id);
+								const uint32_t occ = __ldcg(src_occ + id);
+								a.rest_kmer[rest_at + (mine - before)] = v;
+								a.rest_occ[rest_at + (mine - before)] = occ;
+								// what reorder_buffer leaves in slot 0: item 0 if it was rejected, else the last rejected item
+								if (c == 0 || (first_accepted && mine == F - 1u)) {
 									vctl->slot0_kmer[i] = v;
 									vctl->slot0_occ[i] = occ;
 								}
-							} else {
+							} else if (c < F) {
 								const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;   // owner of this bucket's next array
-								a.peer_buf_kmer[t & 1][nx][id] = v;
-								a.peer_buf_occ[t & 1][nx][id] = occ;
+								a.peer_buf_kmer[t & 1][nx][id] = __ldcg(src_kmer + id);
+								a.peer_buf_occ[t & 1][nx][id] = __ldcg(src_occ + id);
+							} else {
+								a.excl_rank[id] = mine;
 							}
-						} else {
-							a.excl_rank[id] = excl;
+						} else if (!last_round && c < F) {
+							a.holepos[(i << kBucketLog) + (c - mine)] = c;
 						}
-					} else if (c < F) {
-						a.holepos[(i << kBucketLog) + (c - excl)] = c;
 					}
 				}
 			}
-			grid.sync();
+			gsync_fetch(par);
+			if (s_hot[3]) return;                               // uniform over the grid (survivor list overflow)
 			if (tid == 0) {
 				long long now = clock64();
 				vctl->phase_cycles[5] += (unsigned long long)(now - tick);
 				tick = now;
 			}
-			for (uint32_t x = tid; x < n_round; x += T) {
-				const uint32_t id = dense_to_id(x);
-				const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
-				const uint32_t F = n_next[i];
-				if (c < F) continue;
-				if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
-				const uint32_t d = F - __ldcg(a.excl_rank + id) - 1;
-				const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
-				const uint64_t v = __ldcg(src_kmer + id);
-				const uint32_t occ = __ldcg(src_occ + id);
-				if (last_round) {
-					a.rest_kmer[rest_base[i] + to] = v;
-					a.rest_occ[rest_base[i] + to] = occ;
-					if (to == 0) {
-						vctl->slot0_kmer[i] = v;
-						vctl->slot0_occ[i] = occ;
-					}
-				} else {
+			uint32_t n_next[BM];
+#pragma unroll
+			for (int i = 0; i < BM; i++) {
+				const bool mine = i < nb && ((i + t) % nb) % a.n_active == a.rank;
+				n_next[i] = mine ? s_hot[4 + i] : 0;                     // the other buckets' counts arrive with the round barrier
+			}
+			if (!last_round) {
+				for (uint32_t x = tid; x < n_round; x += T) {
+					const uint32_t id = dense_to_id(x);
+					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
+					const uint32_t F = n_next[i];
+					if (c < F) continue;
+					if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
+					const uint32_t d = F - __ldcg(a.excl_rank + id) - 1;
+					const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
 					const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;
-					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = v;
-					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = occ;
+					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_kmer + id);
+					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_occ + id);
 				}
 			}
 			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;
-			{   // clear the part of the claim bitmaps this round used
-				const uint32_t words = 1u << (claim_log2 - 5);
-				const uint32_t total = (uint32_t)nb * 2 * words;
-				for (uint32_t x = tid; x < total; x += T) a.claim[(size_t)(x / words) * claim_stride + (x % words)] = 0;
+			{   // clear the part of the claim bitmaps this round used (only the arrays this rank worked on), 16 bytes per store
+				const uint32_t vecs = 1u << (claim_log2 - 7);
+				uint32_t act = 0, n_act = 0;                     // 4 bits per active array
+#pragma unroll
+				for (int i = 0; i < BM; i++) {
+					if (n_work[i] != 0) {
+						act |= (uint32_t)((i + t) % nb) << (4 * n_act);
+						n_act++;
+					}
+				}
+				const uint32_t total = n_act * 2 * vecs;
+				for (uint32_t x = tid; x < total; x += T) {
+					const uint32_t q = x / vecs;
+					const uint32_t arr = (act >> (4 * (q >> 1))) & 15u;
+					reinterpret_cast<uint4*>(a.claim + ((size_t)arr * 2 + (q & 1u)) * claim_stride)[x % vecs] = make_uint4(0u, 0u, 0u, 0u);
+				}
 			}
 			if (tid == 0) {
 				unsigned long long att = 0, fail = 0;
@@ -811,7 +865,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				vctl->iterations += iter;
 			}
 			if (a.n_active > 1) __threadfence_system();          // survivors written into a peer's buffers
-			grid.sync();
+			if (a.n_active > 1) GSYNC();
+			else gsync_fetch(par);
 			if (tid == 0) vctl->phase_cycles[6] += (unsigned long long)(clock64() - tick);
 			if (a.n_active > 1) {
 				// round barrier across the GPUs: publish "round seq done" on every rank, wait for all of them
@@ -834,11 +889,11 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					__threadfence_system();
 					vctl->phase_cycles[7] += (unsigned long long)(clock64() - wait0);
 				}
-				grid.sync();
-				if (vctl->error) return;                            // uniform over the grid
+				gsync_fetch(par);
 			}
+			if (s_hot[3]) return;                               // uniform over the grid
 #pragma unroll
-			for (int i = 0; i < BM; i++) n_cur[i] = i < nb ? vctl->nfail[par][i] : 0;
+			for (int i = 0; i < BM; i++) n_cur[i] = i < nb ? s_hot[4 + i] : 0;
 		}
 	}
 	if (tid == 0) {
@@ -846,6 +901,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 		vctl->seq = seq;
 	}
 }
+
+#undef GSYNC
 
 cudaError_t insert_grid_size(int* blocks_out, int sm_count) {
 	int per_sm = 0;

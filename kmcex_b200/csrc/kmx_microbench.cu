@@ -6,8 +6,10 @@
 //   kind 1: random 32-bit atomic OR, no return     (Bloom / km_back inserts, red.global.or.b32)
 //   kind 2: random 64-bit atomic OR, no return     (coupled-array commits)
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include "../../include/kmx.h"
+#include "kmx_gridbar.cuh"
 
 namespace {
 
@@ -87,6 +89,57 @@ extern "C" int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint6
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	cudaFree(buf);
+	cudaFree(sink);
+	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
+}
+
+// ---- grid-barrier cost: the persistent insert kernel pays ~10 grid barriers per round ------------------------------
+namespace {
+template <int MODE>
+__global__ void grid_barrier_kernel(int reps, unsigned int* bar, unsigned long long* sink) {
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	kmx::GridBarrier gb;
+	gb.init(bar);
+	grid.sync();
+	unsigned long long acc = 0;
+	for (int r = 0; r < reps; r++) {
+		acc += threadIdx.x + r;
+		if (MODE == 0) grid.sync();
+		else gb.sync();
+	}
+	if (acc == 0x1234567ULL) *sink = acc;
+}
+}  // namespace
+
+// mode 0: cooperative_groups grid.sync(); mode 1: the counter barrier of kmx_gridbar.cuh.  grid = blocks_per_sm * SMs
+// blocks of `threads` threads; *us_out = microseconds per barrier
+extern "C" int kmx_microbench_grid_barrier(int mode, int threads, int blocks_per_sm, int reps, float* us_out) {
+	if (mode < 0 || mode > 1 || threads < 32 || threads > 1024 || blocks_per_sm < 1 || reps < 1 || !us_out) return KMX_EARG;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	unsigned int* bar = nullptr;
+	unsigned long long* sink = nullptr;
+	if (cudaMalloc(&bar, 256) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) return KMX_ECUDA;
+	cudaMemset(bar, 0, 256);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	void* args[3] = { (void*)&reps, (void*)&bar, (void*)&sink };
+	const void* fn = mode == 0 ? (const void*)grid_barrier_kernel<0> : (const void*)grid_barrier_kernel<1>;
+	cudaError_t e = cudaSuccess;
+	for (int r = -1; r < 1 && e == cudaSuccess; r++) {
+		if (r == 0) cudaEventRecord(e0);
+		e = cudaLaunchCooperativeKernel(fn, dim3(blocks_per_sm * sms), dim3(threads), args, 0, 0);
+	}
+	cudaEventRecord(e1);
+	if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	*us_out = 1e3f * ms / reps;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(bar);
 	cudaFree(sink);
 	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
 }
