@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			};
 			auto reject = [&](uint32_t id) {
 				a.status[id] = kRejected;
-				atomicAdd(a.tile_fail + (id / kIdTile), 1u);
+				red_add32(a.tile_fail + (id / kIdTile), 1u);
 			};
 			// accept: set tag (+ value) at every position that was untagged, OR the (k-2)-mer into km_back (kmodel.hpp:546-550)
 			auto commit = [&](uint32_t id, const ItemCtx& it, uint32_t untagged) {
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					if (j < nh && ((untagged >> j) & 1u)) {      // tagged positions already hold the wanted value
 						const uint32_t sh = ((uint32_t)it.pos[j] & 31u) ^ 7u;
 						const unsigned long long want = (it.bin >> j) & 1u;
-						atomicOr(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh);
+						red_or64(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh);
 					}
 				}
 				HashPrep p;
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 #pragma unroll
 				for (int j = 0; j < HM; j++)
 					if (j < nh && ((need >> j) & 1u))
-						atomicMin(table + 2 * ((uint32_t)it.pos[j] & slot_mask) + ((it.bin >> j) & 1u), key_hi | it.c);
+						red_min32(table + 2 * ((uint32_t)it.pos[j] & slot_mask) + ((it.bin >> j) & 1u), key_hi | it.c);
 			};
 			auto holds_reservations = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) -> bool {
 				const uint32_t* table = a.resv + (size_t)it.arr * 2 * a.resv_slots;
@@ -586,14 +586,14 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					for (int j = 0; j < HM; j++) {
 						if (j < nh && ((untagged >> j) & 1u)) {
 							const uint32_t bit = (uint32_t)it.pos[j] & claim_mask;
-							atomicOr(cl + ((it.bin >> j) & 1u) * claim_stride + (bit >> 5), 1u << (bit & 31u));
+							red_or32(cl + ((it.bin >> j) & 1u) * claim_stride + (bit >> 5), 1u << (bit & 31u));
 						}
 					}
 					if (!a.claim_first) a.status[id] = untagged;
 				}
 			}
 			GSYNC();
-			if (tid == 0) {
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
 				vctl->phase_cycles[0] += (unsigned long long)(now - tick);
 				tick = now;
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				}
 			}
 			gsync_fetch(par);
-			if (tid == 0) {
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
 				vctl->phase_cycles[1] += (unsigned long long)(now - tick);
 				tick = now;
@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			uint32_t iter = 1;
 			int cur = 0;
 			epoch++;
-			if (tid == 0) {
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
 				vctl->phase_cycles[2] += (unsigned long long)(now - tick);
 				tick = now;
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					return;                                     // uniform over the grid
 				}
 			}
-			if (tid == 0) {
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
 				vctl->phase_cycles[3] += (unsigned long long)(now - tick);
 				tick = now;
@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			}
 			gsync_fetch(par);
 			if (s_hot[3]) return;                               // uniform over the grid (survivor list overflow)
-			if (tid == 0) {
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
 				vctl->phase_cycles[5] += (unsigned long long)(now - tick);
 				tick = now;
@@ -867,7 +867,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			if (a.n_active > 1) __threadfence_system();          // survivors written into a peer's buffers
 			if (a.n_active > 1) GSYNC();
 			else gsync_fetch(par);
-			if (tid == 0) vctl->phase_cycles[6] += (unsigned long long)(clock64() - tick);
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) vctl->phase_cycles[6] += (unsigned long long)(clock64() - tick);
 			if (a.n_active > 1) {
 				// round barrier across the GPUs: publish "round seq done" on every rank, wait for all of them
 				seq++;

@@ -56,6 +56,14 @@ struct DevDb {
 
 #ifdef __CUDACC__
 
+// ---- fire-and-forget reductions -----------------------------------------------------------
+// atomicOr / atomicAdd / atomicMin with the result unused still compile to ATOMG (a returning atomic) inside the
+// cooperative insert kernel; the scattered bit traffic of this path wants RED: no response packet, no scoreboard slot.
+KMX_D void red_or32(uint32_t* p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory"); }
+KMX_D void red_or64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.or.b64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "l"(v) : "memory"); }
+KMX_D void red_add32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory"); }
+KMX_D void red_min32(uint32_t* p, uint32_t v) { asm volatile("red.global.min.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory"); }
+
 // ---- bit probes -------------------------------------------------------------------------
 KMX_D bool filter_test(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);
@@ -63,7 +71,7 @@ KMX_D bool filter_test(const DevFilter& f, uint64_t h) {
 }
 KMX_D void filter_set(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);
-	atomicOr(f.words + (pos >> 5), bit_mask32(pos));
+	red_or32(f.words + (pos >> 5), bit_mask32(pos));
 }
 
 #endif  // __CUDACC__

@@ -26,8 +26,9 @@ struct GridBarrier {
 			unsigned int seen;
 			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
 			seen += 1;
-			while ((int)(seen - target) < 0)
-				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+			while ((int)(seen - target) < 0)                     // relaxed polls: an acquire load invalidates the L1 every time round
+				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 			target += gridDim.x;
 		}
 	}
@@ -38,8 +39,9 @@ struct GridBarrier {
 			unsigned int seen;
 			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(seen) : "l"(counter) : "memory");
 			seen += 1;
-			while ((int)(seen - target) < 0)
-				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+			while ((int)(seen - target) < 0)                     // relaxed polls: an acquire load invalidates the L1 every time round
+				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 			target += gridDim.x;
 		}
 		__syncthreads();

@@ -1119,6 +1119,8 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	a.claim_first = 0;
 	if (const char* e = getenv("KMX_CLAIM_FIRST")) a.claim_first = atoi(e) ? 1 : 0;
 	a.max_iterations = kBucket + 64;
+	a.phase_round = -1;
+	if (const char* e = getenv("KMX_PHASE_ROUND")) a.phase_round = atoi(e);
 	CU(insert_grid_size(&b.grid, m->sm_count));
 	// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
 	// all launches queue without a host round trip; beyond that it grows between launches.

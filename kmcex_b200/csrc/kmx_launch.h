@@ -97,6 +97,7 @@ struct InsertArgs {
 	uint32_t* peer_flags[kMaxRanks];  // peer_flags[p][r]: rounds rank r has completed, as visible on rank p
 	unsigned long long first_batch, n_batches;
 	unsigned int max_iterations;      // safety cap per round
+	int phase_round;                  // diagnostic: phase_cycles count only round t == phase_round of every batch (-1: all rounds)
 };
 
 // bitwise-OR all-reduce of a filter region over peer-mapped copies (kmx_dist.cu)

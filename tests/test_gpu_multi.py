@@ -21,6 +21,18 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
+def _spawn(fn, args_after_port, nprocs):
+    """mp.spawn with a fresh rendezvous port; a port that got taken between the probe and the bind is retried"""
+    for attempt in range(3):
+        port = _free_port()
+        try:
+            mp.spawn(fn, args=(nprocs, port) + tuple(args_after_port), nprocs=nprocs, join=True)
+            return
+        except Exception as e:          # torch.multiprocessing.ProcessRaisedException carrying EADDRINUSE
+            if "EADDRINUSE" not in str(e) or attempt == 2:
+                raise
+
+
 def _worker(rank, world, port, base, ci, work_dir, q_path):
     import kmcex_b200 as kx
     from kmcex_b200 import distributed as kd
@@ -52,7 +64,7 @@ def test_two_ranks_replicated_model_sharded_queries(case_dbs, golden, tmp_path):
     q = cases.case_queries(sp)
     q_path = str(tmp_path / "q.u64")
     q.tofile(q_path)
-    mp.spawn(_worker, args=(2, _free_port(), base, cases.CASES[name]["ci"], str(tmp_path), q_path), nprocs=2, join=True)
+    _spawn(_worker, (base, cases.CASES[name]["ci"], str(tmp_path), q_path), 2)
     for r in range(2):
         occ = np.load(str(tmp_path / f"occ{r}.npy"))
         assert hashlib.md5(occ.tobytes()).hexdigest() == golden[name]["occ_md5"]
@@ -95,7 +107,7 @@ def test_array_owner_build_is_byte_identical(name, ranks, case_dbs, golden, tmp_
     world = min(torch.cuda.device_count(), 8) if ranks == 0 else ranks
     if world > torch.cuda.device_count():
         pytest.skip(f"needs {world} GPUs")
-    mp.spawn(_owner_worker, args=(world, _free_port(), base, cases.CASES[name]["ci"], str(tmp_path), q_path), nprocs=world, join=True)
+    _spawn(_owner_worker, (base, cases.CASES[name]["ci"], str(tmp_path), q_path), world)
     for r in range(world):
         for f in ("header", "km.bin", "rest.bin"):
             assert cases.md5_file(str(tmp_path / f"owner_rank{r}" / f)) == golden[name]["model_md5"][f], (r, f)
