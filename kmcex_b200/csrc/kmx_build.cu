@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 
 	uint32_t epoch = vctl->epoch;
 	uint32_t seq = vctl->seq;
+	const unsigned long long evict_first = make_evict_first_policy();
 #if KMX_GRIDBAR
 	GridBarrier gbar;
 	gbar.init(&ctl->bar);
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				unsigned long long cell[HM];
 #pragma unroll
 				for (int j = 0; j < HM; j++)
-					if (j < nh) cell[j] = __ldcg(m.cells[it.arr] + (it.pos[j] >> 5));
+					if (j < nh) cell[j] = (a.stream_cells & 1) ? ld_stream64(m.cells[it.arr] + (it.pos[j] >> 5), evict_first) : __ldcg(m.cells[it.arr] + (it.pos[j] >> 5));
 				conflict = false;
 				untagged = 0;
 #pragma unroll
@@ -479,14 +480,20 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					if (j < nh && ((untagged >> j) & 1u)) {      // tagged positions already hold the wanted value
 						const uint32_t sh = ((uint32_t)it.pos[j] & 31u) ^ 7u;
 						const unsigned long long want = (it.bin >> j) & 1u;
-						red_or64(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh);
+						if (a.stream_cells & 2) red_or64_stream(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh, evict_first);
+						else red_or64(m.cells[it.arr] + (it.pos[j] >> 5), ((1ULL << 32) | want) << sh);
 					}
 				}
 				HashPrep p;
 				hash_prepare(middle_r(it.r, k), k - 2, p);
 #pragma unroll
-				for (int j = 0; j < HM - 2; j++)
-					if (j < hk) filter_set(m.km_back, hash_finish(p, k - 2, c_seeds[j]));
+				for (int j = 0; j < HM - 2; j++) {
+					if (j < hk) {
+						const uint64_t pos = fastmod(hash_finish(p, k - 2, c_seeds[j]), m.km_back.mod);
+						if (a.stream_cells & 4) red_or32_stream(m.km_back.words + (pos >> 5), bit_mask32(pos), evict_first);
+						else red_or32(m.km_back.words + (pos >> 5), bit_mask32(pos));
+					}
+				}
 				a.status[id] = kAccepted;
 			};
 			auto reserve = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) {
@@ -559,6 +566,12 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			uint32_t id_n = tid < n_round ? dense_to_id(tid) : 0;
 			uint64_t v_n = tid < n_round ? __ldcg(src_kmer + id_n) : 0;
 			uint32_t occ_n = tid < n_round ? __ldcg(src_occ + id_n) : 0;
+			// what this thread learns about its first item (x = tid) stays in registers for phase 1, whose first
+			// iteration is the same item: rounds of at most one item per thread skip two dependent load waves there
+			const uint32_t id_first = id_n;
+			const uint64_t v_first = v_n;
+			const uint32_t occ_first = occ_n;
+			uint32_t st_first = 0;
 			for (uint32_t x = tid; x < n_round; x += T) {
 				const uint32_t id = id_n;
 				const uint64_t v_c = v_n;
@@ -580,6 +593,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				if (!a.claim_first) read_cells(it, conflict, untagged);
 				if (conflict) {
 					reject(id);
+					if (x == tid) st_first = kRejected;
 				} else {
 					uint32_t* cl = a.claim + (size_t)it.arr * 2 * claim_stride;
 #pragma unroll
@@ -589,7 +603,10 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 							red_or32(cl + ((it.bin >> j) & 1u) * claim_stride + (bit >> 5), 1u << (bit & 31u));
 						}
 					}
-					if (!a.claim_first) a.status[id] = untagged;
+					if (!a.claim_first) {
+						a.status[id] = untagged;
+						if (x == tid) st_first = untagged;
+					}
 				}
 			}
 			GSYNC();
@@ -601,12 +618,25 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			// ---- phase 1: an item nobody contests (no live item wants the opposite value at any of its
 			// untagged positions) interacts with nobody and commits at once; the others reserve ----
 			uint32_t key_hi = (kEpochMax - epoch) << kBucketLog;
+			// (iteration 0 comes from phase 0's registers, the following ones are fetched one step ahead)
+			id_n = id_first;
+			v_n = v_first;
+			occ_n = occ_first;
+			uint32_t st_n = st_first;
 			for (uint32_t x = tid; x < n_round; x += T) {
-				const uint32_t id = dense_to_id(x);
-				uint32_t untagged = a.claim_first ? 0u : a.status[id];
+				const uint32_t id = id_n;
+				const uint64_t v_c = v_n;
+				const uint32_t occ_c = occ_n;
+				uint32_t untagged = st_n;
+				if (x + T < n_round) {
+					id_n = dense_to_id(x + T);
+					st_n = a.claim_first ? 0u : __ldcg(a.status + id_n);
+					v_n = __ldcg(src_kmer + id_n);
+					occ_n = __ldcg(src_occ + id_n);
+				}
 				if (untagged >> kStateShift) continue;
 				ItemCtx it;
-				load_item(id, it);
+				prepare_item(id, v_c, occ_c, it);
 				if (a.claim_first) {
 					bool conflict;
 					read_cells(it, conflict, untagged);

@@ -64,6 +64,27 @@ KMX_D void red_or64(unsigned long long* p, unsigned long long v) { asm volatile(
 KMX_D void red_add32(uint32_t* p, uint32_t v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory"); }
 KMX_D void red_min32(uint32_t* p, uint32_t v) { asm volatile("red.global.min.u32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(v) : "memory"); }
 
+// ---- random probes of arrays far larger than the L2 -----------------------------------------
+// A probe sector of an HBM-resident array is not touched again before hundreds of megabytes of other sectors have
+// passed through the L2: let it be the first thing the L2 drops, so that the small hot structures of the insert
+// (claim bitmaps, status words, lists) stay resident instead of being washed out by the probe stream.
+KMX_D unsigned long long make_evict_first_policy() {
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+KMX_D unsigned long long ld_stream64(const unsigned long long* p, unsigned long long pol) {
+	unsigned long long v;
+	asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+	return v;
+}
+KMX_D void red_or64_stream(unsigned long long* p, unsigned long long v, unsigned long long pol) {
+	asm volatile("red.global.or.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "l"(v), "l"(pol) : "memory");
+}
+KMX_D void red_or32_stream(uint32_t* p, uint32_t v, unsigned long long pol) {
+	asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "r"(v), "l"(pol) : "memory");
+}
+
 // ---- bit probes -------------------------------------------------------------------------
 KMX_D bool filter_test(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);

@@ -197,8 +197,8 @@ static int rest_prefix_len(int k) {              // rest.hpp:78-83
 struct DevCtx {
 	int device = 0;
 	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaStream_t reader[8] = {};
-	cudaEvent_t reader_ev[8][2] = {};
+	cudaStream_t reader[16] = {};
+	cudaEvent_t reader_ev[16][2] = {};
 	cudaEvent_t ev_build[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
 		CountOut count;
@@ -677,8 +677,8 @@ extern "C" void kmx_db_info(const kmx_db* db, kmx_db_info_t* info) {
 
 // Process-wide pinned bounce buffers for file -> device streaming (allocated once, kept).
 namespace {
-constexpr size_t kChunk = 8u << 20;
-constexpr int kReaders = 8, kSlotsPerReader = 2;
+constexpr size_t kChunk = 2u << 20;                 // small chunks: the first PCIe transfer starts after 2 MiB of page-cache copy
+constexpr int kReaders = 16, kSlotsPerReader = 2;
 struct Bounce {
 	std::mutex mu;
 	uint8_t* buf[kReaders][kSlotsPerReader] = {};
@@ -695,8 +695,9 @@ struct Bounce {
 Bounce g_bounce;
 }  // namespace
 
-// .kmc_suf record area -> HBM: kReaders threads pread() 8 MiB chunks into pinned bounce buffers
-// and push each with its own stream, so page-cache copies and PCIe transfers overlap.
+// .kmc_suf record area -> HBM: reader threads pread() 2 MiB chunks into pinned bounce buffers and push each with
+// its own stream, so page-cache copies and PCIe transfers overlap.  The page-cache copy (5-6 GB/s per thread) is the
+// slow half: one thread per host core, up to kReaders.
 extern "C" int kmx_db_upload(kmx_db* db) {
 	if (!db) return fail(KMX_EARG, "null database");
 	if (db->d_suf) return KMX_OK;
@@ -720,7 +721,7 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 	CU(cudaStreamSynchronize(x->stream));                // the allocation is usable from the reader streams now
 	TRACE(t0, "upload: buffers ready");
 	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
-	int want_thr = 4;
+	int want_thr = std::max(1, std::min<int>(kReaders, (int)std::thread::hardware_concurrency()));
 	if (const char* e = getenv("KMX_READERS")) want_thr = std::max(1, std::min(kReaders, atoi(e)));
 	const int n_thr = (int)std::min<uint64_t>(want_thr, n_chunks);
 	std::vector<int> status(kReaders, KMX_OK);
@@ -1118,6 +1119,9 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	// for HBM-resident models (hc14 shape: 187 ms against 186 ms) and slower for L2-resident ones, so it stays off.
 	a.claim_first = 0;
 	if (const char* e = getenv("KMX_CLAIM_FIRST")) a.claim_first = atoi(e) ? 1 : 0;
+	// arrays + km_back well beyond the L2 (126 MB): their random sectors should not wash the insert's hot structures out of it
+	a.stream_cells = (2ULL * m->n_bits * m->bytes[6] + m->bytes[7]) > (192ULL << 20) ? 7 : 0;
+	if (const char* e = getenv("KMX_STREAM_CELLS")) a.stream_cells = atoi(e) & 7;
 	a.max_iterations = kBucket + 64;
 	a.phase_round = -1;
 	if (const char* e = getenv("KMX_PHASE_ROUND")) a.phase_round = atoi(e);
