@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 	uint32_t epoch = vctl->epoch;
 	uint32_t seq = vctl->seq;
 	const unsigned long long evict_first = make_evict_first_policy();
+	const unsigned long long evict_last = make_evict_last_policy();
 #if KMX_GRIDBAR
 	GridBarrier gbar;
 	gbar.init(&ctl->bar);
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					if (j < hk) {
 						const uint64_t pos = fastmod(hash_finish(p, k - 2, c_seeds[j]), m.km_back.mod);
 						if (a.stream_cells & 4) red_or32_stream(m.km_back.words + (pos >> 5), bit_mask32(pos), evict_first);
+						else if (a.stream_cells & 8) red_or32_stream(m.km_back.words + (pos >> 5), bit_mask32(pos), evict_last);
 						else red_or32(m.km_back.words + (pos >> 5), bit_mask32(pos));
 					}
 				}

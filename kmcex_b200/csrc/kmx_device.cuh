@@ -73,6 +73,11 @@ KMX_D unsigned long long make_evict_first_policy() {
 	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 	return pol;
 }
+KMX_D unsigned long long make_evict_last_policy() {
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
 KMX_D unsigned long long ld_stream64(const unsigned long long* p, unsigned long long pol) {
 	unsigned long long v;
 	asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));

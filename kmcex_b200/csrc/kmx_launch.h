@@ -84,7 +84,7 @@ struct InsertArgs {
 	uint32_t* claim;                  // [n_bits][2][2^claim_log2 / 32] claim bitmaps (position, wanted value)
 	uint32_t claim_log2;              // bits per bitmap (upper bound; a round uses a prefix sized to its items)
 	int claim_first;                  // 1: phase 0 claims blindly, phase 1 reads and commits back to back (HBM-resident arrays)
-	int stream_cells;                 // the arrays are far larger than the L2: L2 evict-first policy for 1 = cell loads, 2 = cell reductions, 4 = km_back reductions
+	int stream_cells;                 // the arrays are far larger than the L2: L2 evict-first policy for 1 = cell loads, 2 = cell reductions, 4 = km_back reductions; 8 = evict-last for km_back reductions
 	uint64_t* rest_kmer;              // survivors of all batches
 	uint32_t* rest_occ;
 	unsigned long long rest_cap;
