@@ -179,6 +179,8 @@ int kmx_microbench_random(int kind, uint64_t footprint_bytes, uint64_t n_items, 
 /* the same with locality: the accesses of items that run together fall into one window of window_bytes (0 = none) */
 /* microseconds per grid-wide barrier of a co-resident kernel: mode 0 cooperative_groups grid.sync(), 1 the library's counter barrier */
 int kmx_microbench_grid_barrier(int mode, int threads, int blocks_per_sm, int reps, float* us_out);
+/* nanoseconds per returning atomicAdd when every warp of a full grid hammers n_counters addresses (list appends) */
+int kmx_microbench_hot_atomic(int n_counters, int per_warp, float* ns_out);
 int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out);
 
 #ifdef __cplusplus

@@ -95,6 +95,7 @@ SIGNATURES = {
     "kmx_dist_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_grid_barrier": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "kmx_microbench_hot_atomic": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_windowed": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 

@@ -27,8 +27,10 @@ constexpr int kMaxHash = 12;                      // n_hash supported by this bu
 constexpr int kMaxBf = 3;                         // kmodel.hpp:50   bf_num is 1 or 3
 
 // ---------------------------------------------------------------------------------------
-// exact h % d for a runtime-constant d:  q' = mulhi(h, floor((2^64-1)/d)) is q-2..q, so the
-// remainder estimate is below 3d and two conditional subtractions finish it (d < 2^62).
+// exact h % d for a runtime-constant d >= 2:  with m = floor(2^64 / d) + 1 (so m*d > 2^64 and
+// m <= 2^64/d + 1), q' = mulhi(h, m) satisfies h/d < h*m/2^64 < h/d + 1, i.e. q' is q or q + 1;
+// h - q'*d is then the remainder or the remainder minus d (negative as a signed word, d < 2^63):
+// one sign-masked add finishes it.  (A probe position costs one of these on top of its hash.)
 // ---------------------------------------------------------------------------------------
 struct FastMod {
 	uint64_t d;
@@ -38,7 +40,8 @@ struct FastMod {
 inline FastMod make_fastmod(uint64_t d) {
 	FastMod f;
 	f.d = d;
-	f.magic = d ? (~0ULL) / d : 0;
+	f.magic = 0;
+	if (d >= 2) f.magic = (~0ULL) / d + ((~0ULL) % d == d - 1 ? 1 : 0) + 1;   // floor(2^64 / d) + 1
 	return f;
 }
 
@@ -51,11 +54,9 @@ KMX_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 }
 
 KMX_HD uint64_t fastmod(uint64_t h, const FastMod& f) {
-	uint64_t q = mulhi64(h, f.magic);
-	uint64_t r = h - q * f.d;
-	if (r >= f.d) r -= f.d;
-	if (r >= f.d) r -= f.d;
-	return r;
+	const uint64_t q = mulhi64(h, f.magic);
+	const uint64_t r = h - q * f.d;
+	return r + (f.d & (uint64_t)((int64_t)r >> 63));
 }
 
 // ---------------------------------------------------------------------------------------

@@ -1792,7 +1792,7 @@ extern "C" void kmx_host_sizes(const uint64_t kmer_counts[3], int bf_num, uint64
 	model_sizes(kmer_counts, bf_num, km_kmers, n_hash, bytes);
 }
 
-extern "C" uint64_t kmx_host_fastmod(uint64_t h, uint64_t d) { return d ? fastmod(h, make_fastmod(d)) : 0; }
+extern "C" uint64_t kmx_host_fastmod(uint64_t h, uint64_t d) { return d >= 2 ? fastmod(h, make_fastmod(d)) : 0; }   // filter lengths are >= 8 bits
 
 // the closed form insert_kernel uses for reorder_buffer (kmodel.hpp:529-540)
 extern "C" int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm) {

@@ -143,3 +143,44 @@ extern "C" int kmx_microbench_grid_barrier(int mode, int threads, int blocks_per
 	cudaFree(sink);
 	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
 }
+
+// ---- returning atomics on few addresses: the list appends of the insert kernel (one atomicAdd per warp and iteration) ---
+namespace {
+__global__ void __launch_bounds__(256) hot_atomic_kernel(unsigned int* counters, int n_counters, int per_warp, unsigned int* sink) {
+	const unsigned int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	unsigned int acc = 0;
+	if ((threadIdx.x & 31) == 0)
+		for (int r = 0; r < per_warp; r++) acc += atomicAdd(counters + 32 * ((warp_g + r) % n_counters), 1u);   // one counter per 128-byte line
+	if (acc == 0x12345u) *sink = acc;
+}
+}  // namespace
+
+// every warp of a full grid (4 blocks of 256 threads per SM) issues per_warp dependent atomicAdd-with-result on one of
+// n_counters addresses; *ns_out = nanoseconds per atomic (wall time of the kernel / atomics issued)
+extern "C" int kmx_microbench_hot_atomic(int n_counters, int per_warp, float* ns_out) {
+	if (n_counters < 1 || n_counters > 1024 || per_warp < 1 || !ns_out) return KMX_EARG;
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	unsigned int* counters = nullptr;
+	unsigned int* sink = nullptr;
+	if (cudaMalloc(&counters, 1024 * 128) != cudaSuccess || cudaMalloc(&sink, 4) != cudaSuccess) return KMX_ECUDA;
+	cudaMemset(counters, 0, 1024 * 128);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	const int grid = 4 * sms;
+	hot_atomic_kernel<<<grid, 256>>>(counters, n_counters, per_warp, sink);
+	cudaEventRecord(e0);
+	hot_atomic_kernel<<<grid, 256>>>(counters, n_counters, per_warp, sink);
+	cudaEventRecord(e1);
+	cudaError_t e = cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	*ns_out = 1e6f * ms / ((float)grid * 8 * per_warp);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(counters);
+	cudaFree(sink);
+	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
+}

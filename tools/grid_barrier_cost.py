@@ -15,3 +15,7 @@ for threads, per_sm in ((256, 4), (512, 2), (1024, 1), (256, 1)):
         us = C.c_float(0)
         kx._lib.check(lib.kmx_microbench_grid_barrier(mode, threads, per_sm, 2000, C.byref(us)))
         print(f"{name:16s} {per_sm * 148:4d} blocks x {threads:4d} threads: {us.value:6.2f} us per barrier")
+for n_counters in (1, 4, 16, 64):
+    ns = C.c_float(0)
+    kx._lib.check(lib.kmx_microbench_hot_atomic(n_counters, 9, C.byref(ns)))
+    print(f"returning atomicAdd, 4736 warps x 9 on {n_counters:3d} address(es): {ns.value:6.2f} ns per atomic ({ns.value * 4736 * 9 / 1e3:7.1f} us for the lot)")
