@@ -148,6 +148,50 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 		bins[i] = bin;
 		full[i] = ok;
 	}
+	if (H != 0 && B != 0 && H <= 8) {
+		// Stage B, one pending array per lane and iteration: an array passes stage A for only a few lanes of a warp
+		// (its resident k-mers plus ~14 % of the others), so walking the arrays one after the other issues the same
+		// ~250 instructions n_bits times with 3-4 active lanes each.  Here every lane takes ITS next pending array
+		// (array index, seeds and cell pointer become per-lane values), and the warp is done after
+		// max-over-lanes(pending arrays) rounds, typically 2.  The packed results go back into bins / full.
+		uint32_t pending = 0;
+#pragma unroll
+		for (int i = 0; i < kBmax(B); i++)
+			if (i < c.b() && full[i]) pending |= 1u << i;
+		unsigned long long packed = 0;
+		uint32_t okmask = 0;
+		while (pending) {
+			const int i = __ffs((int)pending) - 1;
+			pending &= pending - 1;
+			const unsigned long long* cells = m.cells[i];
+			unsigned long long cell[kHmax(H)];
+			uint32_t sh[kHmax(H)];
+#pragma unroll
+			for (int j = kStageA; j < kHmax(H); j++) {
+				const uint64_t pos = fastmod(hash_finish(q.p31, c.k(), m.arr_seed[i][j]), m.arr_mod);
+				sh[j] = ((uint32_t)pos & 31u) ^ 7u;
+				cell[j] = __ldg(cells + (pos >> 5));
+			}
+			uint32_t bin = 0;
+			bool ok = true;
+#pragma unroll
+			for (int j = kStageA; j < kHmax(H); j++) {
+				const unsigned long long x = cell[j] >> sh[j];
+				bin |= ((uint32_t)x & 1u) << j;
+				ok &= ((uint32_t)(x >> 32) & 1u) != 0;
+			}
+			packed |= (unsigned long long)bin << (8 * i);
+			okmask |= (ok ? 1u : 0u) << i;
+		}
+#pragma unroll
+		for (int i = 0; i < kBmax(B); i++) {
+			if (i < c.b() && full[i]) {
+				bins[i] |= (int)((packed >> (8 * i)) & 0xFFu);
+				full[i] = ((okmask >> i) & 1u) != 0;
+			}
+		}
+		return;
+	}
 #pragma unroll
 	for (int i = 0; i < kBmax(B); i++) {
 		if (i < c.b() && full[i]) {
@@ -187,19 +231,41 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 // of bounds there and counts as "no match" here.  Because keys are sorted globally, "in group g
 // with equal suffix" is "equal full key", found through a bucket index over the top key bits;
 // the false-hit suffix of each prefix is precomputed (rest_quirk_kernel).
-__device__ __forceinline__ int rest_lookup_indexed(const DevRest& R, uint64_t v) {
+// Split in two so that the first wave of loads (bucket bounds, false-hit suffix) is in flight together with the
+// Bloom / km_back probes of the caller; the bucket's keys (about one per bucket) are then fetched in one wave.
+struct RestProbe {
+	uint32_t lo, hi;
+	uint64_t quirk;
+};
+
+__device__ __forceinline__ RestProbe rest_begin(const DevRest& R, uint64_t v) {
+	RestProbe p;
 	const uint32_t b = (uint32_t)(v >> R.fine_shift);
-	uint32_t lo = __ldg(R.fine + b), hi = __ldg(R.fine + b + 1);
+	p.lo = __ldg(R.fine + b);
+	p.hi = __ldg(R.fine + b + 1);
+	p.quirk = __ldg(R.quirk_suffix + (uint32_t)(v >> R.suffix_bits));
+	return p;
+}
+
+__device__ __forceinline__ int rest_finish(const DevRest& R, uint64_t v, const RestProbe& p) {
+	uint32_t lo = p.lo, hi = p.hi;
 	while (hi - lo > 4) {                          // long bucket (skewed data): bisect down first
 		const uint32_t mid = (lo + hi) >> 1;
 		if (__ldg(R.keys + mid) <= v) lo = mid; else hi = mid;
 	}
-	for (uint32_t e = lo; e < hi; e++)
-		if (__ldg(R.keys + e) == v) return __ldg(R.counts + e);
-	const uint32_t pre = (uint32_t)(v >> R.suffix_bits);
-	if (__ldg(R.quirk_suffix + pre) == (v & R.suffix_mask)) return __ldg(R.counts + __ldg(R.quirk_index + pre));
+	uint64_t key[4];
+#pragma unroll
+	for (uint32_t e = 0; e < 4; e++) key[e] = lo + e < hi ? __ldg(R.keys + lo + e) : ~0ULL;   // packed k-mers are below 2^64 - 1
+	int found = -1;
+#pragma unroll
+	for (uint32_t e = 0; e < 4; e++)
+		if (key[e] == v) found = (int)(lo + e);
+	if (found >= 0) return __ldg(R.counts + found);
+	if (p.quirk == (v & R.suffix_mask)) return __ldg(R.counts + __ldg(R.quirk_index + (uint32_t)(v >> R.suffix_bits)));
 	return 0;
 }
+
+__device__ __forceinline__ int rest_lookup_indexed(const DevRest& R, uint64_t v) { return rest_finish(R, v, rest_begin(R, v)); }
 
 // get_candidates (kmodel.hpp:326-342) for one neighbour; returns -1 when it adds nothing
 template <int K, int H, int B>
@@ -250,11 +316,12 @@ template <int K, int H, int B>
 __device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uint64_t r, Primary& P) {
 	QueryCfg<K, H, B> c(m);
 	// the rest lookup's loads and the Bloom wave are independent of each other
+	const RestProbe rp = rest_begin(m.rest, v);
 	QueryHashes<K, H, B> q;
 	q.compute(c, r);
 	const bool in_back = check_km_back(c, q);
 	P.occ = check_all_bf(c, q);
-	const int rest = rest_lookup_indexed(m.rest, v);
+	const int rest = rest_finish(m.rest, v, rp);
 	P.nc = 0;
 	if (rest != 0) {                       // kmodel.hpp:104-105
 		P.path = 1;
