@@ -77,17 +77,38 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 			hit[i] = ok;
 		}
 	}
+	if (H != 0) {
+		// stage B with one pending filter pair per lane and iteration (see probe_arrays): a pair passes stage A for
+		// a quarter of the lanes, so the warp is done after max-over-lanes(pending pairs) rounds instead of bf_num
+		uint32_t pending = 0, okmask = 0;
 #pragma unroll
-	for (int i = 0; i < kMaxBf; i++) {
-		if (i < m.bf_num && hit[i]) {
+		for (int i = 0; i < kMaxBf; i++)
+			if (i < m.bf_num && hit[i]) pending |= 1u << i;
+		while (pending) {
+			const int i = __ffs((int)pending) - 1;
+			pending &= pending - 1;
 			bool ok = true;
 #pragma unroll
-			for (int j = kStageA; j < kHmax(H) - 1; j++)
-				if (j < hb) ok &= filter_test(m.bf[i], q.h31[j]);
+			for (int j = kStageA; j < kHmax(H) - 1; j++) ok &= filter_test(m.bf[i], q.h31[j]);
 #pragma unroll
-			for (int j = 0; j < kHmax(H) - 2; j++)
-				if (j < hk) ok &= filter_test(m.bf_back[i], q.h29[j]);
-			hit[i] = ok;
+			for (int j = 0; j < kHmax(H) - 2; j++) ok &= filter_test(m.bf_back[i], q.h29[j]);
+			okmask |= (ok ? 1u : 0u) << i;
+		}
+#pragma unroll
+		for (int i = 0; i < kMaxBf; i++) hit[i] = hit[i] && ((okmask >> i) & 1u) != 0;
+	} else {
+#pragma unroll
+		for (int i = 0; i < kMaxBf; i++) {
+			if (i < m.bf_num && hit[i]) {
+				bool ok = true;
+#pragma unroll
+				for (int j = kStageA; j < kHmax(H) - 1; j++)
+					if (j < hb) ok &= filter_test(m.bf[i], q.h31[j]);
+#pragma unroll
+				for (int j = 0; j < kHmax(H) - 2; j++)
+					if (j < hk) ok &= filter_test(m.bf_back[i], q.h29[j]);
+				hit[i] = ok;
+			}
 		}
 	}
 	if (m.bf_num == 1) return hit[0] ? m.ci : 0;
