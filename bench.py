@@ -132,7 +132,7 @@ class ClockSampler:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch, from profiles/ (ncu --set full)
-NCU_TRAFFIC = {"rs": 9.89e8}         # profiles/r1_m_ncu_full_bench_rs.txt
+NCU_TRAFFIC = {"rs": 9.86e8}         # profiles/r1_o_ncu_full_bench_rs.txt
 
 
 def random_sector_peaks() -> dict:

@@ -215,6 +215,12 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
 	__shared__ uint32_t s_warp[9];
 	__shared__ uint64_t s_slot[2];
+	// Bloom-bound k-mers of the tile, compacted: a thread walks 8 consecutive records (the stream must keep file order),
+	// of which some fraction is Bloom-bound -- hashing them in place would run the ~650-instruction insert 8 times per
+	// warp with that fraction of the lanes; from this list every lane of the block has work (order is free for ORs)
+	__shared__ uint64_t s_bloom_kmer[LIST ? 1 : kTile];
+	__shared__ uint8_t s_bloom_class[LIST ? 1 : kTile];
+	__shared__ unsigned int s_bloom_n;
 	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
 	const int k = K ? K : db.k;
 	const int nh = H ? H : m.n_hash;
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
 		const bool bloom_tile = LIST || (tile >= bloom_lo && tile < bloom_hi);   // this launch's share of the Bloom inserts
 		__syncthreads();
+		if (threadIdx.x == 0) s_bloom_n = 0;
 		stage_tile(db, s0, n_rec, s_stage);
 		if (threadIdx.x < 2) {
 			uint64_t s = threadIdx.x == 0 ? s0 : s0 + n_rec - 1;
@@ -248,20 +255,32 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 					if (to_stream) {
 						keep |= 1u << j;
 						n_keep++;
-					} else if (bloom_tile && c >= (uint32_t)m.ci) {
-						const int f = (int)c - m.ci;
-						uint64_t r = reverse_bases(kmer[j], k);
-						HashPrep p;
-						hash_prepare(r, k, p);
-#pragma unroll
-						for (int q = 0; q < (H ? H : kMaxHash) - 1; q++)
-							if (q < nh - 1) filter_set(m.bf[f], hash_finish(p, k, c_seeds[q]));
-						hash_prepare(middle_r(r, k), k - 2, p);
-#pragma unroll
-						for (int q = 0; q < (H ? H : kMaxHash) - 2; q++)
-							if (q < nh - 2) filter_set(m.bf_back[f], hash_finish(p, k - 2, c_seeds[q]));
+					} else if (!LIST && bloom_tile && c >= (uint32_t)m.ci) {
+						cg::coalesced_group g = cg::coalesced_threads();
+						unsigned int at = 0;
+						if (g.thread_rank() == 0) at = atomicAdd(&s_bloom_n, g.size());
+						at = g.shfl(at, 0) + g.thread_rank();
+						s_bloom_kmer[at] = kmer[j];
+						s_bloom_class[at] = (uint8_t)(c - (uint32_t)m.ci);
 					}
 				}
+			}
+		}
+		if (!LIST) {
+			__syncthreads();
+			const unsigned int n_bloom = s_bloom_n;
+			for (unsigned int x = threadIdx.x; x < n_bloom; x += blockDim.x) {
+				const int f = s_bloom_class[x];
+				const uint64_t r = reverse_bases(s_bloom_kmer[x], k);
+				HashPrep p;
+				hash_prepare(r, k, p);
+#pragma unroll
+				for (int q = 0; q < (H ? H : kMaxHash) - 1; q++)
+					if (q < nh - 1) filter_set(m.bf[f], hash_finish(p, k, c_seeds[q]));
+				hash_prepare(middle_r(r, k), k - 2, p);
+#pragma unroll
+				for (int q = 0; q < (H ? H : kMaxHash) - 2; q++)
+					if (q < nh - 2) filter_set(m.bf_back[f], hash_finish(p, k - 2, c_seeds[q]));
 			}
 		}
 		if (out_kmer == nullptr) continue;                   // Bloom share only (uniform over the grid)
