@@ -110,8 +110,8 @@ void kmx_info(const kmx_model* m, kmx_info_t* info);
 int kmx_model_sync(kmx_model* m);                 /* wait for the model's stream               */
 
 /* ---- KMC database listing: CKMCFile::OpenForListing / ReadNextKmer kmc_file.cpp:66-99,428-515 */
-kmx_db* kmx_db_open(const char* db_base);         /* parse .kmc_pre, read .kmc_suf into pinned memory */
-int kmx_db_upload(kmx_db* db);                    /* copy LUT + records to the device (idempotent) */
+kmx_db* kmx_db_open(const char* db_base);         /* parse .kmc_pre (header + LUT), check .kmc_suf; records stay on disk */
+int kmx_db_upload(kmx_db* db);                    /* LUT + records -> device through pinned bounce buffers (idempotent) */
 void kmx_db_info(const kmx_db* db, kmx_db_info_t* info);
 /* GPU listing: all records in file order, count filter of ReadNextKmer applied; returns the
  * number listed through *n_out; kmers/counts need room for total_kmers entries (host)        */

@@ -61,7 +61,6 @@ struct InsertCtl {                    // lives in device memory, survives across
 	unsigned int nfail[2][kMaxArrays];   // survivors of each bucket after a round, by round parity (peers write it too)
 	unsigned int seq;                 // rounds completed: the cross-GPU barrier counts with it
 	unsigned int bar;                 // arrivals at the grid barrier (kmx_gridbar.cuh), never reset
-	unsigned long long rest_base[kMaxArrays];
 	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
 	unsigned int slot0_occ[kMaxArrays];
 	unsigned int slot0_valid[kMaxArrays];

@@ -3,9 +3,10 @@
 * retrieval: the finished model is REPLICATED on every rank (broadcast of the three model files'
   bytes from the rank that built it) and the query batch is SHARDED contiguously over the ranks;
   answers are gathered in batch order.  No per-query communication.
-* build: in this round every rank builds whole models (independent databases, or replicas of the
-  same one) -- the coupled-array insert is sequential per array (kmodel.hpp:557-573) and its
-  array-owner decomposition is the next row.
+* build: either every rank builds whole models (independent databases -- `bench.py --gpus N`), or
+  ONE model is built by all ranks (`build_array_owner`): Bloom inserts sharded by record range and
+  OR-ed through peer memory, coupled arrays split by ownership with survivors handed from owner to
+  owner through peer memory.
 
 The collectives run on CUDA tensors under NCCL and on CPU tensors under gloo (the CPU tests use
 gloo with world_size 2 and the oracle standing in for the GPU model)."""
