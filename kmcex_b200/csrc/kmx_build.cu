@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 	// Control words every thread needs after a barrier (list lengths, error flag, survivor counts) are fetched ONCE per
 	// block, by the thread that waited at the barrier, and handed out through shared memory: a word read by every warp of
 	// the grid is several thousand requests to one L2 slice, microseconds per word and barrier.
-	__shared__ uint32_t s_hot[12];                        // list_n[0], list_n[1], epoch, error, nfail[parity][0..7]
+	__shared__ uint32_t s_hot[12];                        // list_n[0..2], error, nfail[parity][0..7]
 	auto gsync_fetch = [&](unsigned int parity) {
 #if KMX_GRIDBAR
 		gbar.arrive_wait();
@@ -517,15 +517,16 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				}
 				a.status[id] = kAccepted;
 			};
-			auto reserve = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) {
-				uint32_t* table = a.resv + (size_t)it.arr * 2 * a.resv_slots;
+			// (two reservation tables per array: the classic iterations use table 0 only, the merged passes alternate)
+			auto reserve = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi, uint32_t tab = 0) {
+				uint32_t* table = a.resv + ((size_t)it.arr * 2 + tab) * 2 * a.resv_slots;
 #pragma unroll
 				for (int j = 0; j < HM; j++)
 					if (j < nh && ((need >> j) & 1u))
 						red_min32(table + 2 * ((uint32_t)it.pos[j] & slot_mask) + ((it.bin >> j) & 1u), key_hi | it.c);
 			};
-			auto holds_reservations = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi) -> bool {
-				const uint32_t* table = a.resv + (size_t)it.arr * 2 * a.resv_slots;
+			auto holds_reservations = [&](const ItemCtx& it, uint32_t need, uint32_t key_hi, uint32_t tab = 0) -> bool {
+				const uint32_t* table = a.resv + ((size_t)it.arr * 2 + tab) * 2 * a.resv_slots;
 				const uint32_t key = key_hi | it.c;
 				bool ok = true;
 #pragma unroll
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			const size_t claim_stride = (size_t)1 << (a.claim_log2 - 5);     // words per (array, want) bitmap
 
 			if (epoch + 2 >= kEpochMax) {                      // reservation keys can get no smaller: start the epochs over
-				for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
+				for (size_t x = tid; x < (size_t)nb * 4 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
 				epoch = 0;
 				GSYNC();
 			}
@@ -581,6 +582,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			if (tid == 0) {                                     // nobody touches the lists during phase 0
 				vctl->list_n[0] = 0;
 				vctl->list_n[1] = 0;
+				vctl->list_n[2] = 0;
 			}
 			// ---- first iteration, phase 0: reject on the committed state, or claim (position, wanted value) ----
 			// (the next item's k-mer and count are fetched while the current one is hashed and probed)
@@ -690,74 +692,164 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				vctl->phase_cycles[1] += (unsigned long long)(now - tick);
 				tick = now;
 			}
-			// ---- phase 2: contested items that hold all their reservations commit, the rest go to the list ----
-			const uint32_t n_contested = s_hot[1];
-			for (uint32_t x = tid; x < n_contested; x += T) {
-				const uint32_t id = __ldcg(a.list[1] + x);
-				const uint32_t st = a.status[id];
-				ItemCtx it;
-				load_item(id, it);
-				if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
-				else append(a.list[0], &ctl->list_n[0], id);
-			}
-			gsync_fetch(par);
-			uint32_t n_list = s_hot[0];
 			uint32_t iter = 1;
-			int cur = 0;
-			epoch++;
-			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
-				long long now = clock64();
-				vctl->phase_cycles[2] += (unsigned long long)(now - tick);
-				tick = now;
-			}
-			// ---- later iterations walk the list of still undecided (contested) items ----
-			while (n_list != 0) {
-				if (epoch + 1 >= kEpochMax) {                   // keys can get no smaller: start over
-					for (size_t x = tid; x < (size_t)nb * 2 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
-					epoch = 0;
-					GSYNC();
-				}
-				key_hi = (kEpochMax - epoch) << kBucketLog;
-				const uint32_t* list_cur = a.list[cur];
-				if (tid == 0) vctl->list_n[cur ^ 1] = 0;
-				for (uint32_t x = tid; x < n_list; x += T) {
-					const uint32_t id = __ldcg(list_cur + x);
-					const uint32_t st = a.status[id];
-					ItemCtx it;
-					load_item(id, it);
-					bool conflict;
-					uint32_t untagged;
-					read_cells(it, conflict, untagged);
-					if (conflict) {
-						reject(id);
-						continue;
+			if (a.merged) {
+				// ---- merged passes: reserve for the next pass while committing for this one -------------------------
+				// A contested item that holds its reservations of the PREVIOUS pass commits; one that does not reserves
+				// in the OTHER table for the next pass, in the same sweep -- one barrier per iteration instead of two and
+				// one hashing of the item instead of two.  Two items that both commit in a pass never want opposite values
+				// at a shared untagged position (both would have it in their contested set and only the smaller index
+				// holds it), so commits and the cell reads of the same pass may interleave freely; an item that loses
+				// re-reads its cells at the start of the next pass and is rejected there if the winner conflicts with it.
+				// A reservation left behind by an item that gets rejected can only delay somebody by one pass.
+				uint32_t n_list = s_hot[1];
+				int cur = 1;
+				uint32_t tab = 0;
+				bool fresh = true;                                // status words are current: no need to re-read the cells
+				while (n_list != 0) {
+					if (epoch + 2 >= kEpochMax) {
+						// keys can get no smaller: clear the tables and let every undecided item reserve again before
+						// anybody commits (the first half of a classic iteration)
+						for (size_t x = tid; x < (size_t)nb * 4 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
+						epoch = 0;
+						GSYNC();
+						key_hi = (kEpochMax - epoch) << kBucketLog;
+						for (uint32_t x = tid; x < n_list; x += T) {
+							const uint32_t id = __ldcg(a.list[cur] + x);
+							const uint32_t st = a.status[id];
+							if (st >> kStateShift) continue;
+							ItemCtx it;
+							load_item(id, it);
+							bool conflict;
+							uint32_t untagged;
+							read_cells(it, conflict, untagged);
+							if (conflict) {
+								reject(id);
+								continue;
+							}
+							const uint32_t need = (st >> kNeedShift) & untagged;
+							a.status[id] = untagged | (need << kNeedShift);
+							if (need) reserve(it, need, key_hi, tab);
+						}
+						GSYNC();
+						fresh = true;
 					}
-					const uint32_t need = (st >> kNeedShift) & untagged;     // contested positions that are still open
-					if (need == 0) {
-						commit(id, it, untagged);
-					} else {
-						reserve(it, need, key_hi);
-						a.status[id] = untagged | (need << kNeedShift);
+					const uint32_t key_prev = key_hi;             // what the undecided items reserved with, in table `tab`
+					epoch++;
+					key_hi = (kEpochMax - epoch) << kBucketLog;   // what this pass reserves with, in table `tab ^ 1`
+					// three lists in rotation: this pass reads `cur`, appends to `nxt` and clears the counter of the third,
+					// which the pass before last read (every block has fetched that length two barriers ago) and the
+					// next pass appends to
+					const int nxt = cur == 2 ? 0 : cur + 1, spare = nxt == 2 ? 0 : nxt + 1;
+					const uint32_t* list_cur = a.list[cur];
+					if (tid == 0) vctl->list_n[spare] = 0;
+					for (uint32_t x = tid; x < n_list; x += T) {
+						const uint32_t id = __ldcg(list_cur + x);
+						const uint32_t st = a.status[id];
+						if (st >> kStateShift) continue;          // rejected while the epochs were restarted
+						ItemCtx it;
+						load_item(id, it);
+						uint32_t untagged = st & kMaskBits, need = (st >> kNeedShift) & kMaskBits;
+						if (!fresh) {
+							bool conflict;
+							uint32_t now_untagged;
+							read_cells(it, conflict, now_untagged);
+							if (conflict) {
+								reject(id);
+								continue;
+							}
+							need &= now_untagged;                 // contested positions that are still open
+							untagged = now_untagged;
+						}
+						if (need == 0 || holds_reservations(it, need, key_prev, tab)) {
+							commit(id, it, untagged);
+						} else {
+							reserve(it, need, key_hi, tab ^ 1u);
+							a.status[id] = untagged | (need << kNeedShift);
+							append(a.list[nxt], &ctl->list_n[nxt], id);
+						}
+					}
+					gsync_fetch(par);
+					n_list = s_hot[nxt];
+					cur = nxt;
+					tab ^= 1u;
+					fresh = false;
+					iter++;
+					if (iter >= a.max_iterations) {
+						if (tid == 0) vctl->error = 1;
+						return;                                     // uniform over the grid
 					}
 				}
-				GSYNC();
-				for (uint32_t x = tid; x < n_list; x += T) {
-					const uint32_t id = __ldcg(list_cur + x);
+			} else {
+				// ---- phase 2: contested items that hold all their reservations commit, the rest go to the list ----
+				const uint32_t n_contested = s_hot[1];
+				for (uint32_t x = tid; x < n_contested; x += T) {
+					const uint32_t id = __ldcg(a.list[1] + x);
 					const uint32_t st = a.status[id];
-					if (st >> kStateShift) continue;
 					ItemCtx it;
 					load_item(id, it);
 					if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
-					else append(a.list[cur ^ 1], &ctl->list_n[cur ^ 1], id);
+					else append(a.list[0], &ctl->list_n[0], id);
 				}
 				gsync_fetch(par);
-				n_list = s_hot[cur ^ 1];
-				cur ^= 1;
-				iter++;
+				uint32_t n_list = s_hot[0];
+				iter = 1;
+				int cur = 0;
 				epoch++;
-				if (iter >= a.max_iterations) {
-					if (tid == 0) vctl->error = 1;
-					return;                                     // uniform over the grid
+				if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
+					long long now = clock64();
+					vctl->phase_cycles[2] += (unsigned long long)(now - tick);
+					tick = now;
+				}
+				// ---- later iterations walk the list of still undecided (contested) items ----
+				while (n_list != 0) {
+					if (epoch + 1 >= kEpochMax) {                   // keys can get no smaller: start over
+						for (size_t x = tid; x < (size_t)nb * 4 * a.resv_slots; x += T) a.resv[x] = 0xFFFFFFFFu;
+						epoch = 0;
+						GSYNC();
+					}
+					key_hi = (kEpochMax - epoch) << kBucketLog;
+					const uint32_t* list_cur = a.list[cur];
+					if (tid == 0) vctl->list_n[cur ^ 1] = 0;
+					for (uint32_t x = tid; x < n_list; x += T) {
+						const uint32_t id = __ldcg(list_cur + x);
+						const uint32_t st = a.status[id];
+						ItemCtx it;
+						load_item(id, it);
+						bool conflict;
+						uint32_t untagged;
+						read_cells(it, conflict, untagged);
+						if (conflict) {
+							reject(id);
+							continue;
+						}
+						const uint32_t need = (st >> kNeedShift) & untagged;     // contested positions that are still open
+						if (need == 0) {
+							commit(id, it, untagged);
+						} else {
+							reserve(it, need, key_hi);
+							a.status[id] = untagged | (need << kNeedShift);
+						}
+					}
+					GSYNC();
+					for (uint32_t x = tid; x < n_list; x += T) {
+						const uint32_t id = __ldcg(list_cur + x);
+						const uint32_t st = a.status[id];
+						if (st >> kStateShift) continue;
+						ItemCtx it;
+						load_item(id, it);
+						if (holds_reservations(it, st >> kNeedShift, key_hi)) commit(id, it, st & kMaskBits);
+						else append(a.list[cur ^ 1], &ctl->list_n[cur ^ 1], id);
+					}
+					gsync_fetch(par);
+					n_list = s_hot[cur ^ 1];
+					cur ^= 1;
+					iter++;
+					epoch++;
+					if (iter >= a.max_iterations) {
+						if (tid == 0) vctl->error = 1;
+						return;                                     // uniform over the grid
+					}
 				}
 			}
 			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {

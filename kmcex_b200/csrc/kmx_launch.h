@@ -55,12 +55,13 @@ constexpr int kMaxRanks = 8;
 struct InsertCtl {                    // lives in device memory, survives across launches
 	unsigned long long rest_n;        // survivors appended to the rest list so far
 	unsigned long long attempts, accepted, iterations;
-	unsigned int list_n[2];           // entries of the two undecided-item lists
-	unsigned int epoch;               // reservation epoch (keys of newer epochs are smaller)
+	unsigned int list_n[3];           // entries of the undecided-item lists (the classic iterations use two, the merged passes rotate three)
 	unsigned int error;               // non-zero: iteration cap hit / rest overflow
 	unsigned int nfail[2][kMaxArrays];   // survivors of each bucket after a round, by round parity (peers write it too)
 	unsigned int seq;                 // rounds completed: the cross-GPU barrier counts with it
 	unsigned int bar;                 // arrivals at the grid barrier (kmx_gridbar.cuh), never reset
+	unsigned int epoch;               // reservation epoch (keys of newer epochs are smaller)
+	unsigned int pad0;
 	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
 	unsigned int slot0_occ[kMaxArrays];
 	unsigned int slot0_valid[kMaxArrays];
@@ -77,12 +78,13 @@ struct InsertArgs {
 	uint32_t* excl_rank;              // [n_bits * kBucket]
 	uint32_t* holepos;                // [n_bits * kBucket]
 	uint32_t* tile_fail;              // [n_bits * kBucket / 256]
-	uint32_t* list[2];                // [n_bits * kBucket] ids still undecided, ping-pong
-	uint32_t* resv;                   // [n_bits][2 * resv_slots]
+	uint32_t* list[3];                // [n_bits * kBucket] ids still undecided (two ping-pong, three rotating for the merged passes)
+	uint32_t* resv;                   // [n_bits][2 tables][2 * resv_slots]
 	uint32_t resv_slots;              // power of two
 	uint32_t* claim;                  // [n_bits][2][2^claim_log2 / 32] claim bitmaps (position, wanted value)
 	uint32_t claim_log2;              // bits per bitmap (upper bound; a round uses a prefix sized to its items)
 	int claim_first;                  // 1: phase 0 claims blindly, phase 1 reads and commits back to back (HBM-resident arrays)
+	int merged;                       // 1: contested items are resolved by merged reserve/commit passes (one barrier per iteration)
 	int stream_cells;                 // the arrays are far larger than the L2: L2 evict-first policy for 1 = cell loads, 2 = cell reductions, 4 = km_back reductions; 8 = evict-last for km_back reductions
 	uint64_t* rest_kmer;              // survivors of all batches
 	uint32_t* rest_occ;
