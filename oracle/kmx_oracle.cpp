@@ -8,7 +8,7 @@
 //
 // Parity pin: the reference ships no tests or golden vectors, so this
 // restatement is pinned against the UNMODIFIED reference compiled from /root/reference
-// (oracle/_ref/ref_driver, built by oracle/Makefile): tests/test_oracle_vs_reference.py
+// (oracle/_ref/ref_driver, built by oracle/Makefile): tests/test_oracle.py
 // compares header/km.bin/rest.bin and query outputs byte for byte when the binary is
 // present, and tests/golden/ holds digests + KATs generated from it by
 // tests/golden/make_golden.py.
