@@ -1,15 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- the kmcEx model build + kmer_to_occ path on B200, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload rs|small|hc14]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload rs|small|cfg1|hc14|wgs350|na12878] [--parallelism replicas|array-owner] [--query-sweep]
 
 A step = one model build (KModel::init: counting pass, Bloom inserts, greedy coupled-array
 insert, rest table) from a synthetic KMC database of the named shape; `value` is k-mers
 encoded per second with the database already resident in HBM, `e2e` the same build through
 kmx_init_from_kmc (file -> pinned host -> HBM -> build, host buffers, copies inside the timed
 region).  The retrieval half of the metric (kmer_to_occ queries/s) is measured in the same
-run and reported under "query".  N > 1: see DESIGN.md "Multi-GPU" -- every rank builds from
-its own share of the work and the query batch is sharded over the ranks (weak scaling).
+run and reported under "query" (`--query-sweep`: BASELINE.json configs[4], 10^9 lookups in batches of
+10^5 .. 10^8).  N > 1: see DESIGN.md "Multi-GPU" -- by default every rank builds whole models from
+its own database and the query batch is sharded over the ranks (weak scaling); `--parallelism
+array-owner` has all ranks build ONE model together (strong scaling).  The default workload is
+BASELINE.json configs[1] (RS shape); `na12878` is configs[3], generated bin group by bin group on the GPU.
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from
 /root/reference by oracle/Makefile) on the host cores of this box on the same database.
