@@ -2,26 +2,31 @@
 """bench.py -- the kmcEx model build + kmer_to_occ path on B200, one JSON line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                    [--workload rs|small|cfg1|hc14|wgs350|na12878] [--parallelism replicas|array-owner] [--query-sweep]
+                    [--workload hc14|rs|small|cfg1|wgs350|na12878] [--parallelism team|replicas] [--query-sweep]
 
-A step = one model build (KModel::init: counting pass, Bloom inserts, greedy coupled-array
-insert, rest table) from a synthetic KMC database of the named shape; `value` is k-mers
-encoded per second with the database already resident in HBM, `e2e` the same build through
-kmx_init_from_kmc (file -> pinned host -> HBM -> build, host buffers, copies inside the timed
-region).  The retrieval half of the metric (kmer_to_occ queries/s) is measured in the same
-run and reported under "query" (`--query-sweep`: BASELINE.json configs[4], 10^9 lookups in batches of
-10^5 .. 10^8).  N > 1: see DESIGN.md "Multi-GPU" -- by default every rank builds whole models from
-its own database and the query batch is sharded over the ranks (weak scaling); `--parallelism
-array-owner` has all ranks build ONE model together (strong scaling).  The default workload is
-BASELINE.json configs[1] (RS shape); `na12878` is configs[3], generated bin group by bin group on the GPU.
+A step = one model build (KModel::init: counting pass, Bloom inserts, greedy coupled-array insert, rest table) from a
+synthetic KMC database of the named shape.  `value` is k-mers encoded per second with the database already resident
+in HBM, `e2e` the same build through the file-based entry point (file -> pinned host -> HBM -> build; host buffers,
+copies inside the timed region).  The retrieval half of the metric (kmer_to_occ queries/s) is measured in the same
+run and reported under "query" (`--query-sweep`: BASELINE.json configs[4]).
 
-`--impl reference` times the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from
-/root/reference by oracle/Makefile) on the host cores of this box on the same database.
+Default workload: BASELINE.json configs[2] (HC14 shape, the config named for 1/2/4/8 GPUs).  N > 1: ALL ranks build
+ONE model together (kmcex_b200.distributed.build_team: record range, Bloom inserts and rest sort sharded over the
+ranks, coupled arrays split by ownership, exchanges through NVLink peer memory) -- strong scaling.  At N = 1 the RS
+shape (configs[1], L2-resident) is measured too and reported under "extra".
+
+Parity gate: after the timed regions the model is saved and the md5 of header / km.bin / rest.bin and of the answers
+to the first 2^22 queries are compared with the UNMODIFIED reference's (tests/golden/bench_shapes.json, pinned on the
+same seeded database, and/or the model oracle/_ref/ref_driver built on this box); the line carries "parity" and
+the process exits non-zero on a mismatch, at every N.
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/ref_driver, compiled from /root/reference by
+oracle/Makefile) on the host cores of this box on the same database (a capped number of builds, stated in
+cpu_baseline.sample).
 """
 from __future__ import annotations
 
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -33,67 +38,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from kmcex_b200.workloads import CACHE, MODEL_FILES, SWEEP_POOL, WORKLOADS, ensure_db, golden_for, md5_file, model_digests, occ_digest  # noqa: E402,F401
 
-WORKLOADS = {
-    # name: (synth shape, ci, lut_prefix_length, bins, BASELINE.json config it stands for)
-    "small": ("small", 2, 7, 4, "test-sized (200 kbp, 40x)"),
-    "cfg1": ("cfg1", 1, 3, 8, "configs[0]: 1M-read 100bp, ci1"),
-    "rs": ("rs", 2, 7, 16, "configs[1]: GAGE-RS-shaped synthetic (4.6 Mbp, 100x, 101bp) k31 nh7 nb5 ci2"),
-    "hc14": ("hc14", 1, 7, 64, "configs[2]: GAGE-HC14-shaped synthetic (88 Mbp, 40x) k31 nh7 nb5 ci1"),
-    "wgs350": ("wgs350", 2, 7, 128, "scale check towards configs[3]: 350 Mbp synthetic genome, 30x, k31 nh7 nb5 ci2"),
-    "na12878": ("na12878", 2, 7, 512, "configs[3]: NA12878-shaped synthetic (3.1 Gbp, 30x, 101bp) k31 nh7 nb5 ci2"),
-}
-# shapes generated bin group by bin group on the GPU (kmcex_b200.synth.make_db_streamed): (genome_bp, coverage, read_len)
-STREAMED = {"na12878": (3_100_000_000, 30, 101)}
-SWEEP_POOL = 100_000_000          # distinct queries behind the configs[4] sweep
-CACHE = os.environ.get("KMX_BENCH_CACHE", "/tmp/kmx_bench")
+PARITY_QUERIES = 1 << 22          # answers compared with the reference's (tests/golden/make_bench_golden.py: OCC_N)
+REF_BUDGET_S = 150.0              # the reference arm stops starting new builds after this many seconds of CPU builds
 
 
 def rank_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def ensure_db(workload: str, seed: int = 1):
-    """generate (or reuse) the synthetic KMC database + a query set for it; returns paths and sizes"""
-    from kmcex_b200 import synth
-    shape, ci, lut, bins, _ = WORKLOADS[workload]
-    d = os.path.join(CACHE, f"{workload}_s{seed}")
-    base = os.path.join(d, "db")
-    meta_path = os.path.join(d, "meta.json")
-    if os.path.exists(meta_path):
-        with open(meta_path) as f:
-            return json.load(f)
-    os.makedirs(d, exist_ok=True)
-    if workload in STREAMED:
-        import shutil
-        import torch
-        g, cov, rl = STREAMED[workload]
-        need = int(g * 1.4 * 8) + (8 << 30)
-        if shutil.disk_usage(d).free < need:
-            raise SystemExit(f"{workload}: {need >> 30} GiB of scratch space needed under {CACHE} (set KMX_BENCH_CACHE)")
-        r = synth.make_db_streamed(base, g, cov, rl, seed=seed, ci=ci, lut_prefix_length=lut, n_bins=bins, n_present=SWEEP_POOL // 2)
-        torch.cuda.empty_cache()
-        q = synth.mixed_queries(r["present"], SWEEP_POOL, seed=seed + 100)
-        q.tofile(os.path.join(d, "queries.u64"))
-        meta = {"db": base, "queries": os.path.join(d, "queries.u64"), "n_kmers": int(r["n_kmers"]), "n_queries": int(q.size), "ci": ci,
-                "suffix_bytes": os.path.getsize(base + ".kmc_suf"), "prefix_bytes": os.path.getsize(base + ".kmc_pre")}
-        tmp = meta_path + f".{os.getpid()}"
-        with open(tmp, "w") as f:
-            json.dump(meta, f)
-        os.replace(tmp, meta_path)
-        return meta
-    sp = synth.make_db(base, shape, seed=seed, ci=ci, lut_prefix_length=lut, n_bins=bins)
-    # query set: 50 % present (random strand) / 50 % absent + neighbours, BASELINE.json configs[4] mix
-    n_q = 1 << 24
-    q = synth.neighbour_rich_queries(sp, n_q // 2, n_q // 2 - (n_q // 2) // 4, seed=seed + 100)
-    q.tofile(os.path.join(d, "queries.u64"))
-    meta = {"db": base, "queries": os.path.join(d, "queries.u64"), "n_kmers": int(sp.kmers.size), "n_queries": int(q.size), "ci": ci,
-            "suffix_bytes": os.path.getsize(base + ".kmc_suf"), "prefix_bytes": os.path.getsize(base + ".kmc_pre")}
-    tmp = meta_path + f".{os.getpid()}"
-    with open(tmp, "w") as f:
-        json.dump(meta, f)
-    os.replace(tmp, meta_path)
-    return meta
+def config_of(workload: str, meta: dict) -> dict:
+    """the `config` object: identical in both arms"""
+    return {"workload": WORKLOADS[workload][4], "n_kmers": meta["n_kmers"], "k": 31, "n_hash": 7, "n_bits": 5, "ci": meta["ci"], "cs": 1023}
 
 
 class ClockSampler:
@@ -135,24 +92,34 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch, from profiles/ (ncu --set full)
-NCU_TRAFFIC = {"rs": 9.86e8}         # profiles/r1_o_ncu_full_bench_rs.txt
-
-
-def random_sector_peaks() -> dict:
-    """GB/s of 32-byte sectors the chip sustains for random access (tools/random_sector_peaks.py, committed under profiles/):
-    mean of the load and atomic figures, for an L2-resident (64 MiB) and an HBM-resident (4 GiB) footprint"""
-    p = os.path.join(ROOT, "profiles", "r1_random_sector_peaks.json")
-    if not os.path.exists(p):
+def random_sector_rates() -> dict:
+    """G sectors/s the chip sustains for random 8-byte loads and random 64-bit reductions (tools/random_sector_peaks.py,
+    committed under profiles/), for an L2-resident (64 MiB) and an HBM-resident (4 GiB) footprint"""
+    for name in ("r2_random_sector_peaks.json", "r1_random_sector_peaks.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            break
+    else:
         return {}
     with open(p) as f:
         res = json.load(f)["results"]
-    out = {}
-    for name, mb in (("l2", 64), ("hbm", 4096)):
-        v = [r["gb_per_s_32B"] for r in res if r["footprint_mb"] == mb]
-        if v:
-            out[name] = sum(v) / len(v)
+    out = {"source": "profiles/" + name}
+    for res_name, mb in (("l2", 64), ("hbm", 4096)):
+        ld = [r["g_accesses_per_s"] for r in res if r["footprint_mb"] == mb and r["kind"] == "load8"]
+        rd = [r["g_accesses_per_s"] for r in res if r["footprint_mb"] == mb and r["kind"] == "red_or64"]
+        if ld and rd:
+            out[res_name] = {"load": ld[0], "red": rd[0]}
     return out
+
+
+def measured_traffic(workload: str, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of insert_kernel per launch from this round's `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json, written by tools/ncu_summarize.py); None when there is no capture of this workload"""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(workload, {}).get("dram_bytes_per_launch")
 
 
 def measured_peaks():
@@ -164,44 +131,80 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm: the unmodified reference on the host cores
+# the unmodified reference on the host cores: reference arm, cpu_baseline leg, parity model
 # ---------------------------------------------------------------------------------------------
+def ref_driver_path() -> str:
+    return os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+
+def ref_model_dir(workload: str, seed: int = 1) -> str:
+    return os.path.join(CACHE, f"{workload}_s{seed}", "ref_model")
+
+
+def reference_build(workload: str, meta: dict) -> float:
+    """one KModel::init + save of the unmodified reference; returns init seconds; stamps the model with the database digest"""
+    out_dir = ref_model_dir(workload)
+    os.makedirs(out_dir, exist_ok=True)
+    stamp = os.path.join(out_dir, "stamp.json")
+    if os.path.exists(stamp):
+        os.remove(stamp)
+    cores = os.cpu_count() or 1
+    r = subprocess.run([ref_driver_path(), "build", meta["db"], out_dir, str(meta["ci"]), "1023", "7", "5"], capture_output=True, text=True,
+                       env=dict(os.environ, OMP_NUM_THREADS=str(cores)), check=True)
+    t = json.loads(r.stdout.strip().splitlines()[-1])
+    with open(stamp, "w") as f:
+        json.dump({"db_md5": meta["db_md5"], "model_md5": model_digests(out_dir), "init_s": t["init_s"]}, f)
+    return float(t["init_s"])
+
+
+def reference_stamp(workload: str, meta: dict):
+    stamp = os.path.join(ref_model_dir(workload), "stamp.json")
+    if not os.path.exists(stamp):
+        return None
+    with open(stamp) as f:
+        s = json.load(f)
+    return s if s.get("db_md5") == meta["db_md5"] else None
+
+
 def run_reference(args) -> None:
     rank, _, world = rank_env()
     if rank != 0:
         return
-    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    if not os.path.exists(ref):
+    if not os.path.exists(ref_driver_path()):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (needs /root/reference at build time)"}))
         return
     meta = ensure_db(args.workload)
     cores = os.cpu_count() or 1
-    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
-    out_dir = os.path.join(CACHE, f"{args.workload}_ref_model")
-    os.makedirs(out_dir, exist_ok=True)
-    times = []
-    for step in range(args.warmup + args.steps):
-        r = subprocess.run([ref, "build", meta["db"], out_dir, str(meta["ci"]), "1023", "7", "5"], capture_output=True, text=True, env=env, check=True)
-        t = json.loads(r.stdout.strip().splitlines()[-1])
-        if step >= args.warmup:
-            times.append(t["init_s"])
+    # a capped number of whole-database builds: warm-up builds only while they are cheap, timed builds until the budget is spent
+    times, spent, warm = [], 0.0, 0
+    while len(times) < max(1, args.steps):
+        t = reference_build(args.workload, meta)
+        spent += t
+        if warm < args.warmup and t < 5.0 and spent < REF_BUDGET_S / 3:
+            warm += 1
+            continue
+        times.append(t)
+        if spent + t > REF_BUDGET_S:
+            break
     ms = 1e3 * sum(times) / len(times)
     value = meta["n_kmers"] / (ms / 1e3)
     # retrieval: bounded sample of the query set, every host core (kmer_to_occ(vector, t_num), kmodel.hpp:90)
     n_q = min(meta["n_queries"], 1 << 21)
     qs = os.path.join(CACHE, f"{args.workload}_ref_q.u64")
     np.fromfile(meta["queries"], dtype=np.uint64, count=n_q).tofile(qs)
-    r = subprocess.run([ref, "query", out_dir, qs, "31", qs + ".occ", str(cores)], capture_output=True, text=True, env=env, check=True)
+    r = subprocess.run([ref_driver_path(), "query", ref_model_dir(args.workload), qs, "31", qs + ".occ", str(cores)], capture_output=True, text=True,
+                       env=dict(os.environ, OMP_NUM_THREADS=str(cores)), check=True)
     tq = json.loads(r.stdout.strip().splitlines()[-1])
     qps = n_q / tq["query_s"]
     line = {
-        "impl": "reference", "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": meta["n_kmers"], "k": 31, "n_hash": 7, "n_bits": 5,
-                                        "ci": meta["ci"], "cs": 1023},
+        "impl": "reference", "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": args.gpus, "steps": len(times),
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": config_of(args.workload, meta),
         "e2e": {"value": value, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_baseline": {"value": value, "unit": "k-mers/s", "cores": cores, "kind": "reference",
-                         "sample": f"whole database ({meta['n_kmers']} k-mers), KModel::init only; build uses the reference's hard-coded 4/n_bits threads"},
+                         "sample": f"whole database ({meta['n_kmers']} k-mers), KModel::init only, {len(times)} timed build(s) after {warm} warm-up "
+                                   f"(capped at {REF_BUDGET_S:.0f} s of CPU builds; requested steps={args.steps} warmup={args.warmup}); the build "
+                                   "uses the reference's hard-coded 4/n_bits threads"},
         "query": {"value": qps, "unit": "queries/s", "threads": cores, "sample": f"{n_q} queries of the bench query set"},
         "gpu_launches": 0,
     }
@@ -211,172 +214,193 @@ def run_reference(args) -> None:
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def main() -> None:
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
-    ap.add_argument("--workload", default="rs", choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--query-sweep", action="store_true",
-                    help="BASELINE.json configs[4]: 1e9 kmer_to_occ lookups against the built model in batches of 1e5 .. 1e8 "
-                         "(device-resident and host->host), reported under \"query_sweep\"")
-    ap.add_argument("--parallelism", default="replicas", choices=["replicas", "array-owner"],
-                    help="N > 1 build: independent whole builds per rank (weak scaling) or ONE build with the coupled arrays owned by "
-                         "different GPUs (kmcex_b200.distributed.build_array_owner, strong scaling)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import kmcex_b200 as kx
+        from kmcex_b200 import distributed as kd
+        self.torch, self.dist, self.kx, self.kd, self.args = torch, dist, kx, kd, args
+        self.rank, self.local_rank, self.world = rank_env()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: kmcex_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        kx._lib.check(kx.lib().kmx_set_device(self.local_rank))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)     # > 126 MB L2
+        self.team = self.world > 1 and args.parallelism == "team"
+        self.builds_per_step = 1 if (self.team or self.world == 1) else self.world
 
-    import torch
-    import torch.distributed as dist
-    import kmcex_b200 as kx
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    rank, local_rank, world = rank_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: kmcex_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    kx._lib.check(kx.lib().kmx_set_device(local_rank))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    if rank == 0:
-        meta = ensure_db(args.workload)
-    if world > 1:
-        dist.barrier()
-    meta = ensure_db(args.workload)
-    n_kmers = meta["n_kmers"]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---------------- build, database resident in HBM ----------------
-    from kmcex_b200 import distributed as kd
-    owner_mode = world > 1 and args.parallelism == "array-owner"
-    builds_per_step = 1 if owner_mode else world          # array-owner: all ranks build ONE model together
-    db = kx.KmcDatabase(meta["db"]).upload()
-    infos, wall = [], []
-    sampler = ClockSampler(local_rank)
-    for step in range(args.warmup + args.steps):
-        if step == args.warmup:
-            sampler.start()
-        flush.fill_(step & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        m = kx.get_model(meta["ci"], 1023, 7, 5)
-        if owner_mode:
-            kd.build_array_owner(m, db)
+    def sum_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def meta_for(self, workload: str) -> dict:
+        if self.rank == 0:
+            ensure_db(workload)
+        if self.world > 1:
+            self.dist.barrier()
+        return ensure_db(workload)
+
+    def new_model(self, meta):
+        return self.kx.get_model(meta["ci"], 1023, 7, 5)
+
+    def build(self, m, db) -> None:
+        """db: an opened KmcDatabase (resident or not) or a path"""
+        if self.team:
+            self.kd.build_team(m, db)
         else:
             m.init(db)
-        m.sync()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if step >= args.warmup:
-            wall.append(dt)
-            infos.append(m.info)
-        if step < args.warmup + args.steps - 1:
-            m.close()
-    clocks = sampler.stop()
-    t_build = max_over_ranks(sum(wall))
-    ms_per_step = 1e3 * t_build / args.steps
-    value = builds_per_step * n_kmers * args.steps / t_build
-    info = infos[-1]
-    dev_ms = float(np.mean([i["ms_total_device"] for i in infos]))
-    ins_ms = float(np.mean([i["ms_insert"] for i in infos]))
-    # our kernels per build: count, tile scan, encode, one insert launch per 64 batches, rest first/index/fine/quirk (the CUB sort launches are not counted)
-    launches_per_step = 3 + (info["batches"] + 63) // 64 + 4
 
-    # ---------------- build, end to end from the files (host buffers) ----------------
-    e2e_wall = []
-    for step in range(2 + args.steps):
-        flush.fill_(step & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        m2 = kx.get_model(meta["ci"], 1023, 7, 5)
-        if owner_mode:
-            db2 = kx.KmcDatabase(meta["db"])
-            kd.build_array_owner(m2, db2)
-            db2.close()
+    # ---- build legs ------------------------------------------------------------------------
+    def build_legs(self, workload: str, meta: dict, steps: int, warmup: int, sample_clocks: bool):
+        kx, torch = self.kx, self.torch
+        n_kmers = meta["n_kmers"]
+        db = kx.KmcDatabase(meta["db"])
+        if self.team:
+            db.upload_share(self.rank, self.world)
         else:
-            m2.init(meta["db"])
-        m2.sync()
-        dt = time.perf_counter() - t0
-        if step >= 2:
-            e2e_wall.append(dt)
-        m2.close()
-    t_e2e = max_over_ranks(sum(e2e_wall))
-    e2e_value = builds_per_step * n_kmers * args.steps / t_e2e
+            db.upload()
+        infos, wall, m = [], [], None
+        sampler = ClockSampler(self.local_rank) if sample_clocks else None
+        launches0 = 0
+        for step in range(warmup + steps):
+            if step == warmup:
+                if sampler:
+                    sampler.start()
+                launches0 = kx.lib().kmx_launch_count()
+            self.flush.fill_(step & 0xFF)
+            self.barrier()
+            t0 = time.perf_counter()
+            m = self.new_model(meta)
+            self.build(m, db)
+            m.sync()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if step >= warmup:
+                wall.append(dt)
+                infos.append(m.info)
+            if step < warmup + steps - 1:
+                m.close()
+        launches = kx.lib().kmx_launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        db.close()
+        t_build = self.max_over_ranks(sum(wall))
+        res = {
+            "n_kmers": n_kmers, "ms_per_step": 1e3 * t_build / steps, "value": self.builds_per_step * n_kmers * steps / t_build,
+            "wall_ms_steps": [round(1e3 * w, 3) for w in wall], "info": infos[-1], "infos": infos, "clocks": clocks,
+            "gpu_launches": int(self.sum_over_ranks(launches)),
+        }
+        # end to end from the files (host buffers): open, read this rank's share, copy, build
+        e2e_wall = []
+        for step in range(2 + steps):
+            self.flush.fill_(step & 0xFF)
+            self.barrier()
+            t0 = time.perf_counter()
+            m2 = self.new_model(meta)
+            if self.team:
+                db2 = kx.KmcDatabase(meta["db"])
+                self.build(m2, db2)
+                db2.close()
+            else:
+                m2.init(meta["db"])
+            m2.sync()
+            dt = time.perf_counter() - t0
+            if step >= 2:
+                e2e_wall.append(dt)
+            m2.close()
+        t_e2e = self.max_over_ranks(sum(e2e_wall))
+        h2d = meta["suffix_bytes"] // (self.world if self.team else 1) + meta["prefix_bytes"]
+        res["e2e"] = {"value": self.builds_per_step * n_kmers * steps / t_e2e, "unit": "k-mers/s",
+                      "h2d_bytes_per_step": int(self.sum_over_ranks(h2d)), "d2h_bytes_per_step": 512 * self.world,
+                      "ms_per_step": 1e3 * t_e2e / steps, "wall_ms_steps": [round(1e3 * w, 3) for w in e2e_wall]}
+        return m, res
 
-    # ---------------- retrieval ----------------
-    q_all = np.fromfile(meta["queries"], dtype=np.uint64)
-    per = min(q_all.size // world, 1 << 24)
-    q_host = torch.from_numpy(q_all[rank * per:(rank + 1) * per].astype(np.int64)).pin_memory()
-    q_dev = q_host.to(dev)
-    out_dev = torch.empty(per, dtype=torch.int32, device=dev)
-    out_host = torch.empty(per, dtype=torch.int32).pin_memory()
-    stream = torch.cuda.Stream(device=dev)                    # a real (non-NULL) stream: the kernel and the events share it
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    q_ms = []
-    for step in range(args.warmup + args.steps):
-        flush.fill_(step & 0xFF)
-        barrier()
-        stream.wait_stream(torch.cuda.current_stream())
-        ev[0].record(stream)
-        m.query_device(q_dev.data_ptr(), per, out_dev.data_ptr(), stream.cuda_stream)
-        ev[1].record(stream)
-        torch.cuda.synchronize()
-        if step >= args.warmup:
-            q_ms.append(ev[0].elapsed_time(ev[1]))
-    t_q = max_over_ranks(sum(q_ms) / 1e3)
-    qps = world * per * args.steps / t_q
-    q_e2e = []
-    for step in range(2 + args.steps):
-        flush.fill_(step & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        kx._lib.check(kx.lib().kmx_query_packed(m._h, q_host.data_ptr(), per, out_host.data_ptr()))
-        dt = time.perf_counter() - t0
-        if step >= 2:
-            q_e2e.append(dt)
-    t_qe = max_over_ranks(sum(q_e2e))
-    qps_e2e = world * per * args.steps / t_qe
-    assert bool((out_host.to(dev) == out_dev).all())
-    # the reference-facing form of the call: ASCII strings (kmer_to_occ(vector<string>)), flattened at stride k
-    from kmcex_b200 import synth as _synth
-    n_a = min(per, 1 << 22)
-    a_host = torch.from_numpy(_synth.to_ascii(q_all[rank * per: rank * per + n_a], 31)).pin_memory()
-    a_out = torch.empty(n_a, dtype=torch.int32).pin_memory()
-    q_asc = []
-    for step in range(2 + args.steps):
-        flush.fill_(step & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        kx._lib.check(kx.lib().kmx_query_ascii(m._h, a_host.data_ptr(), 31, n_a, a_out.data_ptr()))
-        dt = time.perf_counter() - t0
-        if step >= 2:
-            q_asc.append(dt)
-    t_qa = max_over_ranks(sum(q_asc))
-    qps_ascii = world * n_a * args.steps / t_qa
-    assert bool((a_out == out_host[:n_a]).all())
+    # ---- retrieval -------------------------------------------------------------------------
+    def query_legs(self, m, meta: dict, steps: int, warmup: int) -> dict:
+        kx, torch = self.kx, self.torch
+        rank, world, dev = self.rank, self.world, self.dev
+        q_all = np.fromfile(meta["queries"], dtype=np.uint64)
+        per = min(q_all.size // world, 1 << 24)
+        q_host = torch.from_numpy(q_all[rank * per:(rank + 1) * per].astype(np.int64)).pin_memory()
+        q_dev = q_host.to(dev)
+        out_dev = torch.empty(per, dtype=torch.int32, device=dev)
+        out_host = torch.empty(per, dtype=torch.int32).pin_memory()
+        stream = torch.cuda.Stream(device=dev)                    # a real (non-NULL) stream: the kernel and the events share it
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        q_ms = []
+        for step in range(warmup + steps):
+            self.flush.fill_(step & 0xFF)
+            self.barrier()
+            stream.wait_stream(torch.cuda.current_stream())
+            ev[0].record(stream)
+            m.query_device(q_dev.data_ptr(), per, out_dev.data_ptr(), stream.cuda_stream)
+            ev[1].record(stream)
+            torch.cuda.synchronize()
+            if step >= warmup:
+                q_ms.append(ev[0].elapsed_time(ev[1]))
+        t_q = self.max_over_ranks(sum(q_ms) / 1e3)
+        qps = world * per * steps / t_q
+        q_e2e = []
+        for step in range(2 + steps):
+            self.flush.fill_(step & 0xFF)
+            self.barrier()
+            t0 = time.perf_counter()
+            kx._lib.check(kx.lib().kmx_query_packed(m._h, q_host.data_ptr(), per, out_host.data_ptr()))
+            dt = time.perf_counter() - t0
+            if step >= 2:
+                q_e2e.append(dt)
+        t_qe = self.max_over_ranks(sum(q_e2e))
+        qps_e2e = world * per * steps / t_qe
+        assert bool((out_host.to(dev) == out_dev).all()), "host-pointer and device-pointer queries disagree"
+        # the reference-facing form of the call: ASCII strings (kmer_to_occ(vector<string>)), flattened at stride k
+        from kmcex_b200 import synth as _synth
+        n_a = min(per, 1 << 22)
+        a_host = torch.from_numpy(_synth.to_ascii(q_all[rank * per: rank * per + n_a], 31)).pin_memory()
+        a_out = torch.empty(n_a, dtype=torch.int32).pin_memory()
+        q_asc = []
+        for step in range(2 + steps):
+            self.flush.fill_(step & 0xFF)
+            self.barrier()
+            t0 = time.perf_counter()
+            kx._lib.check(kx.lib().kmx_query_ascii(m._h, a_host.data_ptr(), 31, n_a, a_out.data_ptr()))
+            dt = time.perf_counter() - t0
+            if step >= 2:
+                q_asc.append(dt)
+        t_qa = self.max_over_ranks(sum(q_asc))
+        qps_ascii = world * n_a * steps / t_qa
+        assert bool((a_out == out_host[:n_a]).all()), "ASCII and packed queries disagree"
+        res = {"value": qps, "unit": "queries/s", "batch": per, "ms_per_batch": 1e3 * t_q / steps,
+               "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": per * 8 * world, "d2h_bytes_per_step": per * 4 * world},
+               "e2e_ascii": {"value": qps_ascii, "unit": "queries/s", "batch": n_a, "h2d_bytes_per_step": n_a * 31 * world, "d2h_bytes_per_step": n_a * 4 * world,
+                             "note": "kmx_query_ascii: 31-character strings at stride 31, encoded to 2 bits on the device"}}
+        if self.args.query_sweep:
+            res["sweep"] = self.query_sweep(m, q_all, stream, ev)
+        return res
 
-    # ---------------- configs[4]: 1e9 lookups in batches of 1e5 .. 1e8 ----------------
-    sweep = None
-    if args.query_sweep:
+    def query_sweep(self, m, q_all, stream, ev):
+        """configs[4]: 1e9 lookups in batches of 1e5 .. 1e8"""
+        kx, torch = self.kx, self.torch
+        rank, world, dev = self.rank, self.world, self.dev
         pool_n = q_all.size // world
         lookups = 1_000_000_000 // world                     # per rank; the batch is sharded over the ranks
         pool_host = torch.from_numpy(q_all[rank * pool_n:(rank + 1) * pool_n].astype(np.int64)).pin_memory()
@@ -391,7 +415,7 @@ def main() -> None:
             n_b = max(1, lookups // B)
             span = pool_n - B + 1
             offs = [(i * B) % span for i in range(n_b)]
-            barrier()
+            self.barrier()
             stream.wait_stream(torch.cuda.current_stream())
             for o in offs[:2]:                               # warm-up
                 m.query_device(pool_dev.data_ptr() + 8 * o, B, s_out_dev.data_ptr(), stream.cuda_stream)
@@ -400,79 +424,178 @@ def main() -> None:
                 m.query_device(pool_dev.data_ptr() + 8 * o, B, s_out_dev.data_ptr(), stream.cuda_stream)
             ev[1].record(stream)
             torch.cuda.synchronize()
-            t_dev = max_over_ranks(ev[0].elapsed_time(ev[1]) / 1e3)
+            t_dev = self.max_over_ranks(ev[0].elapsed_time(ev[1]) / 1e3)
             n_e = min(n_b, 2000)                             # host->host: bounded number of calls for the small batches
-            barrier()
+            self.barrier()
             t0 = time.perf_counter()
             for o in offs[:n_e]:
                 kx._lib.check(kx.lib().kmx_query_packed(m._h, pool_host.data_ptr() + 8 * o, B, s_out_host.data_ptr()))
-            t_host = max_over_ranks(time.perf_counter() - t0)
+            t_host = self.max_over_ranks(time.perf_counter() - t0)
             sweep.append({"batch": B, "batches": n_b, "lookups": n_b * B * world, "device_qps": world * n_b * B / t_dev,
                           "host_batches": n_e, "host_qps": world * n_e * B / t_host})
-        del pool_dev, s_out_dev
+        return {"note": "BASELINE.json configs[4]: 50 % present / 37.5 % absent / 12.5 % neighbours, pool of "
+                        f"{q_all.size} distinct queries walked cyclically", "unit": "queries/s", "results": sweep}
 
-    # ---------------- roofline of the dominant kernel ----------------
-    peak, peak_src = measured_peaks()
-    rs_peaks = random_sector_peaks()
-    # insert_kernel (largest share of the step).  Algorithmic traffic, one 32-byte sector per touch
-    # (DESIGN.md section 3): each attempt reads n_hash cells; each accept issues n_hash cell atomics
-    # + (n_hash-2) km_back atomics.  Reservation / claim traffic is implementation overhead, not counted.
-    ins_sectors = 7 * info["insert_attempts"] + (7 + 5) * info["insert_accepted"]
-    ins_gbs = 32.0 * ins_sectors / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
-    model_bytes = info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"]
-    resident = "l2" if model_bytes < (100 << 20) else "hbm"
-    rs_peak = rs_peaks.get(resident)
-    roofline = {"kernel": "insert_kernel", "bound": "hbm", "achieved": ins_gbs, "peak": peak, "unit": "GB/s", "frac": ins_gbs / peak,
-                "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src, "ms_per_launch": ins_ms,
-                "sectors_per_launch": ins_sectors, "residency": resident,
-                "random_sector_peak_gbs": rs_peak, "frac_of_random_sector_peak": (ins_gbs / rs_peak) if rs_peak else None,
-                "note": "random 32-byte sectors: the streaming-copy peak is not reachable by construction; the measured random-sector "
-                        "peak (profiles/r1_random_sector_peaks.json: loads / atomics averaged, L2- or HBM-resident footprint) is the honest bound"}
-    q_sectors_est = None
+    # ---- parity gate -----------------------------------------------------------------------
+    def parity(self, m, workload: str, meta: dict) -> dict:
+        """md5 of the saved model and of the answers to the first PARITY_QUERIES queries, on EVERY rank, against the
+        reference's digests (committed golden of the same seeded database and/or the reference model built on this box)"""
+        rank = self.rank
+        out_dir = os.path.join(CACHE, f"{workload}_s1", f"kmx_model_rank{rank}")
+        os.makedirs(out_dir, exist_ok=True)
+        m.save(out_dir)
+        mine = model_digests(out_dir)
+        q = np.fromfile(meta["queries"], dtype=np.uint64, count=PARITY_QUERIES)
+        occ_md5 = occ_digest(m.kmer_to_occ(q))
+        gold = golden_for(workload)
+        if gold is not None and gold["db_md5"] != meta["db_md5"]:
+            gold = None                                      # another database than the pinned one (generator changed?)
+        stamp = reference_stamp(workload, meta)
+        res = {"checked": False, "vs": [], "db_md5_equals_golden": gold is not None}
+        expect_model, expect_occ = None, None
+        if gold is not None:
+            expect_model, expect_occ = gold["model_md5"], (gold["occ_md5"] if gold["occ_n"] == q.size else None)
+            res["vs"].append("tests/golden/bench_shapes.json (oracle/_ref on the same seeded database)")
+        if stamp is not None:
+            if expect_model is not None and stamp["model_md5"] != expect_model:
+                res["reference_on_this_box_equals_golden"] = False
+            expect_model = expect_model or stamp["model_md5"]
+            res["vs"].append("oracle/_ref model built on this box")
+        if expect_model is not None:
+            res["checked"] = True
+            for f in MODEL_FILES:
+                res[f] = mine[f] == expect_model[f]
+            if expect_occ is None and stamp is not None and rank == 0 and os.path.exists(ref_driver_path()):
+                qs = os.path.join(CACHE, f"{workload}_s1", "parity_q.u64")
+                q.tofile(qs)
+                subprocess.run([ref_driver_path(), "query", ref_model_dir(workload), qs, "31", qs + ".occ", str(os.cpu_count() or 1)],
+                               capture_output=True, text=True, check=True)
+                expect_occ = occ_digest(np.fromfile(qs + ".occ", dtype=np.int32))
+            if expect_occ is not None:
+                res["kmer_to_occ"] = occ_md5 == expect_occ
+        else:
+            res["why"] = "no pinned digest for this database and no reference model on this box (run --impl reference first)"
+        ok = all(v for k, v in res.items() if k in MODEL_FILES or k == "kmer_to_occ")
+        all_ok = self.sum_over_ranks(0.0 if ok else 1.0) == 0.0
+        res["all_ranks"] = all_ok
+        res["ranks_checked"] = self.world
+        res["occ_md5"] = occ_md5
+        res["model_md5"] = mine
+        return res
+
+    # ---- roofline --------------------------------------------------------------------------
+    def roofline(self, workload: str, res: dict) -> dict:
+        infos = res["infos"]
+        info = infos[-1]
+        world = self.world
+        ins_ms = self.max_over_ranks(float(np.mean([i["ms_insert"] for i in infos])))
+        n_active = min(world, 5) if self.team else world
+        # insert_kernel (largest share of the step).  Algorithmic traffic, one 32-byte sector per touch (DESIGN.md section 3):
+        # each attempt reads n_hash cells; each accept issues n_hash cell reductions + (n_hash-2) km_back reductions.
+        # Claim / reservation traffic is implementation overhead and not counted.  (team build: attempts / accepted are the
+        # totals over the array owners, the time is the slowest owner's)
+        loads, reds = 7 * info["insert_attempts"], 12 * info["insert_accepted"]
+        if not self.team:
+            loads, reds = loads * world, reds * world            # replicas: every rank does a whole build
+        sectors = loads + reds
+        gbs = 32.0 * sectors / (ins_ms * 1e-3) / 1e9 if ins_ms > 0 else 0.0
+        peak1, peak_src = measured_peaks()
+        peak = peak1 * n_active
+        model_bytes = info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"]
+        resident = "l2" if model_bytes < (100 << 20) else "hbm"
+        rates = random_sector_rates()
+        rs_peak = None
+        if resident in rates and sectors:
+            r = rates[resident]
+            # mix-weighted: the time the measured random-access rates need for this launch's loads and reductions
+            t_min = loads / (r["load"] * 1e9) + reds / (r["red"] * 1e9)
+            rs_peak = 32.0 * sectors / t_min / 1e9 * n_active
+        return {"kernel": "insert_kernel", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                "traffic": measured_traffic(workload, world), "peak_source": peak_src + (f" x {n_active} GPUs running the kernel" if n_active > 1 else ""),
+                "ms_per_launch": ins_ms, "sectors_per_launch": sectors, "load_sectors": loads, "reduction_sectors": reds,
+                "residency": resident, "gpus_running_the_kernel": n_active,
+                "random_sector_peak_gbs": rs_peak, "frac_of_random_sector_peak": (gbs / rs_peak) if rs_peak else None,
+                "random_sector_source": rates.get("source"),
+                "note": "random 32-byte sectors: `peak` is the streaming-copy figure the contract asks for; the bound that applies is the "
+                        "measured random-sector rate at this residency (loads and reductions weighted by this launch's mix)"
+                        + ("; the model is L2-resident, so the bound is the L2's random-sector rate, not HBM" if resident == "l2" else "")}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kmx", choices=["kmx", "reference"])
+    ap.add_argument("--workload", default="hc14", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary RS-shape record at N = 1")
+    ap.add_argument("--query-sweep", action="store_true",
+                    help="BASELINE.json configs[4]: 1e9 kmer_to_occ lookups against the built model in batches of 1e5 .. 1e8 "
+                         "(device-resident and host->host), reported under query.sweep")
+    ap.add_argument("--parallelism", default="team", choices=["team", "replicas"],
+                    help="N > 1 build: ONE model built by all ranks (kmcex_b200.distributed.build_team, strong scaling; default) or "
+                         "independent whole builds per rank (weak scaling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    B = Bench(args)
+    rank, world = B.rank, B.world
+    meta = B.meta_for(args.workload)
+    m, res = B.build_legs(args.workload, meta, args.steps, args.warmup, sample_clocks=True)
+    query = B.query_legs(m, meta, args.steps, args.warmup)
+    info = res["info"]
+
     line = {
-        "metric": "kmers_encoded_per_s", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if owner_mode else "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][4], "n_kmers": n_kmers, "k": 31, "n_hash": 7, "n_bits": 5, "ci": meta["ci"], "cs": 1023,
-                   "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": (args.parallelism if world > 1 else "single")},
-        "device_ms_per_step": dev_ms, "wall_ms_steps": [round(1e3 * w, 3) for w in wall], "e2e_wall_ms_steps": [round(1e3 * w, 3) for w in e2e_wall],
-        "stage_ms": {k: float(np.mean([i[k] for i in infos])) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
-        "e2e": {"value": e2e_value, "unit": "k-mers/s", "h2d_bytes_per_step": meta["suffix_bytes"] + meta["prefix_bytes"], "d2h_bytes_per_step": 256,
-                "ms_per_step": 1e3 * t_e2e / args.steps},
-        "query": {"value": qps, "unit": "queries/s", "batch": per, "ms_per_batch": 1e3 * t_q / args.steps,
-                  "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": per * 8, "d2h_bytes_per_step": per * 4},
-                  "e2e_ascii": {"value": qps_ascii, "unit": "queries/s", "batch": n_a, "h2d_bytes_per_step": n_a * 31, "d2h_bytes_per_step": n_a * 4,
-                                "note": "kmx_query_ascii: 31-character strings at stride 31, encoded to 2 bits on the device"}},
-        "gpu_launches": int(launches_per_step * args.steps),
-        "roofline": roofline,
-        "clocks": clocks,
+        "metric": "kmers_encoded_per_s", "value": res["value"], "unit": "k-mers/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if (B.team or world == 1) else "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": config_of(args.workload, meta),
+        "l2": "flushed between timed iterations (256 MiB fill)", "parallelism": (args.parallelism if world > 1 else "single"),
+        "device_ms_per_step": B.max_over_ranks(float(np.mean([i["ms_total_device"] for i in res["infos"]]))),
+        "wall_ms_steps": res["wall_ms_steps"],
+        "stage_ms": {k: B.max_over_ranks(float(np.mean([i[k] for i in res["infos"]]))) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
+        "e2e": res["e2e"], "query": query, "gpu_launches": res["gpu_launches"],
+        "roofline": B.roofline(args.workload, res), "clocks": res["clocks"],
         "build_stats": {k: info[k] for k in ("insert_attempts", "insert_accepted", "insert_iterations", "batches", "rest_kmers", "km_kmers", "bf_kmers", "insert_phase_cycles")},
-        "model_bytes": model_bytes,
+        "model_bytes": info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"],
     }
-    if sweep is not None:
-        line["query_sweep"] = {"note": "BASELINE.json configs[4]: 50 % present / 37.5 % absent / 12.5 % neighbours, pool of "
-                               f"{q_all.size} distinct queries walked cyclically; the model is far larger than the L2", "unit": "queries/s",
-                               "results": sweep}
 
-    # ---------------- CPU baseline beside it (rank 0, N = 1) ----------------
+    # ---------------- CPU baseline beside it (rank 0, N = 1): also leaves the reference model for the parity gate ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
         cores = os.cpu_count() or 1
-        if os.path.exists(ref):
-            out_dir = os.path.join(CACHE, f"{args.workload}_ref_model")
-            os.makedirs(out_dir, exist_ok=True)
-            r = subprocess.run([ref, "build", meta["db"], out_dir, str(meta["ci"]), "1023", "7", "5"], capture_output=True, text=True,
-                               env=dict(os.environ, OMP_NUM_THREADS=str(cores)))
-            if r.returncode == 0:
-                t = json.loads(r.stdout.strip().splitlines()[-1])
-                line["cpu_baseline"] = {"value": n_kmers / t["init_s"], "unit": "k-mers/s", "cores": cores, "kind": "reference",
-                                        "sample": f"whole database ({n_kmers} k-mers), KModel::init of the unmodified reference, one run"}
-        if "cpu_baseline" not in line:
+        if os.path.exists(ref_driver_path()):
+            t = reference_build(args.workload, meta)
+            line["cpu_baseline"] = {"value": meta["n_kmers"] / t, "unit": "k-mers/s", "cores": cores, "kind": "reference",
+                                    "sample": f"whole database ({meta['n_kmers']} k-mers), KModel::init of the unmodified reference, one run"}
+        else:
             line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+    B.barrier()
+    line["parity"] = B.parity(m, args.workload, meta)
+    m.close()
+
+    # ---------------- secondary record: the RS shape (configs[1], L2-resident), N = 1 only ----------------
+    if world == 1 and not args.no_extra and args.workload != "rs":
+        meta_rs = B.meta_for("rs")
+        m_rs, r_rs = B.build_legs("rs", meta_rs, args.steps, args.warmup, sample_clocks=False)
+        q_rs = B.query_legs(m_rs, meta_rs, args.steps, args.warmup)
+        roof = B.roofline("rs", r_rs)
+        roof["bound"] = "l2"
+        line["extra"] = {"rs": {"config": config_of("rs", meta_rs), "value": r_rs["value"], "unit": "k-mers/s", "ms_per_step": r_rs["ms_per_step"],
+                                "e2e": r_rs["e2e"], "query": q_rs, "roofline": roof,
+                                "stage_ms": {k: float(np.mean([i[k] for i in r_rs["infos"]])) for k in ("ms_count", "ms_encode", "ms_insert", "ms_rest")},
+                                "parity": B.parity(m_rs, "rs", meta_rs)}}
+        m_rs.close()
     if rank == 0:
         print(json.dumps(line))
+    ok = line["parity"]["all_ranks"] and (("extra" not in line) or line["extra"]["rs"]["parity"]["all_ranks"])
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("PARITY MISMATCH: the GPU build differs from the reference's -- see \"parity\" in the line above\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -95,10 +95,13 @@ int kmx_save(kmx_model* m, const char* dir);
 
 /* ---- retrieval: KModel::kmer_to_occ kmodel.hpp:90-116 -------------------------------------
  * n k-mers of length k (the model's k) as ASCII, record i at flat + i*stride (stride >= k);
- * upper-case ACGT is the supported alphabet.  out[i] = occurrence estimate.                  */
+ * out[i] = occurrence estimate.                                                              */
 int kmx_query_ascii(kmx_model* m, const char* flat, size_t stride, size_t n, int32_t* out);
 int kmx_query_packed(kmx_model* m, const uint64_t* kmers, size_t n, int32_t* out);
-/* device-resident variants: pointers are CUDA device pointers on the model's device,
+/* ASCII queries are not validated by the reference (tools.hpp:63-76,160-167): a byte that is not C/G/T encodes as A for
+ * the canonical-form decision and the rest lookup, but when the string's forward orientation is the canonical one the
+ * filters are probed with hashes of its RAW bytes (N, lower case included).  kmx_query_ascii* reproduce exactly that.
+ * device-resident variants: pointers are CUDA device pointers on the model's device,
  * stream is a cudaStream_t (NULL = the model's own stream); asynchronous w.r.t. the host     */
 int kmx_query_packed_device(kmx_model* m, const uint64_t* d_kmers, size_t n, int32_t* d_out, void* stream);
 int kmx_query_ascii_device(kmx_model* m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, void* stream);
@@ -141,36 +144,40 @@ typedef struct kmx_count_info_t {
 } kmx_count_info_t;
 int kmx_count_fastq(const char* const* fastq_paths, int n_files, int k, int ci, int cs, const char* out_base, kmx_count_info_t* info);
 
-/* ---- multi-GPU build: array-owner decomposition (option A) -------------
- * One process per GPU, `world` of them.  Every rank calls prepare: it runs the counting pass, inserts the
- * Bloom-bound records of ITS share of the database (record range rank/world) into its copy of the filters,
- * writes the item stream if it owns a coupled array (rank < n_active), allocates its exchange buffers and
- * returns two 64-byte CUDA IPC handles (survivor exchange slab, filter slab).  The ranks exchange the handles
- * (any out-of-band channel) and call connect with the handles of ranks 0..world-1 concatenated (128 bytes
- * each).  merge(0) ORs the partial Bloom filters over the ranks through peer memory (one kernel: reduce-scatter
- * + all-gather with flag barriers, no NCCL); insert: rank r < n_active owns the coupled arrays a with
- * a % n_active == r, the persistent kernels pass each bucket's survivors to the next owner through peer memory
- * with a flag barrier per round; merge(1) ORs km_back.  buffers() exposes the device pointers the caller's
- * collectives complete (owned arrays are broadcast, survivor lists are concatenated); finish() builds the rest
- * table.  Results are identical to kmx_init_from_db for every world / n_active.                       */
-typedef struct kmx_dist_buffers_t {
-	int32_t n_bits;
-	uint64_t cell_bytes;              /* bytes of one coupled array in the device layout          */
-	void* cells[8];                   /* device pointers, array a valid on its owner after insert */
-	void* km_back;
-	uint64_t km_back_bytes;
-	void* rest_kmer;                  /* this rank's survivors: u64 k-mers ...                    */
-	void* rest_occ;                   /* ... and u32 counts                                       */
-	uint64_t rest_n;
-	uint64_t insert_attempts, insert_accepted;
-} kmx_dist_buffers_t;
-int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, int world, void* ipc_handles_out /* 128 bytes */);
-int kmx_dist_connect(kmx_model* m, const void* handles /* world * 128 bytes */);
-int kmx_dist_merge(kmx_model* m, int which /* 0: Bloom filters, 1: km_back */);
-int kmx_dist_insert(kmx_model* m);
-int kmx_dist_buffers(kmx_model* m, kmx_dist_buffers_t* out);
-int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n,
-                    uint64_t attempts, uint64_t accepted);
+/* ---- multi-GPU build: ONE model built by the GPUs of one node ----------------
+ * KModel::init (kmodel.hpp:57-86) over `world` GPUs; the result is byte-identical to kmx_init_from_kmc on one GPU for every
+ * world size.  Record range, Bloom inserts and the rest-table sort are sharded over all ranks; the coupled arrays are split
+ * by ownership (array a on rank a % min(world, n_bits) -- the reference's own decomposition, kmodel.hpp:561-565); array-bound
+ * k-mers go from the decoding rank straight into the owner's memory, survivors from owner to owner, the finished pieces to
+ * every rank -- all through peer-mapped device memory (NVLink), no NCCL.  Every rank ends with the complete model.
+ *
+ * (a) inside ONE process: kmx_set_devices({d0, d1, ...}) (or KMX_GPUS=N in the environment) before kmx_init_from_kmc -- one
+ *     host thread per GPU, plain peer access.  The model handle then also shards kmx_query_* batches over its replicas.
+ * (b) one process per GPU: every rank runs the kmx_team_steps() steps in lock step; after each step the ranks all-gather
+ *     their kmx_team_blob_bytes()-byte blob (any channel: MPI, a process-group all-gather, a pipe) and pass the `world` blobs, in rank
+ *     order, to the next step.  The blobs carry counts, CUDA IPC handles and return codes; bulk data never touches them.
+ *     A rank runs every step even after a failure (the codes travel in the blobs and fail the next step on all ranks). */
+int kmx_set_devices(const int* ordinals, int n);      /* n >= 2: team of these GPUs for kmx_init_from_kmc; n <= 1: single GPU */
+int kmx_db_upload_share(kmx_db* db, int rank, int world);   /* only this rank's tile range of the records -> device */
+int kmx_team_steps(void);
+int kmx_team_blob_bytes(void);
+int kmx_team_step(kmx_model* m, kmx_db* db, int rank, int world, int step, const void* blobs_in, void* blob_out);
+
+/* host-side pieces of the team build, for tests: where stream item g goes (owner rank, index in the owner's shard), and the
+ * prefix ranges of the sharded rest build (cut[world + 1], cut_off[world + 1]) */
+void kmx_host_route(uint64_t g, int n_active, int n_bits, int32_t* owner, uint64_t* index);
+int kmx_host_prefix_cuts(const uint32_t* hist, int map_size, int world, uint32_t* cut, uint64_t* cut_off);
+
+/* device-side known-answer hook: the hash -> exact modulo -> word / bit addressing chain of the build and query kernels with an
+ * arbitrary array length d (the NA12878 shape has d ~ 1.1e10 > 2^32).  kmers[n] are hashed with seeds[n_seeds] modulo d on
+ * the device and set as tag + value in a cell array and as bits in a Bloom-style filter of d bits; pos_out[n * n_seeds] gets
+ * the positions, counts[0] = positions found set again, counts[1] / counts[2] = tag / filter bits set in the whole arrays
+ * (an address truncated anywhere would make them differ from the number of distinct positions). */
+int kmx_selftest_positions(const uint64_t* kmers, size_t n, int k, uint64_t d, const uint32_t* seeds, int n_seeds, uint64_t* pos_out,
+                           uint64_t counts[3]);
+
+/* kernels launched by this process's libkmx so far (bench.py reports the launches inside its timed region) */
+unsigned long long kmx_launch_count(void);
 
 /* ---- roofline denominators: random 32-byte-sector throughput of the device (diagnostic) ------
  * kind 0: random 8-byte loads, 1: random 32-bit atomic OR, 2: random 64-bit atomic OR; 7 accesses

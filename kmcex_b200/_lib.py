@@ -47,13 +47,6 @@ class KmxCountInfo(C.Structure):
                 ("lut_prefix_length", C.c_uint32), ("counter_size", C.c_uint32)]
 
 
-class KmxDistBuffers(C.Structure):
-    _fields_ = [
-        ("n_bits", C.c_int32), ("cell_bytes", C.c_uint64), ("cells", C.c_void_p * 8), ("km_back", C.c_void_p), ("km_back_bytes", C.c_uint64),
-        ("rest_kmer", C.c_void_p), ("rest_occ", C.c_void_p), ("rest_n", C.c_uint64), ("insert_attempts", C.c_uint64), ("insert_accepted", C.c_uint64),
-    ]
-
-
 # name -> (restype, argtypes); kept in one table so that the CPU test can check it against kmx.h
 SIGNATURES = {
     "kmx_last_error": (C.c_char_p, []),
@@ -87,12 +80,15 @@ SIGNATURES = {
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "kmx_count_fastq": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(KmxCountInfo)]),
-    "kmx_dist_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "kmx_dist_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "kmx_dist_merge": (C.c_int, [C.c_void_p, C.c_int]),
-    "kmx_dist_insert": (C.c_int, [C.c_void_p]),
-    "kmx_dist_buffers": (C.c_int, [C.c_void_p, C.POINTER(KmxDistBuffers)]),
-    "kmx_dist_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "kmx_set_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "kmx_db_upload_share": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "kmx_team_steps": (C.c_int, []),
+    "kmx_team_blob_bytes": (C.c_int, []),
+    "kmx_team_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "kmx_launch_count": (C.c_ulonglong, []),
+    "kmx_selftest_positions": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "kmx_host_route": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    "kmx_host_prefix_cuts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_grid_barrier": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_hot_atomic": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),

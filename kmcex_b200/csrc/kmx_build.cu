@@ -22,7 +22,6 @@
 //   than the bit array (positions alias), which can only delay an acceptance, never change it.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
-#include <cub/device/device_radix_sort.cuh>
 #include "kmx_device.cuh"
 #include "kmx_launch.h"
 #include "kmx_gridbar.cuh"
@@ -119,13 +118,12 @@ __device__ __forceinline__ uint64_t decode_kmer(const DevDb& db, const uint8_t* 
 // pass 1 (kmodel.hpp:423-434).  LIST = true only counts listed records per tile (kmx_db_list).
 template <bool LIST>
 __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevDb db, int ci, int cs, int bf_num, CountOut* out,
-                                                    uint32_t* __restrict__ tile_cnt) {
+                                                    uint32_t* __restrict__ tile_cnt, uint64_t tile_first, uint64_t tile_end) {
 	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
 	__shared__ unsigned long long s_sum[8];
 	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
-	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
 	unsigned long long acc[6] = { 0, 0, 0, 0, 0, 0 };        // thread 0: class0..2, listed, array, bad
-	for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x) {
 		const uint64_t s0 = tile * kTile;
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
 		__syncthreads();
@@ -156,7 +154,7 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevD
 			const unsigned long long m21 = (1ULL << 21) - 1;
 			acc[0] += p0 & m21; acc[1] += (p0 >> 21) & m21; acc[2] += (p0 >> 42) & m21;
 			acc[3] += p1 & m21; acc[4] += (p1 >> 21) & m21; acc[5] += (p1 >> 42) & m21;
-			tile_cnt[tile] = LIST ? (uint32_t)(p1 & m21) : (uint32_t)((p1 >> 21) & m21);
+			tile_cnt[tile - tile_first] = LIST ? (uint32_t)(p1 & m21) : (uint32_t)((p1 >> 21) & m21);
 		}
 	}
 	if (threadIdx.x == 0 && out) {
@@ -209,8 +207,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 // inserted into their filters (kmodel.hpp:473-477,498-506), array-bound ones go to the stream.
 template <bool LIST, int K, int H>
 __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ DevDb db, const __grid_constant__ DevModel m,
-                                                     const uint64_t* __restrict__ tile_off, uint64_t* __restrict__ out_kmer,
-                                                     uint32_t* __restrict__ out_occ, uint64_t bloom_lo, uint64_t bloom_hi,
+                                                     const uint64_t* __restrict__ tile_off, const __grid_constant__ ItemRoute route,
                                                      uint64_t tile_first, uint64_t tile_end) {
 	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
 	__shared__ uint32_t s_warp[9];
@@ -228,7 +225,6 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x) {
 		const uint64_t s0 = tile * kTile;
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
-		const bool bloom_tile = LIST || (tile >= bloom_lo && tile < bloom_hi);   // this launch's share of the Bloom inserts
 		__syncthreads();
 		if (threadIdx.x == 0) s_bloom_n = 0;
 		stage_tile(db, s0, n_rec, s_stage);
@@ -250,12 +246,11 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 				cnt[j] = c;
 				if (c >= db.min_count && c <= db.max_count) {
 					const bool to_stream = LIST ? true : (c >= (uint32_t)(m.ci + m.bf_num));
-					if (to_stream ? (out_kmer != nullptr) : bloom_tile)
-						kmer[j] = decode_kmer(db, rec, lut_slot(db.lut, slot_lo, slot_hi, s0 + t));
+					kmer[j] = decode_kmer(db, rec, lut_slot(db.lut, slot_lo, slot_hi, s0 + t));
 					if (to_stream) {
 						keep |= 1u << j;
 						n_keep++;
-					} else if (!LIST && bloom_tile && c >= (uint32_t)m.ci) {
+					} else if (!LIST && c >= (uint32_t)m.ci) {
 						cg::coalesced_group g = cg::coalesced_threads();
 						unsigned int at = 0;
 						if (g.thread_rank() == 0) at = atomicAdd(&s_bloom_n, g.size());
@@ -283,16 +278,20 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Dev
 					if (q < nh - 2) filter_set(m.bf_back[f], hash_finish(p, k - 2, c_seeds[q]));
 			}
 		}
-		if (out_kmer == nullptr) continue;                   // Bloom share only (uniform over the grid)
 		uint32_t total;
 		uint32_t rank = block_excl_scan<8>(n_keep, s_warp, &total);
-		uint64_t dst = __ldg(tile_off + tile) + rank;
+		unsigned long long g = route.base + __ldg(tile_off + (tile - tile_first)) + rank;      // stream position (file order)
 #pragma unroll
 		for (int j = 0; j < PER; j++) {
 			if (keep & (1u << j)) {
-				out_kmer[dst] = kmer[j];
-				out_occ[dst] = cnt[j];
-				dst++;
+				// bucket B = g >> 18 -> batch B / n_bits, bucket i = B % n_bits, round-0 array i, owner i % n_active; the owner
+				// keeps its buckets back to back (one GPU: the shard is the stream itself)
+				int owner = 0;
+				unsigned long long at = g;
+				if (route.n_active > 1) route_item(g, route.n_active, route.n_bits, &owner, &at);
+				route.kmer[owner][at] = kmer[j];
+				route.occ[owner][at] = cnt[j];
+				g++;
 			}
 		}
 	}
@@ -303,40 +302,37 @@ static int stream_grid(uint64_t n_tiles, int sm_count, int per_sm) {
 	return (int)(n_tiles < cap ? (n_tiles ? n_tiles : 1) : cap);
 }
 
-cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, int sm_count,
-                         cudaStream_t stream) {
-	if (db.total == 0) return cudaSuccess;
-	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	count_kernel<false><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt);
+cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, uint64_t tile_first,
+                         uint64_t tile_end, int sm_count, cudaStream_t stream) {
+	if (tile_end <= tile_first) return cudaSuccess;
+	count_kernel<false><<<stream_grid(tile_end - tile_first, sm_count, 8), 256, 0, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end);
+	note_launch();
 	return cudaGetLastError();
 }
 
 cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream) {
 	if (db.total == 0) return cudaSuccess;
 	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	count_kernel<true><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt);
+	count_kernel<true><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles);
+	note_launch();
 	return cudaGetLastError();
 }
 
 cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint64_t* d_tile_off, cudaStream_t stream) {
 	tile_scan_kernel<<<1, 1024, 0, stream>>>(d_tile_cnt, n_tiles, d_tile_off);
+	note_launch();
 	return cudaGetLastError();
 }
 
-cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, uint64_t* d_item_kmer,
-                          uint32_t* d_item_occ, uint64_t bloom_tile_lo, uint64_t bloom_tile_hi, bool stream_items, int sm_count,
-                          cudaStream_t stream) {
-	if (db.total == 0) return cudaSuccess;
-	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	if (bloom_tile_hi > n_tiles) bloom_tile_hi = n_tiles;
-	const uint64_t first = stream_items ? 0 : bloom_tile_lo, end = stream_items ? n_tiles : bloom_tile_hi;
-	if (end <= first) return cudaSuccess;
-	if (!stream_items) d_item_kmer = nullptr;
-	int grid = stream_grid(end - first, sm_count, 8);
+cudaError_t launch_encode(const DevDb& db, const DevModel& m, const uint64_t* d_tile_off, const ItemRoute& route, uint64_t tile_first,
+                          uint64_t tile_end, int sm_count, cudaStream_t stream) {
+	if (tile_end <= tile_first) return cudaSuccess;
+	int grid = stream_grid(tile_end - tile_first, sm_count, 8);
 	if (db.k == 31 && m.n_hash == 7)
-		encode_kernel<false, 31, 7><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ, bloom_tile_lo, bloom_tile_hi, first, end);
+		encode_kernel<false, 31, 7><<<grid, 256, 0, stream>>>(db, m, d_tile_off, route, tile_first, tile_end);
 	else
-		encode_kernel<false, 0, 0><<<grid, 256, 0, stream>>>(db, m, d_tile_off, d_item_kmer, d_item_occ, bloom_tile_lo, bloom_tile_hi, first, end);
+		encode_kernel<false, 0, 0><<<grid, 256, 0, stream>>>(db, m, d_tile_off, route, tile_first, tile_end);
+	note_launch();
 	return cudaGetLastError();
 }
 
@@ -345,7 +341,13 @@ cudaError_t launch_list(const DevDb& db, const uint64_t* d_tile_off, uint64_t* d
 	if (db.total == 0) return cudaSuccess;
 	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
 	DevModel dummy = {};
-	encode_kernel<true, 0, 0><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, dummy, d_tile_off, d_kmers, d_counts, 0, n_tiles, 0, n_tiles);
+	ItemRoute route = {};
+	route.kmer[0] = d_kmers;
+	route.occ[0] = d_counts;
+	route.n_active = 1;
+	route.n_bits = 1;
+	encode_kernel<true, 0, 0><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, dummy, d_tile_off, route, 0, n_tiles);
+	note_launch();
 	return cudaGetLastError();
 }
 
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 	};
 	grid.sync();                                            // everybody has read ctl->epoch / seq / bar before they are rewritten
 
+	const uint32_t per_batch_mine = buckets_per_batch(a.rank, a.n_active, nb);
 	for (unsigned long long batch = a.first_batch; batch < a.first_batch + a.n_batches; batch++) {
 		const unsigned long long base = batch * total_ids;
 		if (base >= a.n_items) break;
@@ -446,8 +449,21 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 
 		for (int t = 0; t < nb; t++) {
 			const bool last_round = (t == nb - 1);
-			const uint64_t* src_kmer = t == 0 ? a.item_kmer + base : a.buf_kmer[(t - 1) & 1];
-			const uint32_t* src_occ = t == 0 ? a.item_occ + base : a.buf_occ[(t - 1) & 1];
+			const uint64_t* src_kmer = t == 0 ? a.item_kmer : a.buf_kmer[(t - 1) & 1];
+			const uint32_t* src_occ = t == 0 ? a.item_occ : a.buf_occ[(t - 1) & 1];
+			// where item id = (bucket i << 18 | c) of this round lives in src_*: rounds > 0 read the ping-pong buffer, indexed by
+			// id; round 0 reads the item stream, in which this owner keeps its buckets (those whose round-0 array i it owns) back
+			// to back, batch after batch (one GPU: bucket i of batch b is bucket b * n_bits + i of the stream)
+			uint32_t src_bucket[BM];
+#pragma unroll
+			for (int i = 0; i < BM; i++)
+				src_bucket[i] = t == 0 ? (uint32_t)batch * per_batch_mine + (uint32_t)i / (uint32_t)a.n_active : (uint32_t)i;
+			auto src_at = [&](uint32_t id) -> size_t {
+				uint32_t sb = 0;
+#pragma unroll
+				for (int i = 0; i < BM; i++) sb = (id >> kBucketLog) == (uint32_t)i ? src_bucket[i] : sb;
+				return ((size_t)sb << kBucketLog) | (id & (kBucket - 1));
+			};
 
 			// ---------------- decide every item of the round ----------------
 			// ItemCtx: what every phase recomputes from the item (hashing is cheaper than keeping
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				for (int j = 0; j < HM; j++)
 					if (j < nh) it.pos[j] = fastmod(hash_finish(p, k, m.arr_seed[it.arr][j]), m.arr_mod);
 			};
-			auto load_item = [&](uint32_t id, ItemCtx& it) { prepare_item(id, __ldcg(src_kmer + id), __ldcg(src_occ + id), it); };
+			auto load_item = [&](uint32_t id, ItemCtx& it) { prepare_item(id, __ldcg(src_kmer + src_at(id)), __ldcg(src_occ + src_at(id)), it); };
 			// read the item's cells: conflict with the committed state? which positions are still untagged?
 			auto read_cells = [&](const ItemCtx& it, bool& conflict, uint32_t& untagged) {
 				unsigned long long cell[HM];
@@ -587,8 +603,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 			// ---- first iteration, phase 0: reject on the committed state, or claim (position, wanted value) ----
 			// (the next item's k-mer and count are fetched while the current one is hashed and probed)
 			uint32_t id_n = tid < n_round ? dense_to_id(tid) : 0;
-			uint64_t v_n = tid < n_round ? __ldcg(src_kmer + id_n) : 0;
-			uint32_t occ_n = tid < n_round ? __ldcg(src_occ + id_n) : 0;
+			uint64_t v_n = tid < n_round ? __ldcg(src_kmer + src_at(id_n)) : 0;
+			uint32_t occ_n = tid < n_round ? __ldcg(src_occ + src_at(id_n)) : 0;
 			// what this thread learns about its first item (x = tid) stays in registers for phase 1, whose first
 			// iteration is the same item: rounds of at most one item per thread skip two dependent load waves there
 			const uint32_t id_first = id_n;
@@ -601,8 +617,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				const uint32_t occ_c = occ_n;
 				if (x + T < n_round) {
 					id_n = dense_to_id(x + T);
-					v_n = __ldcg(src_kmer + id_n);
-					occ_n = __ldcg(src_occ + id_n);
+					v_n = __ldcg(src_kmer + src_at(id_n));
+					occ_n = __ldcg(src_occ + src_at(id_n));
 				}
 				ItemCtx it;
 				prepare_item(id, v_c, occ_c, it);
@@ -654,8 +670,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				if (x + T < n_round) {
 					id_n = dense_to_id(x + T);
 					st_n = a.claim_first ? 0u : __ldcg(a.status + id_n);
-					v_n = __ldcg(src_kmer + id_n);
-					occ_n = __ldcg(src_occ + id_n);
+					v_n = __ldcg(src_kmer + src_at(id_n));
+					occ_n = __ldcg(src_occ + src_at(id_n));
 				}
 				if (untagged >> kStateShift) continue;
 				ItemCtx it;
@@ -930,8 +946,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 						if (!valid) continue;
 						if (failed) {
 							if (last_round) {
-								const uint64_t v = __ldcg(src_kmer + id);
-								const uint32_t occ = __ldcg(src_occ + id);
+								const uint64_t v = __ldcg(src_kmer + src_at(id));
+								const uint32_t occ = __ldcg(src_occ + src_at(id));
 								a.rest_kmer[rest_at + (mine - before)] = v;
 								a.rest_occ[rest_at + (mine - before)] = occ;
 								// what reorder_buffer leaves in slot 0: item 0 if it was rejected, else the last rejected item
@@ -941,8 +957,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 								}
 							} else if (c < F) {
 								const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;   // owner of this bucket's next array
-								a.peer_buf_kmer[t & 1][nx][id] = __ldcg(src_kmer + id);
-								a.peer_buf_occ[t & 1][nx][id] = __ldcg(src_occ + id);
+								a.peer_buf_kmer[t & 1][nx][id] = __ldcg(src_kmer + src_at(id));
+								a.peer_buf_occ[t & 1][nx][id] = __ldcg(src_occ + src_at(id));
 							} else {
 								a.excl_rank[id] = mine;
 							}
@@ -975,13 +991,15 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					const uint32_t d = F - __ldcg(a.excl_rank + id) - 1;
 					const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
 					const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;
-					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_kmer + id);
-					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_occ + id);
+					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_kmer + src_at(id));
+					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_occ + src_at(id));
 				}
 			}
 			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;
-			{   // clear the part of the claim bitmaps this round used (only the arrays this rank worked on), 16 bytes per store
-				const uint32_t vecs = 1u << (claim_log2 - 7);
+			{   // clear the part of the claim bitmaps this round used (only the arrays this rank worked on), 16 bytes per store;
+				// a bitmap that spans the whole array (claim bit = position, small models) is only as long as the array
+				const unsigned long long span = (1ULL << claim_log2) < m.arr_mod.d ? (1ULL << claim_log2) : m.arr_mod.d;
+				const uint32_t vecs = (uint32_t)((span + 127) >> 7);
 				uint32_t act = 0, n_act = 0;                     // 4 bits per active array
 #pragma unroll
 				for (int i = 0; i < BM; i++) {
@@ -1063,28 +1081,15 @@ cudaError_t insert_grid_size(int* blocks_out, int sm_count) {
 cudaError_t launch_insert(const DevModel& m, const InsertArgs& a, int grid_blocks, cudaStream_t stream) {
 	if (grid_blocks < m.n_bits) return cudaErrorInvalidConfiguration;
 	void* args[2] = { (void*)&m, (void*)&a };
+	note_launch();
 	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5)
 		return cudaLaunchCooperativeKernel((const void*)insert_kernel<31, 7, 5>, dim3(grid_blocks), dim3(kInsThreads), args, 0, stream);
 	return cudaLaunchCooperativeKernel((const void*)insert_kernel<0, 0, 0>, dim3(grid_blocks), dim3(kInsThreads), args, 0, stream);
 }
 
 // =========================================================================================
-// rest table (rest.hpp:95-135): survivors sorted by packed value, group index per prefix
+// rest table (rest.hpp:95-135): survivors sorted by packed value (kmx_sort.cu), group index per prefix
 // =========================================================================================
-cudaError_t rest_sort_bytes(size_t n, size_t* temp_bytes) {
-	*temp_bytes = 0;
-	if (n == 0) return cudaSuccess;
-	return cub::DeviceRadixSort::SortPairs(nullptr, *temp_bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-	                                       (const uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)n, 0, 64);
-}
-
-cudaError_t launch_rest_sort(void* d_temp, size_t temp_bytes, const uint64_t* d_keys_in, uint64_t* d_keys_out,
-                             const uint32_t* d_vals_in, int32_t* d_vals_out, size_t n, int key_bits, cudaStream_t stream) {
-	if (n == 0) return cudaSuccess;
-	return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys_in, d_keys_out, d_vals_in, (uint32_t*)d_vals_out, (int64_t)n,
-	                                       0, key_bits, stream);
-}
-
 __global__ void rest_first_kernel(const uint64_t* __restrict__ keys, uint64_t n, int suffix_bits, int32_t* __restrict__ first) {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint32_t pre = (uint32_t)(keys[i] >> suffix_bits);
@@ -1138,8 +1143,10 @@ cudaError_t launch_rest_index(const uint64_t* d_keys, uint64_t n, int suffix_bit
 	if (n) {
 		uint64_t blocks = (n + 255) / 256;
 		rest_first_kernel<<<(int)(blocks < 4096 ? blocks : 4096), 256, 0, stream>>>(d_keys, n, suffix_bits, d_first);
+		note_launch();
 	}
 	rest_index_kernel<<<1, 1024, 0, stream>>>(d_first, map_size, n, d_hash2index, d_pre_buffer, d_groups);
+	note_launch();
 	return cudaGetLastError();
 }
 
@@ -1164,12 +1171,14 @@ cudaError_t launch_split_cells(const unsigned long long* d_cells, uint64_t n_wor
 	if (n_words == 0) return cudaSuccess;
 	uint64_t blocks = (n_words + 255) / 256;
 	split_cells_kernel<<<(int)(blocks < 65535 ? blocks : 65535), 256, 0, stream>>>(d_cells, n_words, d_val, d_tag);
+	note_launch();
 	return cudaGetLastError();
 }
 cudaError_t launch_merge_cells(const uint32_t* d_val, const uint32_t* d_tag, uint64_t n_words, unsigned long long* d_cells, cudaStream_t stream) {
 	if (n_words == 0) return cudaSuccess;
 	uint64_t blocks = (n_words + 255) / 256;
 	merge_cells_kernel<<<(int)(blocks < 65535 ? blocks : 65535), 256, 0, stream>>>(d_val, d_tag, n_words, d_cells);
+	note_launch();
 	return cudaGetLastError();
 }
 

@@ -140,6 +140,27 @@ KMX_HD void hash_prepare(uint64_t r, int len, HashPrep& p) {
 	p.h0 = (uint64_t)len * kMurM;
 }
 
+// the same preparation from the raw bytes of a string (len <= 39): what the reference hashes when a query keeps its
+// original characters (tools.hpp:160-167 returns the string itself when the forward orientation is the smaller one)
+KMX_HD void hash_prepare_bytes(const uint8_t* s, int len, HashPrep& p) {
+	const int nblocks = len >> 3;
+	const int tb = len & 7;
+#pragma unroll
+	for (int b = 0; b < 4; b++) {
+		if (b < nblocks) {
+			uint64_t w = 0;
+			for (int j = 0; j < 8; j++) w |= (uint64_t)s[8 * b + j] << (8 * j);
+			w *= kMurM;
+			w ^= w >> 47;
+			w *= kMurM;
+			p.w[b] = w;
+		}
+	}
+	p.tail = 0;
+	for (int j = 0; j < tb; j++) p.tail |= (uint64_t)s[8 * nblocks + j] << (8 * j);
+	p.h0 = (uint64_t)len * kMurM;
+}
+
 KMX_HD uint64_t hash_finish(const HashPrep& p, int len, uint32_t seed) {
 	const int nblocks = len >> 3;
 	uint64_t h = (uint64_t)seed ^ p.h0;

@@ -16,114 +16,102 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
-#include "../../include/kmx.h"
-#include "kmx_device.cuh"
-#include "kmx_launch.h"
+#include "kmx_internal.h"
 
 using namespace kmx;
 
 // =========================================================================================
-// errors
+// errors, device selection, launch counter
 // =========================================================================================
 static thread_local char g_err[512] = "";
-static int g_device = 0;
-
-// KMX_TRACE=1: host-side timeline of a build on stderr (milliseconds since the call started)
-static bool trace_on() {
-	static int on = -1;
-	if (on < 0) on = getenv("KMX_TRACE") ? 1 : 0;
-	return on == 1;
-}
-#define TRACE(t0, what)                                                                                             \
-	do {                                                                                                           \
-		if (trace_on())                                                                                            \
-			fprintf(stderr, "[kmx] %8.3f ms  %s\n",                                                                \
-			        1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - (t0)).count(), what); \
-	} while (0)
-
-static int fail(int code, const char* fmt, ...) {
-	va_list ap;
-	va_start(ap, fmt);
-	vsnprintf(g_err, sizeof(g_err), fmt, ap);
-	va_end(ap);
-	return code;
-}
+static thread_local int g_err_code = 0;
+static int g_device = 0;                       // process-wide default (kmx_set_device)
+static thread_local int t_device = -1;         // per-thread override (threads of an in-process team build)
+static std::atomic<unsigned long long> g_launches{ 0 };
 
 namespace kmx {
-// error reporting for the other translation units of the library
+
 int set_error(int code, const char* fmt, ...) {
 	va_list ap;
 	va_start(ap, fmt);
 	vsnprintf(g_err, sizeof(g_err), fmt, ap);
 	va_end(ap);
+	g_err_code = code;
 	return code;
 }
-}  // namespace kmx
+const char* last_error() { return g_err; }
+int last_error_code() { return g_err_code; }
 
-#define CU(call)                                                                                         \
-	do {                                                                                                 \
-		cudaError_t e__ = (call);                                                                        \
-		if (e__ != cudaSuccess) return fail(KMX_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-	} while (0)
+bool trace_on() {
+	static int on = -1;
+	if (on < 0) on = getenv("KMX_TRACE") ? 1 : 0;
+	return on == 1;
+}
+
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int current_device() { return t_device >= 0 ? t_device : g_device; }
+void set_thread_device(int ordinal) { t_device = ordinal; }
 
 // Stream-ordered allocations from the device's default memory pool, which is told to keep
 // freed blocks: a rebuild (or the next query staging) reuses them instead of paying
 // cudaMalloc/cudaFree (hundreds of microseconds each, and cudaFree synchronises the device).
-static int dev_alloc_impl(void** p, size_t bytes, cudaStream_t s) {
-	static bool pool_ready[64] = { false };
+int dev_alloc_impl(void** p, size_t bytes, cudaStream_t s) {
+	static std::atomic<bool> pool_ready[64];
 	int dev = 0;
 	CU(cudaGetDevice(&dev));
-	if (dev < 64 && !pool_ready[dev]) {
+	if (dev < 64 && !pool_ready[dev].load()) {
 		cudaMemPool_t pool;
 		CU(cudaDeviceGetDefaultMemPool(&pool, dev));
 		uint64_t keep = ~0ULL;
 		CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-		pool_ready[dev] = true;
+		pool_ready[dev].store(true);
 	}
 	CU(cudaMallocAsync(p, bytes ? bytes : 8, s));
 	return KMX_OK;
 }
-template <class T>
-static int dev_alloc(T** p, size_t bytes, cudaStream_t s) { return dev_alloc_impl((void**)p, bytes, s); }
-static void dev_free(void* p, cudaStream_t s) {
+void dev_free(void* p, cudaStream_t s) {
 	if (p) cudaFreeAsync(p, s);
 }
-#define DA(ptr, bytes, stream)                                   \
-	do {                                                         \
-		int rc__ = dev_alloc(ptr, bytes, stream);                \
-		if (rc__) return rc__;                                   \
-	} while (0)
 
-static int require_gpu(int* sm_count) {
+int require_gpu(int* sm_count) {
 	// cudaGetDeviceProperties costs milliseconds: ask once per device
+	static std::mutex mu;
 	static int cached_sm[64] = { 0 };
 	static int cached_n = -1;
+	std::lock_guard<std::mutex> lock(mu);
 	if (cached_n < 0) {
 		int n = 0;
 		cudaError_t e = cudaGetDeviceCount(&n);
 		if (e != cudaSuccess || n <= 0) {
 			cudaGetLastError();
-			return fail(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path): %s", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+			return set_error(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path): %s", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
 		}
 		cached_n = n;
 	}
-	if (g_device >= cached_n || g_device >= 64) return fail(KMX_ENOGPU, "device %d requested, %d present", g_device, cached_n);
-	CU(cudaSetDevice(g_device));
-	if (cached_sm[g_device] == 0) {
+	const int dev = current_device();
+	if (dev >= cached_n || dev >= 64) return set_error(KMX_ENOGPU, "device %d requested, %d present", dev, cached_n);
+	CU(cudaSetDevice(dev));
+	if (cached_sm[dev] == 0) {
 		cudaDeviceProp prop;
-		CU(cudaGetDeviceProperties(&prop, g_device));
-		if (prop.major < 10) return fail(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", g_device, prop.major, prop.minor);
-		cached_sm[g_device] = prop.multiProcessorCount;
+		CU(cudaGetDeviceProperties(&prop, dev));
+		if (prop.major < 10) return set_error(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+		cached_sm[dev] = prop.multiProcessorCount;
 	}
-	if (sm_count) *sm_count = cached_sm[g_device];
+	if (sm_count) *sm_count = cached_sm[dev];
 	return KMX_OK;
 }
+
+}  // namespace kmx
+
+#define fail kmx::set_error
 
 // =========================================================================================
 // OccuBin (occu_bin.hpp:27-83) as two lookup tables
@@ -170,7 +158,7 @@ static int occubin_tables(int max_counter, int n_hash, std::vector<int32_t>& occ
 }
 
 // kmodel.hpp:402-456.  The Bloom size is evaluated in double exactly as the reference writes it.
-static void model_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_kmers, int n_hash, uint64_t bytes[8]) {
+void kmx::model_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_kmers, int n_hash, uint64_t bytes[8]) {
 	const int hb = n_hash - 1, hk = n_hash - 2;
 	for (int i = 0; i < 8; i++) bytes[i] = 0;
 	for (int i = 0; i < bf_num; i++) {
@@ -181,53 +169,25 @@ static void model_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_k
 	bytes[7] = (km_kmers >> 4) * (uint64_t)hk;
 }
 
-static int rest_prefix_len(int k) {              // rest.hpp:78-83
+int kmx::rest_prefix_len(int k) {              // rest.hpp:78-83
 	for (int i = 7; i >= 3; i--)
 		if ((k - i) % 4 == 0) return i;
 	return 3;
 }
 
 // =========================================================================================
-// objects
+// execution contexts (kmx_internal.h: DevCtx), pooled per device
 // =========================================================================================
-// Per-device execution context: streams, events, pinned scratch and the query staging buffers.
-// Creating these costs milliseconds (cudaHostAlloc, cudaStreamCreate), so contexts are pooled
-// for the life of the process: a model borrows one at its first device use and returns it when
-// destroyed; a database upload borrows one for the duration of the copy.
-struct DevCtx {
-	int device = 0;
-	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaStream_t reader[16] = {};
-	cudaEvent_t reader_ev[16][2] = {};
-	cudaEvent_t ev_build[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
-		CountOut count;
-		InsertCtl ctl;
-		int32_t groups;
-	}* h_pinned = nullptr;
-	// pinned staging for host-pointer queries (two slots)
-	void* h_in[2] = { nullptr, nullptr };
-	int32_t* h_out[2] = { nullptr, nullptr };
-	void* d_in[2] = { nullptr, nullptr };
-	int32_t* d_out[2] = { nullptr, nullptr };
-	uint64_t* d_pack[2] = { nullptr, nullptr };
-	DeferredQuery* d_defer[2] = { nullptr, nullptr };
-	unsigned int* d_defer_n[2] = { nullptr, nullptr };
-	size_t stage_bytes = 0, stage_items = 0;
-	cudaEvent_t ev_done[2] = { nullptr, nullptr };
-	std::mutex query_mu;              // host-pointer queries share the staging slots: one batch at a time per model
-};
-
 namespace {
 std::mutex g_ctx_mu;
 std::vector<DevCtx*> g_ctx_free;
 }
 
-static int ctx_acquire(DevCtx** out) {
+int kmx::ctx_acquire(DevCtx** out) {
 	{
 		std::lock_guard<std::mutex> lock(g_ctx_mu);
 		for (size_t i = 0; i < g_ctx_free.size(); i++) {
-			if (g_ctx_free[i]->device == g_device) {
+			if (g_ctx_free[i]->device == current_device()) {
 				*out = g_ctx_free[i];
 				g_ctx_free.erase(g_ctx_free.begin() + i);
 				return KMX_OK;
@@ -235,7 +195,7 @@ static int ctx_acquire(DevCtx** out) {
 		}
 	}
 	DevCtx* c = new DevCtx();
-	c->device = g_device;
+	c->device = current_device();
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 	for (auto& r : c->reader) CU(cudaStreamCreateWithFlags(&r, cudaStreamNonBlocking));
@@ -248,7 +208,7 @@ static int ctx_acquire(DevCtx** out) {
 	return KMX_OK;
 }
 
-static void ctx_release(DevCtx* c) {
+void kmx::ctx_release(DevCtx* c) {
 	if (!c) return;
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->stream2);
@@ -256,81 +216,24 @@ static void ctx_release(DevCtx* c) {
 	g_ctx_free.push_back(c);
 }
 
-struct kmx_db {
-	kmx_db_info_t info;
-	std::vector<uint64_t> lut;        // lut_entries + 1 (guard = total + 1, kmc_file.cpp:223)
-	int fd = -1;                      // .kmc_suf, kept open until the records are on the device
-	size_t suf_alloc = 0;
-	uint8_t* d_suf = nullptr;
-	uint64_t* d_lut = nullptr;
-	int device = 0, sm_count = 0;
-	float ms_upload = 0;
-};
-
-struct RestHost {
-	int32_t k = 0, pre_len = 0, map_size = 0, pre_buffer_size = 0;
-	uint64_t suff_bin_size = 0, count = 0;
-};
-
-// what a build carries from one stage to the next (kmx_init_from_db runs the stages back to back)
-struct BuildState {
-	std::chrono::high_resolution_clock::time_point wall0;
-	uint64_t n_items = 0, n_batches = 0, rest_cap = 0;
-	uint64_t* d_item_kmer = nullptr;
-	uint32_t* d_item_occ = nullptr;
-	InsertArgs a = {};
-	int grid = 0;
-	bool worst_case = true;
-	float ms_upload = 0;
-	// multi-GPU: one cudaMalloc slab with everything peers write into, and the peers' slabs as mapped here
-	void* slab = nullptr;
-	size_t slab_bytes = 0, off[6] = { 0 };
-	uint32_t* flags = nullptr;
-	void* peer_slab[kMaxRanks] = { nullptr };
-	// multi-GPU: the Bloom filters and km_back live in a second cudaMalloc slab that every rank maps, so that the
-	// partial filters can be OR-ed through peer memory (kmx_dist.cu).  Layout: [Bloom filters | km_back | flags | error]
-	void* fslab = nullptr;
-	size_t fslab_bytes = 0, f_bloom_bytes = 0, f_kmback_off = 0, f_kmback_bytes = 0, f_flags_off = 0;
-	void* peer_fslab[kMaxRanks] = { nullptr };
-	uint32_t fseq = 0;
-	int world = 1, dist_rank = 0;
-};
-
-struct kmx_model {
-	int ci = 1, cs = 1023, n_hash = 7, n_bits = 5, bf_num = 1, k = 0;
-	int device = 0, sm_count = 0;
-	bool built = false;
-	uint64_t total_kmers = 0, km_kmers = 0, kmer_counts[3] = { 0, 0, 0 };
-	uint64_t bytes[8] = { 0 };        // see kmx_host_sizes
-	std::vector<int32_t> occ2bin, bin2mean;
-	// device
-	uint32_t* d_bf[3] = { nullptr, nullptr, nullptr };
-	uint32_t* d_bf_back[3] = { nullptr, nullptr, nullptr };
-	uint32_t* d_km_back = nullptr;
-	unsigned long long* d_cells[kMaxArrays] = { nullptr };
-	uint16_t* d_occ2bin = nullptr;
-	int32_t* d_bin2mean = nullptr;
-	int32_t* d_hash2index = nullptr;
-	int32_t* d_pre_buffer = nullptr;
-	uint64_t* d_rest_keys = nullptr;
-	int32_t* d_rest_counts = nullptr;
-	uint32_t* d_fine = nullptr;
-	uint64_t* d_quirk_suffix = nullptr;
-	uint32_t* d_quirk_index = nullptr;
-	int fine_bits = 8;
-	RestHost rest;
-	DevModel dm;
-	kmx_info_t info;
-	DevCtx* x = nullptr;              // borrowed execution context (streams, events, staging)
-	BuildState bs;
-	std::vector<uint16_t> occ2bin16;
-};
-
-static size_t pad8(uint64_t bytes) { return (size_t)((bytes + 7) & ~7ULL) + 8; }
-static uint64_t cell_words(uint64_t km_byte_size) { return (km_byte_size + 3) / 4; }
-
-static void free_model_device(kmx_model* m) {
+void kmx::free_model_device(kmx_model* m) {
 	cudaStream_t s = m->x->stream;
+	if (m->mslab) {
+		// team build: filters and coupled arrays are carved from one peer-mapped slab
+		cudaStreamSynchronize(s);
+		slab_release(m->mslab, m->mslab_bytes, m->device);
+		m->mslab = nullptr;
+		for (int i = 0; i < 3; i++) m->d_bf[i] = m->d_bf_back[i] = nullptr;
+		m->d_km_back = nullptr;
+		for (int i = 0; i < kMaxArrays; i++) m->d_cells[i] = nullptr;
+	}
+	if (m->rslab) {
+		cudaStreamSynchronize(s);
+		slab_release(m->rslab, m->rslab_bytes, m->device);
+		m->rslab = nullptr;
+		m->d_rest_keys = nullptr;
+		m->d_rest_counts = nullptr;
+	}
 	for (int i = 0; i < 3; i++) {
 		dev_free(m->d_bf[i], s);
 		dev_free(m->d_bf_back[i], s);
@@ -357,53 +260,33 @@ static void free_model_device(kmx_model* m) {
 	m->d_rest_counts = nullptr;
 }
 
-static int slab_acquire(void** out, size_t bytes, int device);
-
-// allocate + zero every filter of the model from m->kmer_counts / m->km_kmers (kmodel.hpp:402-456);
-// in_slab: Bloom filters and km_back are carved from one exportable cudaMalloc block (multi-GPU build)
-static int alloc_filters(kmx_model* m, bool in_slab = false) {
+// sizes from m->kmer_counts / m->km_kmers (kmodel.hpp:402-456) and the reference's failure corners on degenerate ones
+int kmx::check_model_sizes(kmx_model* m) {
 	model_sizes(m->kmer_counts, m->bf_num, m->km_kmers, m->n_hash, m->bytes);
 	for (int i = 0; i < m->bf_num; i++) {
 		if (m->bytes[i] == 0 || m->bytes[3 + i] == 0)
-			return fail(KMX_ERANGE, "count class %d holds %llu k-mers: the reference aborts on a zero-length Bloom filter (kmodel.hpp:413-417)",
+			return fail(KMX_ERANGE, "count class %d holds %llu k-mers, which makes a Bloom filter of length 0: the reference (g++ >= 5) dies with "
+			            "std::bad_array_new_length at kmodel.hpp:413-417 (`new uint8_t[0]{ 0 }`) and would divide by zero at kmodel.hpp:378",
 			            m->ci + i, (unsigned long long)m->kmer_counts[i]);
 	}
 	if (m->bytes[6] == 0 || m->bytes[7] == 0)
-		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays: the reference aborts on zero-length arrays (kmodel.hpp:443-447)",
+		return fail(KMX_ERANGE, "%llu k-mers for the coupled arrays make arrays of length 0: the reference dies with std::bad_array_new_length at kmodel.hpp:441-447",
 		            (unsigned long long)m->km_kmers);
-	if (in_slab) {
-		BuildState& b = m->bs;
-		auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-		size_t off = 0, o_bf[3] = { 0, 0, 0 }, o_bb[3] = { 0, 0, 0 };
-		for (int i = 0; i < m->bf_num; i++) {
-			o_bf[i] = off; off += up(pad8(m->bytes[i]));
-			o_bb[i] = off; off += up(pad8(m->bytes[3 + i]));
-		}
-		b.f_bloom_bytes = off;
-		b.f_kmback_off = off;
-		b.f_kmback_bytes = up(pad8(m->bytes[7]));
-		off += b.f_kmback_bytes;
-		b.f_flags_off = off;
-		b.fslab_bytes = off + 256;                           // kMaxRanks barrier counters + the error word
-		int rc = slab_acquire(&b.fslab, b.fslab_bytes, m->device);
-		if (rc) return rc;
-		CU(cudaMemsetAsync(b.fslab, 0, b.fslab_bytes, m->x->stream));
-		uint8_t* base = (uint8_t*)b.fslab;
-		for (int i = 0; i < m->bf_num; i++) {
-			m->d_bf[i] = (uint32_t*)(base + o_bf[i]);
-			m->d_bf_back[i] = (uint32_t*)(base + o_bb[i]);
-		}
-		m->d_km_back = (uint32_t*)(base + b.f_kmback_off);
-	} else {
-		for (int i = 0; i < m->bf_num; i++) {
-			DA(&m->d_bf[i], pad8(m->bytes[i]), m->x->stream);
-			CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->x->stream));
-			DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->x->stream);
-			CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->x->stream));
-		}
-		DA(&m->d_km_back, pad8(m->bytes[7]), m->x->stream);
-		CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->x->stream));
+	return KMX_OK;
+}
+
+// allocate + zero every filter of the model (single GPU: stream-ordered pool allocations)
+static int alloc_filters(kmx_model* m) {
+	int rc = check_model_sizes(m);
+	if (rc) return rc;
+	for (int i = 0; i < m->bf_num; i++) {
+		DA(&m->d_bf[i], pad8(m->bytes[i]), m->x->stream);
+		CU(cudaMemsetAsync(m->d_bf[i], 0, pad8(m->bytes[i]), m->x->stream));
+		DA(&m->d_bf_back[i], pad8(m->bytes[3 + i]), m->x->stream);
+		CU(cudaMemsetAsync(m->d_bf_back[i], 0, pad8(m->bytes[3 + i]), m->x->stream));
 	}
+	DA(&m->d_km_back, pad8(m->bytes[7]), m->x->stream);
+	CU(cudaMemsetAsync(m->d_km_back, 0, pad8(m->bytes[7]), m->x->stream));
 	const uint64_t words = cell_words(m->bytes[6]);
 	for (int i = 0; i < m->n_bits; i++) {
 		DA(&m->d_cells[i], (words + 1) * 8, m->x->stream);
@@ -412,7 +295,7 @@ static int alloc_filters(kmx_model* m, bool in_slab = false) {
 	return KMX_OK;
 }
 
-static void fill_dev_model(kmx_model* m) {
+void kmx::fill_dev_model(kmx_model* m) {
 	DevModel& d = m->dm;
 	memset(&d, 0, sizeof(d));
 	d.k = m->k;
@@ -454,7 +337,7 @@ static void fill_dev_model(kmx_model* m) {
 	d.rest.fine_shift = 2 * m->rest.k - m->fine_bits;
 }
 
-static void fill_info(kmx_model* m) {
+void kmx::fill_info(kmx_model* m) {
 	kmx_info_t& f = m->info;
 	f.ci = m->ci; f.cs = m->cs; f.n_hash = m->n_hash; f.n_bits = m->n_bits; f.bf_num = m->bf_num; f.k = m->k;
 	f.total_kmers = m->total_kmers;
@@ -478,7 +361,8 @@ static void fill_info(kmx_model* m) {
 // process-wide
 // =========================================================================================
 extern "C" const char* kmx_last_error(void) { return g_err; }
-extern "C" const char* kmx_version(void) { return "kmx 0.1 (sm_100a)"; }
+extern "C" unsigned long long kmx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" const char* kmx_version(void) { return "kmx 0.2 (sm_100a)"; }
 
 extern "C" int kmx_device_count(void) {
 	int n = 0;
@@ -493,7 +377,45 @@ extern "C" int kmx_set_device(int ordinal) {
 	int n = kmx_device_count();
 	if (ordinal < 0 || ordinal >= n) return fail(KMX_ENOGPU, "device %d requested, %d present", ordinal, n);
 	g_device = ordinal;
+	t_device = -1;
 	CU(cudaSetDevice(ordinal));
+	return KMX_OK;
+}
+
+// the GPUs one KModel::init is spread over inside this process (kmx_set_devices; default from the environment: KMX_GPUS=N)
+namespace {
+std::mutex g_team_mu;
+std::vector<int> g_team_devices;
+bool g_team_set = false;
+}  // namespace
+
+const std::vector<int>& kmx::team_devices() {
+	std::lock_guard<std::mutex> lock(g_team_mu);
+	if (!g_team_set) {
+		g_team_set = true;
+		if (const char* e = getenv("KMX_GPUS")) {
+			const int want = atoi(e), have = kmx_device_count();
+			for (int d = 0; d < want && d < have && d < kMaxRanks; d++) g_team_devices.push_back(d);
+			if (g_team_devices.size() < 2) g_team_devices.clear();
+		}
+	}
+	return g_team_devices;
+}
+
+extern "C" int kmx_set_devices(const int* ordinals, int n) {
+	if (n < 0 || n > kMaxRanks || (n > 0 && !ordinals)) return fail(KMX_EARG, "kmx_set_devices: 0..%d device ordinals", kMaxRanks);
+	const int have = kmx_device_count();
+	std::vector<int> devs;
+	for (int i = 0; i < n; i++) {
+		if (ordinals[i] < 0 || ordinals[i] >= have) return fail(KMX_ENOGPU, "device %d requested, %d present", ordinals[i], have);
+		for (int d : devs)
+			if (d == ordinals[i]) return fail(KMX_EARG, "kmx_set_devices: device %d listed twice", d);
+		devs.push_back(ordinals[i]);
+	}
+	std::lock_guard<std::mutex> lock(g_team_mu);
+	g_team_set = true;
+	g_team_devices = devs.size() >= 2 ? devs : std::vector<int>();
+	if (devs.size() == 1) g_device = devs[0];
 	return KMX_OK;
 }
 
@@ -522,13 +444,11 @@ extern "C" kmx_model* kmx_create(int ci, int cs, int n_hash, int n_bits) {
 	return m;
 }
 
-static void build_state_free(kmx_model* m);
-
-static int model_attach_device(kmx_model* m) {
+int kmx::model_attach_device(kmx_model* m) {
 	if (m->x) return KMX_OK;
 	int rc = require_gpu(&m->sm_count);
 	if (rc) return rc;
-	m->device = g_device;
+	m->device = current_device();
 	if ((rc = ctx_acquire(&m->x))) return rc;
 	m->occ2bin16.resize(m->occ2bin.size());
 	for (size_t i = 0; i < m->occ2bin16.size(); i++) m->occ2bin16[i] = (uint16_t)m->occ2bin[i];
@@ -542,6 +462,8 @@ static int model_attach_device(kmx_model* m) {
 
 extern "C" void kmx_destroy(kmx_model* m) {
 	if (!m) return;
+	for (kmx_model* r : m->replicas) kmx_destroy(r);
+	m->replicas.clear();
 	if (m->x) {
 		cudaSetDevice(m->device);
 		cudaStreamSynchronize(m->x->stream);
@@ -663,8 +585,7 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 		return nullptr;
 	}
 	db->fd = fd;
-	db->suf_alloc = (size_t)((h.suffix_bytes + 15) & ~15ULL) + 16;
-	db->device = g_device;
+	db->device = current_device();
 	return db;
 }
 
@@ -695,15 +616,19 @@ struct Bounce {
 Bounce g_bounce;
 }  // namespace
 
-// .kmc_suf record area -> HBM: reader threads pread() 2 MiB chunks into pinned bounce buffers and push each with
-// its own stream, so page-cache copies and PCIe transfers overlap.  The page-cache copy (5-6 GB/s per thread) is the
-// slow half: one thread per host core, up to kReaders.
-extern "C" int kmx_db_upload(kmx_db* db) {
+// .kmc_suf record area (records [rec_lo, rec_hi)) -> HBM: reader threads pread() 2 MiB chunks into pinned bounce buffers and
+// push each with its own stream, so page-cache copies and PCIe transfers overlap.  The page-cache copy (5-6 GB/s per
+// thread) is the slow half: one thread per host core, up to kReaders (a team build in N processes asks for cores / N each).
+int kmx::db_upload_range(kmx_db* db, uint64_t rec_lo, uint64_t rec_hi, int reader_threads) {
 	if (!db) return fail(KMX_EARG, "null database");
-	if (db->d_suf) return KMX_OK;
+	if (rec_hi > db->info.total_kmers) rec_hi = db->info.total_kmers;
+	if (rec_lo > rec_hi) rec_lo = rec_hi;
+	if (db->d_suf && db->rec_lo <= rec_lo && db->rec_hi >= rec_hi) return KMX_OK;     // already resident
+	if (db->d_suf) return fail(KMX_ESTATE, "database holds records [%llu, %llu) on the device, [%llu, %llu) requested", (unsigned long long)db->rec_lo,
+	                           (unsigned long long)db->rec_hi, (unsigned long long)rec_lo, (unsigned long long)rec_hi);
 	int rc = require_gpu(&db->sm_count);
 	if (rc) return rc;
-	db->device = g_device;
+	db->device = current_device();
 	auto t0 = std::chrono::high_resolution_clock::now();
 	DevCtx* x = nullptr;
 	if ((rc = ctx_acquire(&x))) return rc;
@@ -713,15 +638,17 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 	} release{ x };
 	std::lock_guard<std::mutex> lock(g_bounce.mu);
 	if ((rc = g_bounce.acquire())) return rc;
+	const uint64_t rec_bytes = db->info.record_bytes;
+	const uint64_t byte_lo = rec_lo * rec_bytes, bytes = (rec_hi - rec_lo) * rec_bytes;
+	db->suf_alloc = (size_t)((bytes + 15) & ~15ULL) + 16;
 	DA(&db->d_suf, db->suf_alloc, x->stream);
 	DA(&db->d_lut, db->lut.size() * 8, x->stream);
 	CU(cudaMemcpyAsync(db->d_lut, db->lut.data(), db->lut.size() * 8, cudaMemcpyHostToDevice, x->stream));
-	const uint64_t bytes = db->info.suffix_bytes;
 	CU(cudaMemsetAsync(db->d_suf + (bytes & ~15ULL), 0, db->suf_alloc - (bytes & ~15ULL), x->stream));
 	CU(cudaStreamSynchronize(x->stream));                // the allocation is usable from the reader streams now
 	TRACE(t0, "upload: buffers ready");
 	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
-	int want_thr = std::max(1, std::min<int>(kReaders, (int)std::thread::hardware_concurrency()));
+	int want_thr = std::max(1, std::min<int>(kReaders, reader_threads > 0 ? reader_threads : (int)std::thread::hardware_concurrency()));
 	if (const char* e = getenv("KMX_READERS")) want_thr = std::max(1, std::min(kReaders, atoi(e)));
 	const int n_thr = (int)std::min<uint64_t>(want_thr, n_chunks);
 	std::vector<int> status(kReaders, KMX_OK);
@@ -735,7 +662,7 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 			uint8_t* b = g_bounce.buf[t][slot];
 			uint64_t got = 0;
 			while (got < len) {
-				ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + off + got));
+				ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + byte_lo + off + got));
 				if (r <= 0) { status[t] = KMX_EIO; break; }
 				got += (uint64_t)r;
 			}
@@ -749,11 +676,34 @@ extern "C" int kmx_db_upload(kmx_db* db) {
 	for (int t = 1; t < n_thr; t++) pool.emplace_back(work, t);
 	if (n_thr > 0) work(0);
 	for (auto& th : pool) th.join();
-	for (int t = 0; t < n_thr; t++)
-		if (status[t] != KMX_OK) return fail(status[t], status[t] == KMX_EIO ? "short read on the .kmc_suf file" : "host-to-device copy of the database failed");
+	for (int t = 0; t < n_thr; t++) {
+		if (status[t] != KMX_OK) {
+			dev_free(db->d_suf, x->stream);
+			dev_free(db->d_lut, x->stream);
+			db->d_suf = nullptr;
+			db->d_lut = nullptr;
+			return fail(status[t], status[t] == KMX_EIO ? "short read on the .kmc_suf file" : "host-to-device copy of the database failed");
+		}
+	}
+	db->rec_lo = rec_lo;
+	db->rec_hi = rec_hi;
 	db->ms_upload = (float)(1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count());
 	TRACE(t0, "upload: done");
 	return KMX_OK;
+}
+
+extern "C" int kmx_db_upload(kmx_db* db) {
+	if (!db) return fail(KMX_EARG, "null database");
+	return db_upload_range(db, 0, db->info.total_kmers, 0);
+}
+
+// the share of a team build's rank: whole decode tiles, [n_tiles * rank / world, n_tiles * (rank + 1) / world)
+extern "C" int kmx_db_upload_share(kmx_db* db, int rank, int world) {
+	if (!db || world < 1 || rank < 0 || rank >= world) return fail(KMX_EARG, "kmx_db_upload_share: bad rank / world");
+	const uint64_t n_tiles = (db->info.total_kmers + kTile - 1) / kTile;
+	const uint64_t lo = n_tiles * (uint64_t)rank / (uint64_t)world, hi = n_tiles * (uint64_t)(rank + 1) / (uint64_t)world;
+	const int cores = (int)std::thread::hardware_concurrency();
+	return db_upload_range(db, lo * kTile, hi * kTile, std::max(2, cores / world));
 }
 
 extern "C" void kmx_db_close(kmx_db* db) {
@@ -768,10 +718,10 @@ extern "C" void kmx_db_close(kmx_db* db) {
 	delete db;
 }
 
-static DevDb dev_db(const kmx_db* db) {
+DevDb kmx::dev_db(const kmx_db* db) {
 	DevDb d;
 	memset(&d, 0, sizeof(d));
-	d.suf = db->d_suf;
+	d.suf = db->d_suf - db->rec_lo * db->info.record_bytes;      // indexed by the global record number; only [rec_lo, rec_hi) is touched
 	d.lut = db->d_lut;
 	d.lut_entries = db->info.lut_entries;
 	d.total = db->info.total_kmers;
@@ -805,10 +755,11 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 		~Release() { ctx_release(x); }
 	} release{ x };
 	cudaStream_t s = x->stream;
-	DA(&d_cnt, n_tiles * 4, s);
-	DA(&d_off, (n_tiles + 1) * 8, s);
-	DA(&d_k, total * 8, s);
-	DA(&d_c, total * 4, s);
+	DevScope scope(s);                                    // frees on every return path
+	if ((rc = scope.alloc(&d_cnt, n_tiles * 4))) return rc;
+	if ((rc = scope.alloc(&d_off, (n_tiles + 1) * 8))) return rc;
+	if ((rc = scope.alloc(&d_k, total * 8))) return rc;
+	if ((rc = scope.alloc(&d_c, total * 4))) return rc;
 	DevDb d = dev_db(db);
 	CU(launch_list_count(d, d_cnt, db->sm_count, s));
 	CU(launch_tile_scan(d_cnt, n_tiles, d_off, s));
@@ -819,19 +770,17 @@ extern "C" int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64
 	CU(cudaMemcpyAsync(kmers, d_k, listed * 8, cudaMemcpyDeviceToHost, s));
 	CU(cudaMemcpyAsync(counts, d_c, listed * 4, cudaMemcpyDeviceToHost, s));
 	CU(cudaStreamSynchronize(s));
-	dev_free(d_cnt, s); dev_free(d_off, s); dev_free(d_k, s); dev_free(d_c, s);
-	CU(cudaStreamSynchronize(s));
 	*n_out = listed;
 	return KMX_OK;
 }
 
 // =========================================================================================
-// build: KModel::init (kmodel.hpp:57-86), in stages so that the multi-GPU path can interleave
-// its exchanges:  encode (count + Bloom + item stream)  ->  insert  ->  rest table
+// build: KModel::init (kmodel.hpp:57-86), in stages (kmx_team.cu interleaves its exchanges with them):
+//   encode (count + Bloom + item stream)  ->  insert  ->  rest table
 // =========================================================================================
 // bucket index over the top key bits (about one entry per bucket) + the per-prefix false-hit table
 // that reproduces the inclusive upper bound of KRestData::check_kmer (rest.hpp:233-237)
-static int build_rest_side_tables(kmx_model* m) {
+int kmx::build_rest_side_tables(kmx_model* m) {
 	const RestHost& r = m->rest;
 	cudaStream_t s = m->x->stream;
 	int bits = 8;
@@ -861,20 +810,20 @@ static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uin
 	int32_t* d_first = nullptr;
 	int32_t* d_groups = nullptr;
 	void* d_temp = nullptr;
-	size_t temp_bytes = 0;
-	DA(&d_first, (size_t)r.map_size * 4, s);
-	DA(&d_groups, 4, s);
-	CU(rest_sort_bytes(n, &temp_bytes));
-	if (temp_bytes) DA(&d_temp, temp_bytes, s);
-	CU(launch_rest_sort(d_temp, temp_bytes, d_surv_kmer, m->d_rest_keys, d_surv_occ, m->d_rest_counts, n, 2 * m->k, s));
+	DevScope scope(s);
+	int rc;
+	if ((rc = scope.alloc(&d_first, (size_t)r.map_size * 4))) return rc;
+	if ((rc = scope.alloc(&d_groups, 4))) return rc;
+	const size_t temp_bytes = radix_sort_temp_bytes(n);
+	if (temp_bytes && (rc = scope.alloc(&d_temp, temp_bytes))) return rc;
+	CU(launch_radix_sort_pairs(d_temp, d_surv_kmer, m->d_rest_keys, d_surv_occ, (uint32_t*)m->d_rest_counts, n, 2 * m->k, s));
 	CU(launch_rest_index(m->d_rest_keys, n, 2 * (m->k - r.pre_len), r.map_size, d_first, m->d_hash2index, m->d_pre_buffer, d_groups, s));
 	CU(cudaMemcpyAsync(h_groups, d_groups, 4, cudaMemcpyDeviceToHost, s));
-	dev_free(d_first, s); dev_free(d_groups, s); dev_free(d_temp, s);
 	return KMX_OK;
 }
 
-// Exchange slabs and peer mappings are kept for the life of the process: cudaMalloc / cudaFree and
-// cudaIpcOpenMemHandle cost milliseconds each, a rebuild with the same geometry reuses them.
+// cudaMalloc blocks other GPUs map are kept for the life of the process: cudaMalloc / cudaFree and cudaIpcOpenMemHandle cost
+// milliseconds each, a rebuild with the same geometry reuses them (and the mappings its peers hold stay valid).
 namespace {
 struct CachedSlab {
 	void* ptr;
@@ -883,10 +832,9 @@ struct CachedSlab {
 };
 std::mutex g_slab_mu;
 std::vector<CachedSlab> g_slab_free;
-std::map<std::string, void*> g_ipc_open;             // 64 handle bytes -> mapping in this process
 }  // namespace
 
-static int slab_acquire(void** out, size_t bytes, int device) {
+int kmx::slab_acquire(void** out, size_t bytes, int device) {
 	{
 		std::lock_guard<std::mutex> lock(g_slab_mu);
 		for (size_t q = 0; q < g_slab_free.size(); q++) {
@@ -896,82 +844,53 @@ static int slab_acquire(void** out, size_t bytes, int device) {
 				return KMX_OK;
 			}
 		}
+		// nothing of this size: give the memory of other cached sizes on this device back before asking for more
+		for (size_t q = 0; q < g_slab_free.size();) {
+			if (g_slab_free[q].device == device) {
+				cudaFree(g_slab_free[q].ptr);
+				g_slab_free.erase(g_slab_free.begin() + q);
+			} else {
+				q++;
+			}
+		}
 	}
 	CU(cudaMalloc(out, bytes));
 	return KMX_OK;
 }
 
-static void slab_release(void* ptr, size_t bytes, int device) {
+void kmx::slab_release(void* ptr, size_t bytes, int device) {
 	std::lock_guard<std::mutex> lock(g_slab_mu);
 	g_slab_free.push_back(CachedSlab{ ptr, bytes, device });
 }
 
-// the filters move from the exchange slab into allocations of their own (the slab goes back to the cache)
-static int filters_leave_slab(kmx_model* m) {
-	BuildState& b = m->bs;
-	if (!b.fslab) return KMX_OK;
-	cudaStream_t s = m->x->stream;
-	auto move = [&](uint32_t** p, uint64_t bytes) -> int {
-		uint32_t* fresh = nullptr;
-		DA(&fresh, pad8(bytes), s);
-		CU(cudaMemcpyAsync(fresh, *p, pad8(bytes), cudaMemcpyDeviceToDevice, s));
-		*p = fresh;
-		return KMX_OK;
-	};
-	for (int i = 0; i < m->bf_num; i++) {
-		int rc = move(&m->d_bf[i], m->bytes[i]);
-		if (!rc) rc = move(&m->d_bf_back[i], m->bytes[3 + i]);
-		if (rc) return rc;
-	}
-	int rc = move(&m->d_km_back, m->bytes[7]);
-	if (rc) return rc;
-	CU(cudaStreamSynchronize(s));
-	slab_release(b.fslab, b.fslab_bytes, m->device);
-	b.fslab = nullptr;
-	fill_dev_model(m);
-	return KMX_OK;
-}
-
-static void build_state_free(kmx_model* m) {
+void kmx::build_state_free(kmx_model* m) {
 	BuildState& b = m->bs;
 	if (!m->x) return;
 	cudaStream_t s = m->x->stream;
 	InsertArgs& a = b.a;
-	if (b.fslab) {                                        // a build that failed half-way: the filters still point into the slab
-		cudaStreamSynchronize(s);
-		for (int i = 0; i < 3; i++) m->d_bf[i] = m->d_bf_back[i] = nullptr;
-		m->d_km_back = nullptr;
-		slab_release(b.fslab, b.fslab_bytes, m->device);
-		b.fslab = nullptr;
-	}
-	dev_free(b.d_item_kmer, s);
-	dev_free(b.d_item_occ, s);
-	if (!b.slab) {
+	const bool team = b.team != nullptr;
+	if (team) team_state_free(m);                         // item shard, ping-pong buffers, control block, survivor list live in its slab
+	if (!team) {
+		dev_free(b.d_item_kmer, s);
+		dev_free(b.d_item_occ, s);
 		for (int q = 0; q < 2; q++) {
 			dev_free(a.buf_kmer[q], s);
 			dev_free(a.buf_occ[q], s);
 		}
 		dev_free(a.ctl, s);
+		dev_free(a.rest_kmer, s);
+		dev_free(a.rest_occ, s);
 	}
 	dev_free(a.status, s); dev_free(a.excl_rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.list[2], s);
 	dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.claim, s);
-	dev_free(a.rest_kmer, s); dev_free(a.rest_occ, s);
-	if (b.slab) {
-		cudaStreamSynchronize(s);
-		slab_release(b.slab, b.slab_bytes, m->device);
-	}
 	b = BuildState();
 }
 
 // stage 1: pass 1 (class histogram, kmodel.hpp:423-434), filter allocation (kmodel.hpp:402-456),
 // pass 2 (Bloom inserts + array-bound stream, kmodel.hpp:68-74)
-// dist_world > 1: this rank inserts the Bloom-bound records of its share of the tiles only (the partial filters are OR-ed
-// afterwards, kmx_dist_merge) and writes the item stream only if stream_items (ranks that own a coupled array)
-static int build_stage_encode(kmx_model* m, kmx_db* db, int dist_rank = 0, int dist_world = 1, bool stream_items = true) {
+static int build_stage_encode(kmx_model* m, kmx_db* db) {
 	BuildState& b = m->bs;
 	b.wall0 = std::chrono::high_resolution_clock::now();
-	b.world = dist_world;
-	b.dist_rank = dist_rank;
 	int rc = model_attach_device(m);
 	if (rc) return rc;
 	TRACE(b.wall0, "device attached");
@@ -980,6 +899,7 @@ static int build_stage_encode(kmx_model* m, kmx_db* db, int dist_rank = 0, int d
 	if (rc) return rc;
 	TRACE(b.wall0, "database on device");
 	if (db->device != m->device) return fail(KMX_EARG, "database is on device %d, model on device %d", db->device, m->device);
+	if (db->rec_lo != 0 || db->rec_hi != db->info.total_kmers) return fail(KMX_ESTATE, "only a share of the database is on the device (team build); KModel::init on one GPU needs all of it");
 	m->k = (int)db->info.k;
 	m->total_kmers = db->info.total_kmers;
 	if (m->k < 3) return fail(KMX_ERANGE, "k=%d: the (k-2)-mer filters need k >= 3", m->k);
@@ -993,12 +913,13 @@ static int build_stage_encode(kmx_model* m, kmx_db* db, int dist_rank = 0, int d
 	uint32_t* d_tile_cnt = nullptr;
 	uint64_t* d_tile_off = nullptr;
 	CountOut* d_count = nullptr;
-	DA(&d_tile_cnt, (n_tiles + 1) * 4, s);
-	DA(&d_tile_off, (n_tiles + 1) * 8, s);
-	DA(&d_count, sizeof(CountOut), s);
+	DevScope scope(s);
+	if ((rc = scope.alloc(&d_tile_cnt, (n_tiles + 1) * 4))) return rc;
+	if ((rc = scope.alloc(&d_tile_off, (n_tiles + 1) * 8))) return rc;
+	if ((rc = scope.alloc(&d_count, sizeof(CountOut)))) return rc;
 	CU(cudaEventRecord(ev[0], s));
 	CU(cudaMemsetAsync(d_count, 0, sizeof(CountOut), s));
-	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, m->sm_count, s));
+	CU(launch_count(d, m->ci, m->cs, m->bf_num, d_count, d_tile_cnt, 0, n_tiles, m->sm_count, s));
 	CU(launch_tile_scan(d_tile_cnt, n_tiles, d_tile_off, s));
 	CountOut& cnt = m->x->h_pinned->count;
 	CU(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, s));
@@ -1006,94 +927,70 @@ static int build_stage_encode(kmx_model* m, kmx_db* db, int dist_rank = 0, int d
 	TRACE(b.wall0, "count pass queued");
 	CU(cudaStreamSynchronize(s));                        // sync 1 of 3: the sizes depend on the counts
 	TRACE(b.wall0, "count pass done");
-	dev_free(d_tile_cnt, s);
-	dev_free(d_count, s);
-	if (cnt.bad_count) {
-		dev_free(d_tile_off, s);
+	if (cnt.bad_count)
 		return fail(KMX_ERANGE, "%llu records have a count below ci=%d or above cs=%d: the reference indexes out of bounds there (kmodel.hpp:427, occu_bin.hpp:70)",
 		            (unsigned long long)cnt.bad_count, m->ci, m->cs);
-	}
 	uint64_t bf_kmers = 0;
 	for (int i = 0; i < m->bf_num; i++) {
 		m->kmer_counts[i] = cnt.class_count[i];
 		bf_kmers += cnt.class_count[i];
 	}
 	m->km_kmers = total - bf_kmers;                       // kmodel.hpp:433: header total, not the listed count
-	rc = alloc_filters(m, dist_world > 1);
-	if (rc) {
-		dev_free(d_tile_off, s);
-		return rc;
-	}
+	if ((rc = alloc_filters(m))) return rc;
 	m->rest.k = m->k;
 	m->rest.pre_len = rest_prefix_len(m->k);
 	fill_dev_model(m);
-	if (dist_world > 1) CU(cudaStreamSynchronize(s));     // the filter slab is zeroed before its handle leaves this process
 
 	b.n_items = cnt.array_bound;
-	if (stream_items) {
-		DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
-		DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
-	}
-	const uint64_t tile_lo = n_tiles * (uint64_t)dist_rank / (uint64_t)dist_world, tile_hi = n_tiles * (uint64_t)(dist_rank + 1) / (uint64_t)dist_world;
-	CU(launch_encode(d, m->dm, d_tile_off, b.d_item_kmer, b.d_item_occ, tile_lo, tile_hi, stream_items, m->sm_count, s));
-	dev_free(d_tile_off, s);
+	DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
+	DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
+	ItemRoute route;
+	memset(&route, 0, sizeof(route));
+	route.kmer[0] = b.d_item_kmer;
+	route.occ[0] = b.d_item_occ;
+	route.base = 0;
+	route.n_active = 1;
+	route.n_bits = m->n_bits;
+	CU(launch_encode(d, m->dm, d_tile_off, route, 0, n_tiles, m->sm_count, s));
 	CU(cudaEventRecord(ev[2], s));
 	return KMX_OK;
 }
 
-// stage 2a: buffers of the greedy insert (kmodel.hpp:508-573).  shared = true puts the buffers
-// other GPUs write into (survivor ping-pong, control block, barrier flags) in one cudaMalloc
-// slab that can be exported with cudaIpcGetMemHandle.
-static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool shared) {
+// stage 2a: buffers of the greedy insert (kmodel.hpp:508-573).  team = true: the buffers other GPUs write into (item shard,
+// survivor ping-pong, control block, barrier flags, survivor list) were carved from the team's exchange slab by kmx_team.cu
+// and are already in m->bs.a; only the private scratch is allocated here.
+int kmx::build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool team) {
 	BuildState& b = m->bs;
 	cudaStream_t s = m->x->stream;
 	InsertArgs& a = b.a;
-	memset(&a, 0, sizeof(a));
+	if (!team) memset(&a, 0, sizeof(a));
 	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
 	b.n_batches = (b.n_items + batch_items - 1) / batch_items;
 	a.rank = rank;
 	a.n_active = n_active;
-	a.item_kmer = b.d_item_kmer;
-	a.item_occ = b.d_item_occ;
 	a.n_items = b.n_items;
-	if (shared) {
-		auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-		const size_t o_k0 = 0, o_k1 = o_k0 + up(batch_items * 8), o_o0 = o_k1 + up(batch_items * 8), o_o1 = o_o0 + up(batch_items * 4),
-		             o_ctl = o_o1 + up(batch_items * 4), o_flags = o_ctl + up(sizeof(InsertCtl));
-		b.slab_bytes = o_flags + up(kMaxRanks * 4);
-		{
-			int rc = slab_acquire(&b.slab, b.slab_bytes, m->device);
-			if (rc) return rc;
-		}
-		CU(cudaMemsetAsync((uint8_t*)b.slab + o_ctl, 0, b.slab_bytes - o_ctl, s));   // control block + barrier flags start at zero
-		b.off[0] = o_k0; b.off[1] = o_k1; b.off[2] = o_o0; b.off[3] = o_o1; b.off[4] = o_ctl; b.off[5] = o_flags;
-		uint8_t* base = (uint8_t*)b.slab;
-		a.buf_kmer[0] = (uint64_t*)(base + o_k0);
-		a.buf_kmer[1] = (uint64_t*)(base + o_k1);
-		a.buf_occ[0] = (uint32_t*)(base + o_o0);
-		a.buf_occ[1] = (uint32_t*)(base + o_o1);
-		a.ctl = (InsertCtl*)(base + o_ctl);
-		b.flags = (uint32_t*)(base + o_flags);
-		b.peer_slab[rank] = b.slab;
-	} else {
+	if (team && rank >= n_active) return KMX_OK;          // this rank owns no coupled array: it launches no insert kernel
+	if (!team) {
+		a.item_kmer = b.d_item_kmer;
+		a.item_occ = b.d_item_occ;
 		for (int q = 0; q < 2; q++) {
 			DA(&a.buf_kmer[q], batch_items * 8, s);
 			DA(&a.buf_occ[q], batch_items * 4, s);
 		}
 		DA(&a.ctl, sizeof(InsertCtl), s);
 		CU(cudaMemsetAsync(a.ctl, 0, sizeof(InsertCtl), s));
+		for (int q = 0; q < 2; q++) {
+			a.peer_buf_kmer[q][rank] = a.buf_kmer[q];
+			a.peer_buf_occ[q][rank] = a.buf_occ[q];
+		}
+		a.peer_ctl[rank] = a.ctl;
+		a.peer_flags[rank] = nullptr;
 	}
 	if (const char* e = getenv("KMX_TEST_EPOCH_START")) {    // lets a small test cross the epoch wrap-around
 		const unsigned int start = (unsigned int)atoi(e);
 		CU(cudaMemcpyAsync(&a.ctl->epoch, &start, sizeof(start), cudaMemcpyHostToDevice, s));
 		CU(cudaStreamSynchronize(s));
 	}
-	for (int q = 0; q < 2; q++) {
-		a.peer_buf_kmer[q][rank] = a.buf_kmer[q];
-		a.peer_buf_occ[q][rank] = a.buf_occ[q];
-	}
-	a.peer_ctl[rank] = a.ctl;
-	a.peer_flags[rank] = b.flags;
 	DA(&a.status, batch_items * 4, s);
 	DA(&a.excl_rank, batch_items * 4, s);
 	DA(&a.holepos, batch_items * 4, s);
@@ -1109,9 +1006,8 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	}
 	DA(&a.resv, (size_t)m->n_bits * 4 * a.resv_slots * 4, s);
 	CU(cudaMemsetAsync(a.resv, 0xFF, (size_t)m->n_bits * 4 * a.resv_slots * 4, s));
-	// contested items: merged reserve/commit passes (hc14 shape: insert 163 -> 155 ms, RS shape: 3.12 -> 3.08 ms); the
-	// multi-GPU build keeps the classic two-barrier iterations it was validated with on 8 GPUs
-	a.merged = n_active == 1 ? 1 : 0;
+	// contested items: merged reserve/commit passes (hc14 shape: insert 163 -> 155 ms, RS shape: 3.12 -> 3.08 ms)
+	a.merged = 1;
 	if (const char* e = getenv("KMX_MERGED_PASSES")) a.merged = atoi(e) ? 1 : 0;
 	a.claim_log2 = 25;
 	if (const char* e = getenv("KMX_CLAIM_LOG2")) {
@@ -1124,27 +1020,31 @@ static int build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool s
 	// for HBM-resident models (hc14 shape: 187 ms against 186 ms) and slower for L2-resident ones, so it stays off.
 	a.claim_first = 0;
 	if (const char* e = getenv("KMX_CLAIM_FIRST")) a.claim_first = atoi(e) ? 1 : 0;
-	// arrays + km_back well beyond the L2 (126 MB): their random sectors should not wash the insert's hot structures out of it
-	// (measured on the hc14 shape: evict-first cell loads + reductions 182 -> 168 ms; evict-first on km_back as well: 171 ms)
-	a.stream_cells = (2ULL * m->n_bits * m->bytes[6] + m->bytes[7]) > (192ULL << 20) ? 3 : 0;
+	// what THIS GPU probes (its share of the coupled arrays + its copy of km_back) well beyond the L2 (126 MB): those random
+	// sectors should not wash the insert's hot structures out of it (measured on the hc14 shape, one GPU: evict-first cell
+	// loads + reductions 182 -> 168 ms; evict-first on km_back as well: 171 ms)
+	const uint64_t my_arrays = n_active > 1 ? (uint64_t)buckets_per_batch(rank < n_active ? rank : 0, n_active, m->n_bits) : (uint64_t)m->n_bits;
+	a.stream_cells = (2ULL * my_arrays * m->bytes[6] + m->bytes[7]) > (192ULL << 20) ? 3 : 0;
 	if (const char* e = getenv("KMX_STREAM_CELLS")) a.stream_cells = atoi(e) & 15;
 	a.max_iterations = kBucket + 64;
 	a.phase_round = -1;
 	if (const char* e = getenv("KMX_PHASE_ROUND")) a.phase_round = atoi(e);
 	CU(insert_grid_size(&b.grid, m->sm_count));
-	// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
-	// all launches queue without a host round trip; beyond that it grows between launches.
-	b.worst_case = b.n_items <= (1ULL << 28) && !getenv("KMX_TEST_GROW_REST");   // the env var lets a small test take the growing path
-	b.rest_cap = b.worst_case ? b.n_items + m->n_bits : 0;
-	if (b.worst_case) {
-		DA(&a.rest_kmer, b.rest_cap * 8, s);
-		DA(&a.rest_occ, b.rest_cap * 4, s);
+	if (!team) {
+		// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
+		// all launches queue without a host round trip; beyond that it grows between launches.
+		b.worst_case = b.n_items <= (1ULL << 28) && !getenv("KMX_TEST_GROW_REST");   // the env var lets a small test take the growing path
+		b.rest_cap = b.worst_case ? b.n_items + m->n_bits : 0;
+		if (b.worst_case) {
+			DA(&a.rest_kmer, b.rest_cap * 8, s);
+			DA(&a.rest_occ, b.rest_cap * 4, s);
+		}
 	}
 	return KMX_OK;
 }
 
 // stage 2b: the launches (64 batches each); returns with the control block on the host
-static int build_stage_insert_run(kmx_model* m) {
+int kmx::build_stage_insert_run(kmx_model* m) {
 	BuildState& b = m->bs;
 	cudaStream_t s = m->x->stream;
 	InsertArgs& a = b.a;
@@ -1152,7 +1052,7 @@ static int build_stage_insert_run(kmx_model* m) {
 	memset(&ctl, 0, sizeof(ctl));
 	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
 	const bool participates = a.rank < a.n_active;
-	CU(cudaEventRecord(m->x->ev_build[5], s));           // the multi-GPU path spends host time between encode and here
+	CU(cudaEventRecord(m->x->ev_build[5], s));
 	if (b.n_items > 0 && participates) {
 		const uint64_t chunk = 64;                         // batches per launch
 		for (uint64_t b0 = 0; b0 < b.n_batches; b0 += chunk) {
@@ -1187,10 +1087,6 @@ static int build_stage_insert_run(kmx_model* m) {
 		CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 	}
 	CU(cudaEventRecord(m->x->ev_build[3], s));
-	TRACE(b.wall0, "encode + insert queued");
-	CU(cudaStreamSynchronize(s));                        // sync 2 of 3: the sort needs the survivor count
-	TRACE(b.wall0, "insert done");
-	if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow, 3: peer GPU timed out)", ctl.error);
 	return KMX_OK;
 }
 
@@ -1236,155 +1132,31 @@ extern "C" int kmx_init_from_db(kmx_model* m, kmx_db* db) {
 	int rc = build_stage_encode(m, db);
 	if (!rc) rc = build_stage_insert_setup(m, 0, 1, false);
 	if (!rc) rc = build_stage_insert_run(m);
+	if (!rc) {
+		TRACE(m->bs.wall0, "encode + insert queued");
+		if (cudaStreamSynchronize(m->x->stream) != cudaSuccess) rc = fail(KMX_ECUDA, "the build stream failed: %s", cudaGetErrorString(cudaGetLastError()));   // sync 2 of 3: the sort needs the survivor count
+		else if (m->x->h_pinned->ctl.error)
+			rc = fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow, 3: peer GPU timed out)", m->x->h_pinned->ctl.error);
+		TRACE(m->bs.wall0, "insert done");
+	}
 	if (!rc) rc = build_stage_finish(m, m->bs.a.rest_kmer, m->bs.a.rest_occ, m->x->h_pinned->ctl.rest_n);
 	if (rc) build_state_free(m);
 	return rc;
 }
 
+// KModel::init(db_file).  With more than one device selected (kmx_set_devices, or KMX_GPUS=N in the environment) the build is
+// spread over them inside this process (kmx_team.cu): one host thread per GPU, peer access instead of IPC, the model ends
+// up replicated and kmer_to_occ batches are sharded over the replicas.
 extern "C" int kmx_init_from_kmc(kmx_model* m, const char* db_base) {
 	if (!m) return fail(KMX_EARG, "null model");
 	int rc = require_gpu(nullptr);
 	if (rc) return rc;
+	const std::vector<int> devs = team_devices();
+	if (devs.size() >= 2) return team_build_in_process(m, db_base, devs);
 	kmx_db* db = kmx_db_open(db_base);
-	if (!db) return KMX_EIO;
+	if (!db) return last_error_code() ? last_error_code() : KMX_EIO;     // unreadable file vs. not a KMC database: kmx_db_open's own code
 	rc = kmx_init_from_db(m, db);
 	kmx_db_close(db);
-	return rc;
-}
-
-// ---- multi-GPU build, array-owner decomposition (option A) ----------------------
-// Every rank decodes the database and fills the Bloom filters (replicated: order-free and cheap);
-// the coupled arrays are split by ownership -- array a lives on rank a % n_active -- and the
-// persistent insert kernels of the ranks hand each bucket's survivors to the next owner through
-// peer-mapped buffers, with a flag barrier per round.  The caller (kmcex_b200/distributed.py)
-// moves IPC handles and, afterwards, the finished pieces with torch.distributed.
-extern "C" int kmx_dist_prepare(kmx_model* m, kmx_db* db, int rank, int n_active, int world, void* ipc_handles_out) {
-	if (!m || !db || !ipc_handles_out) return fail(KMX_EARG, "null argument");
-	if (m->built) return fail(KMX_ESTATE, "model already initialised (KModel::init is one-shot)");
-	if (n_active < 1 || n_active > kMaxRanks || n_active > m->n_bits || rank < 0) return fail(KMX_EARG, "n_active must be in 1..min(%d, n_bits)", kMaxRanks);
-	if (world < n_active || world > kMaxRanks || rank >= world) return fail(KMX_EARG, "world must be in n_active..%d and rank below it", kMaxRanks);
-	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
-	int rc = build_stage_encode(m, db, rank, world, rank < n_active);
-	if (!rc) rc = build_stage_insert_setup(m, rank, n_active, true);
-	if (!rc) {
-		CU(cudaStreamSynchronize(m->x->stream));         // the slabs are zeroed before anybody maps them
-		CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)ipc_handles_out, m->bs.slab));
-		memset((uint8_t*)ipc_handles_out + 64, 0, 64);
-		if (m->bs.fslab) CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)((uint8_t*)ipc_handles_out + 64), m->bs.fslab));
-	}
-	if (rc) build_state_free(m);
-	return rc;
-}
-
-static int ipc_map(const void* handle64, void** out) {
-	cudaIpcMemHandle_t h;
-	memcpy(&h, handle64, 64);
-	std::string key((const char*)&h, 64);
-	std::lock_guard<std::mutex> lock(g_slab_mu);
-	auto it = g_ipc_open.find(key);
-	if (it == g_ipc_open.end()) {
-		void* mapped = nullptr;
-		CU(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
-		it = g_ipc_open.emplace(key, mapped).first;
-	}
-	*out = it->second;
-	return KMX_OK;
-}
-
-extern "C" int kmx_dist_connect(kmx_model* m, const void* handles) {
-	if (!m || !handles || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
-	BuildState& b = m->bs;
-	InsertArgs& a = b.a;
-	const uint8_t* hs = (const uint8_t*)handles;
-	if (a.rank < a.n_active) {                             // an idle rank takes no part in the survivor exchange
-		for (int p = 0; p < a.n_active; p++) {
-			if (p != a.rank) {
-				int rc = ipc_map(hs + 128 * p, &b.peer_slab[p]);
-				if (rc) return rc;
-			}
-			uint8_t* base = (uint8_t*)b.peer_slab[p];
-			a.peer_buf_kmer[0][p] = (uint64_t*)(base + b.off[0]);
-			a.peer_buf_kmer[1][p] = (uint64_t*)(base + b.off[1]);
-			a.peer_buf_occ[0][p] = (uint32_t*)(base + b.off[2]);
-			a.peer_buf_occ[1][p] = (uint32_t*)(base + b.off[3]);
-			a.peer_ctl[p] = (InsertCtl*)(base + b.off[4]);
-			a.peer_flags[p] = (uint32_t*)(base + b.off[5]);
-		}
-	}
-	if (b.fslab) {                                         // every rank takes part in the filter merges
-		for (int p = 0; p < b.world; p++) {
-			if (p == b.dist_rank) b.peer_fslab[p] = b.fslab;
-			else {
-				int rc = ipc_map(hs + 128 * p + 64, &b.peer_fslab[p]);
-				if (rc) return rc;
-			}
-		}
-	}
-	return KMX_OK;
-}
-
-// OR all-reduce over the ranks of the Bloom filters (which = 0, after kmx_dist_prepare) or of km_back (which = 1, after
-// kmx_dist_insert): one kernel per rank, exchanges through peer memory, asynchronous on the model's stream
-extern "C" int kmx_dist_merge(kmx_model* m, int which) {
-	if (!m || !m->bs.fslab || !m->bs.peer_fslab[0]) return fail(KMX_ESTATE, "kmx_dist_prepare / kmx_dist_connect first");
-	BuildState& b = m->bs;
-	OrReduceArgs r;
-	memset(&r, 0, sizeof(r));
-	r.rank = b.dist_rank;
-	r.world = b.world;
-	const size_t off = which == 0 ? 0 : b.f_kmback_off, bytes = which == 0 ? b.f_bloom_bytes : b.f_kmback_bytes;
-	r.n_vec = bytes / 16;
-	for (int p = 0; p < b.world; p++) {
-		r.base[p] = (uint4*)((uint8_t*)b.peer_fslab[p] + off);
-		r.flags[p] = (uint32_t*)((uint8_t*)b.peer_fslab[p] + b.f_flags_off);
-	}
-	r.seq = b.fseq;
-	r.error = (unsigned int*)((uint8_t*)b.fslab + b.f_flags_off + 128);
-	b.fseq += 2;
-	CU(cudaSetDevice(m->device));
-	CU(launch_or_allreduce(r, m->sm_count, m->x->stream));
-	return KMX_OK;
-}
-
-extern "C" int kmx_dist_insert(kmx_model* m) {
-	if (!m || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
-	return build_stage_insert_run(m);
-}
-
-extern "C" int kmx_dist_buffers(kmx_model* m, kmx_dist_buffers_t* out) {
-	if (!m || !out || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
-	memset(out, 0, sizeof(*out));
-	out->n_bits = m->n_bits;
-	out->cell_bytes = (cell_words(m->bytes[6]) + 1) * 8;
-	for (int i = 0; i < m->n_bits; i++) out->cells[i] = m->d_cells[i];
-	out->km_back = m->d_km_back;
-	out->km_back_bytes = pad8(m->bytes[7]);
-	out->rest_kmer = m->bs.a.rest_kmer;
-	out->rest_occ = m->bs.a.rest_occ;
-	out->rest_n = m->x->h_pinned->ctl.rest_n;
-	out->insert_attempts = m->x->h_pinned->ctl.attempts;
-	out->insert_accepted = m->x->h_pinned->ctl.accepted;
-	return KMX_OK;
-}
-
-extern "C" int kmx_dist_finish(kmx_model* m, const uint64_t* d_rest_kmer, const uint32_t* d_rest_occ, uint64_t rest_n,
-                               uint64_t attempts, uint64_t accepted) {
-	if (!m || !m->bs.slab) return fail(KMX_ESTATE, "kmx_dist_prepare first");
-	if (rest_n && (!d_rest_kmer || !d_rest_occ)) return fail(KMX_EARG, "null survivor list");
-	m->x->h_pinned->ctl.attempts = attempts;
-	m->x->h_pinned->ctl.accepted = accepted;
-	CU(cudaDeviceSynchronize());                         // the caller's collectives ran on its own streams
-	if (m->bs.fslab) {
-		unsigned int err = 0;
-		CU(cudaMemcpy(&err, (uint8_t*)m->bs.fslab + m->bs.f_flags_off + 128, 4, cudaMemcpyDeviceToHost));
-		if (err) {
-			build_state_free(m);
-			return fail(KMX_ECUDA, "filter merge stopped: a peer GPU did not reach the barrier within 20 s");
-		}
-	}
-	int rc = filters_leave_slab(m);
-	if (!rc) rc = build_stage_finish(m, d_rest_kmer, d_rest_occ, rest_n);
-	if (rc) build_state_free(m);
 	return rc;
 }
 
@@ -1408,14 +1180,15 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 	std::string base(dir);
 	FILE* fh = fopen((base + "/header").c_str(), "w");
 	if (!fh) return fail(KMX_EIO, "cannot write %s/header (%s); the directory must exist (README.md:77)", dir, strerror(errno));
-	fprintf(fh, "number_hash %d\nnumber_bit %d\nci %d\ncs %d\n", m->n_hash, m->n_bits, m->ci, m->cs);   // kmodel.hpp:175-180
-	fclose(fh);
+	const bool header_ok = fprintf(fh, "number_hash %d\nnumber_bit %d\nci %d\ncs %d\n", m->n_hash, m->n_bits, m->ci, m->cs) > 0;   // kmodel.hpp:175-180
+	if (fclose(fh) != 0 || !header_ok) return fail(KMX_EIO, "cannot write %s/header (%s)", dir, strerror(errno));
 	FILE* f = fopen((base + "/km.bin").c_str(), "wb");
 	if (!f) return fail(KMX_EIO, "cannot write %s/km.bin (%s)", dir, strerror(errno));
 	std::vector<uint8_t> tmp;
 	int rc = KMX_OK;
-	fwrite(&m->km_kmers, 8, 1, f);
-	for (int i = 0; i < m->bf_num; i++) fwrite(&m->kmer_counts[i], 8, 1, f);
+	bool head_ok = fwrite(&m->km_kmers, 8, 1, f) == 1;
+	for (int i = 0; i < m->bf_num; i++) head_ok = head_ok && fwrite(&m->kmer_counts[i], 8, 1, f) == 1;
+	if (!head_ok) rc = fail(KMX_EIO, "short write on %s/km.bin (%s)", dir, strerror(errno));
 	for (int i = 0; i < m->bf_num && !rc; i++) {
 		rc = write_device(f, m->d_bf[i], m->bytes[i], tmp);
 		if (!rc) rc = write_device(f, m->d_bf_back[i], m->bytes[3 + i], tmp);
@@ -1437,6 +1210,7 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 	}
 	cudaFree(d_val);
 	cudaFree(d_tag);
+	if (!rc && (fflush(f) != 0 || ferror(f))) rc = fail(KMX_EIO, "write error on %s/km.bin (%s)", dir, strerror(errno));
 	if (fclose(f) != 0 && !rc) rc = fail(KMX_EIO, "close %s/km.bin (%s)", dir, strerror(errno));
 	if (rc) return rc;
 
@@ -1457,13 +1231,15 @@ extern "C" int kmx_save(kmx_model* m, const char* dir) {
 	FILE* fr = fopen((base + "/rest.bin").c_str(), "wb");
 	if (!fr) return fail(KMX_EIO, "cannot write %s/rest.bin (%s)", dir, strerror(errno));
 	int32_t hdr[4] = { r.k, r.pre_len, r.map_size, r.pre_buffer_size };
-	fwrite(hdr, 4, 4, fr);
-	fwrite(&r.suff_bin_size, 8, 1, fr);
-	fwrite(&r.count, 8, 1, fr);
-	fwrite(h2i.data(), 4, h2i.size(), fr);
-	fwrite(pre.data(), 4, pre.size(), fr);
-	fwrite(suffix.data(), 1, suffix.size(), fr);
-	fwrite(counts.data(), 4, counts.size(), fr);
+	bool ok = fwrite(hdr, 4, 4, fr) == 4 && fwrite(&r.suff_bin_size, 8, 1, fr) == 1 && fwrite(&r.count, 8, 1, fr) == 1 &&
+	          fwrite(h2i.data(), 4, h2i.size(), fr) == h2i.size() && fwrite(pre.data(), 4, pre.size(), fr) == pre.size() &&
+	          fwrite(suffix.data(), 1, suffix.size(), fr) == suffix.size() && fwrite(counts.data(), 4, counts.size(), fr) == counts.size() &&
+	          fflush(fr) == 0 && !ferror(fr);
+	if (!ok) {
+		const int err = errno;
+		fclose(fr);
+		return fail(KMX_EIO, "short write on %s/rest.bin (%s)", dir, strerror(err));
+	}
 	if (fclose(fr) != 0) return fail(KMX_EIO, "close %s/rest.bin (%s)", dir, strerror(errno));
 	return KMX_OK;
 }
@@ -1622,19 +1398,20 @@ static int query_device(kmx_model* m, const void* d_in, size_t stride, size_t n,
 	cudaStream_t s = stream ? (cudaStream_t)stream : m->x->stream;
 	const size_t step = 1u << 24;
 	DeferredQuery* d_defer = nullptr;
-	unsigned int* d_defer_n = nullptr;
+	unsigned int* d_counters = nullptr;
 	uint64_t* d_packed = nullptr;
-	DA(&d_defer, std::min(n, step) * sizeof(DeferredQuery), s);
-	DA(&d_defer_n, sizeof(unsigned int), s);
-	if (ASCII) DA(&d_packed, std::min(n, step) * 8, s);
+	uint32_t* d_dirty = nullptr;
+	DevScope scope(s);                                    // the scratch goes back to the pool on every return path
+	int rc;
+	if ((rc = scope.alloc(&d_defer, std::min(n, step) * sizeof(DeferredQuery)))) return rc;
+	if ((rc = scope.alloc(&d_counters, 2 * sizeof(unsigned int)))) return rc;
+	if (ASCII && (rc = scope.alloc(&d_packed, std::min(n, step) * 8))) return rc;
+	if (ASCII && (rc = scope.alloc(&d_dirty, std::min(n, step) * 4))) return rc;
 	for (size_t off = 0; off < n; off += step) {
 		const size_t cnt = std::min(step, n - off);
-		if (ASCII) CU(launch_query_ascii(m->dm, (const char*)d_in + off * stride, stride, cnt, d_out + off, d_packed, d_defer, d_defer_n, m->sm_count, s));
-		else CU(launch_query_packed(m->dm, (const uint64_t*)d_in + off, cnt, d_out + off, nullptr, d_defer, d_defer_n, m->sm_count, s));
+		if (ASCII) CU(launch_query_ascii(m->dm, (const char*)d_in + off * stride, stride, cnt, d_out + off, d_packed, d_defer, d_dirty, d_counters, m->sm_count, s));
+		else CU(launch_query_packed(m->dm, (const uint64_t*)d_in + off, cnt, d_out + off, nullptr, d_defer, d_counters, m->sm_count, s));
 	}
-	dev_free(d_defer, s);
-	dev_free(d_defer_n, s);
-	dev_free(d_packed, s);
 	return KMX_OK;
 }
 
@@ -1669,7 +1446,8 @@ static int ensure_staging(kmx_model* m, size_t item_bytes, bool need_h_in, bool 
 			DA(&x->d_out[s], items * 4, x->stream);
 			DA(&x->d_pack[s], items * 8, x->stream);
 			DA(&x->d_defer[s], items * sizeof(DeferredQuery), x->stream);
-			DA(&x->d_defer_n[s], sizeof(unsigned int), x->stream);
+			DA(&x->d_dirty[s], items * 4, x->stream);
+			DA(&x->d_defer_n[s], 2 * sizeof(unsigned int), x->stream);
 			fresh = true;
 		}
 	}
@@ -1689,10 +1467,7 @@ static bool is_pinned(const void* p) {
 
 // host buffers -> device in steps of 4 Mi queries, two slots on two streams so that the copy of
 // step i+1 overlaps the kernel and the read-back of step i; pinned caller buffers skip staging
-static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t stride, size_t n, int32_t* out, int32_t* path, bool ascii) {
-	if (!m || (n && (!in || (!out && !path)))) return fail(KMX_EARG, "null argument");
-	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
-	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
+static int query_host_one(kmx_model* m, const void* in, size_t item_bytes, size_t stride, size_t n, int32_t* out, int32_t* path, bool ascii) {
 	if (n == 0) return KMX_OK;
 	std::lock_guard<std::mutex> lock(m->x->query_mu);       // kmer_to_occ may be called from several threads (kmodel.hpp:90-98 is read-only)
 	CU(cudaSetDevice(m->device));
@@ -1717,7 +1492,7 @@ static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t st
 			h_src = m->x->h_in[slot];
 		}
 		CU(cudaMemcpyAsync(m->x->d_in[slot], h_src, cnt * item_bytes, cudaMemcpyHostToDevice, st[slot]));
-		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->x->d_in[slot], stride, cnt, m->x->d_out[slot], m->x->d_pack[slot], m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
+		if (ascii) CU(launch_query_ascii(m->dm, (const char*)m->x->d_in[slot], stride, cnt, m->x->d_out[slot], m->x->d_pack[slot], m->x->d_defer[slot], m->x->d_dirty[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
 		else CU(launch_query_packed(m->dm, (const uint64_t*)m->x->d_in[slot], cnt, path ? nullptr : m->x->d_out[slot], path ? m->x->d_out[slot] : nullptr,
 		                            m->x->d_defer[slot], m->x->d_defer_n[slot], m->sm_count, st[slot]));
 		CU(cudaMemcpyAsync(out_pinned ? (void*)(res + off) : (void*)m->x->h_out[slot], m->x->d_out[slot], cnt * 4, cudaMemcpyDeviceToHost, st[slot]));
@@ -1731,6 +1506,31 @@ static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t st
 			if (!out_pinned) memcpy(res + done_off[s], m->x->h_out[s], done_n[s] * 4);
 		}
 	}
+	return KMX_OK;
+}
+
+// A model built over several GPUs inside this process (kmx_set_devices / KMX_GPUS) is replicated on each of them: the batch
+// is split into contiguous shards, one host thread per replica (SURVEY.md 8e "Query": no per-query communication)
+static int query_host(kmx_model* m, const void* in, size_t item_bytes, size_t stride, size_t n, int32_t* out, int32_t* path, bool ascii) {
+	if (!m || (n && (!in || (!out && !path)))) return fail(KMX_EARG, "null argument");
+	if (!m->built) return fail(KMX_ESTATE, "model is not initialised");
+	if (n > 0x7FFFFFFFULL) return fail(KMX_ERANGE, "batch of %zu: the reference's loop index is an int (kmodel.hpp:91)", n);
+	const size_t n_rep = 1 + m->replicas.size();
+	if (n_rep == 1 || n < (size_t)1 << 16) return query_host_one(m, in, item_bytes, stride, n, out, path, ascii);
+	std::vector<int> rcs(n_rep, KMX_OK);
+	std::vector<std::string> msgs(n_rep);
+	std::vector<std::thread> pool;
+	auto part = [&](size_t r) {
+		kmx_model* rep = r == 0 ? m : m->replicas[r - 1];
+		const size_t lo = n * r / n_rep, hi = n * (r + 1) / n_rep;
+		rcs[r] = query_host_one(rep, (const uint8_t*)in + lo * item_bytes, item_bytes, stride, hi - lo, out ? out + lo : nullptr, path ? path + lo : nullptr, ascii);
+		if (rcs[r]) msgs[r] = last_error();
+	};
+	for (size_t r = 1; r < n_rep; r++) pool.emplace_back(part, r);
+	part(0);
+	for (auto& t : pool) t.join();
+	for (size_t r = 0; r < n_rep; r++)
+		if (rcs[r]) return fail(rcs[r], "replica %zu: %s", r, msgs[r].c_str());
 	return KMX_OK;
 }
 

@@ -45,6 +45,16 @@ struct QueryHashes {
 		HashPrep p29;
 		hash_prepare(r, c.k(), p31);
 		hash_prepare(middle_r(r, c.k()), c.k() - 2, p29);
+		finish(c, p29);
+	}
+	// from the raw characters of the string: kmer and kmer.substr(1, k - 2) (kmodel.hpp:388)
+	__device__ __forceinline__ void compute_bytes(const QueryCfg<K, H, B>& c, const uint8_t* s) {
+		HashPrep p29;
+		hash_prepare_bytes(s, c.k(), p31);
+		hash_prepare_bytes(s + 1, c.k() - 2, p29);
+		finish(c, p29);
+	}
+	__device__ __forceinline__ void finish(const QueryCfg<K, H, B>& c, const HashPrep& p29) {
 #pragma unroll
 		for (int j = 0; j < kHmax(H) - 1; j++)
 			if (j < c.h() - 1) h31[j] = hash_finish(p31, c.k(), c_seeds[j]);
@@ -288,16 +298,12 @@ __device__ __forceinline__ int rest_finish(const DevRest& R, uint64_t v, const R
 
 __device__ __forceinline__ int rest_lookup_indexed(const DevRest& R, uint64_t v) { return rest_finish(R, v, rest_begin(R, v)); }
 
-// get_candidates (kmodel.hpp:326-342) for one neighbour; returns -1 when it adds nothing
+// get_candidates (kmodel.hpp:326-342) for one neighbour in canonical form v with its hashes q; returns -1 when it adds nothing
 template <int K, int H, int B>
-__device__ __forceinline__ int neighbour_candidate(const DevModel& m, uint64_t nb) {
+__device__ __forceinline__ int neighbour_candidate_q(const DevModel& m, uint64_t v, const QueryHashes<K, H, B>& q) {
 	QueryCfg<K, H, B> c(m);
-	uint64_t r;
-	const uint64_t v = canonical(nb, c.k(), &r);
 	int occ = rest_lookup_indexed(m.rest, v);
 	if (occ > 0) return (int)__ldg(m.occ2bin + (occ > m.cs ? m.cs : occ));   // occ > cs is out of bounds in the reference
-	QueryHashes<K, H, B> q;
-	q.compute(c, r);
 	occ = check_all_bf(c, q);
 	if (occ != 0) return occ;
 	if (!check_km_back(c, q)) return -1;
@@ -310,6 +316,16 @@ __device__ __forceinline__ int neighbour_candidate(const DevModel& m, uint64_t n
 	for (int i = 0; i < kBmax(B); i++)
 		if (i < c.b() && full[i] && (result <= 0)) result = bins[i];
 	return result;
+}
+
+template <int K, int H, int B>
+__device__ __forceinline__ int neighbour_candidate(const DevModel& m, uint64_t nb) {
+	QueryCfg<K, H, B> c(m);
+	uint64_t r;
+	const uint64_t v = canonical(nb, c.k(), &r);
+	QueryHashes<K, H, B> q;
+	q.compute(c, r);
+	return neighbour_candidate_q<K, H, B>(m, v, q);
 }
 
 // neighbour number j of the canonical k-mer v (kmodel.hpp:344-359): j < 4 successors (drop the
@@ -333,13 +349,14 @@ __device__ __forceinline__ int bin_to_mean(const QueryCfg<K, H, B>& c, int bin) 
 	return bin < (1 << c.h()) ? __ldg(c.m.bin2mean + bin) : 0;   // unordered_map::operator[] yields 0 for a missing bin
 }
 
-template <int K, int H, int B>
-__device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uint64_t r, Primary& P) {
+template <int K, int H, int B, bool RAW = false>
+__device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uint64_t r, Primary& P, const uint8_t* raw = nullptr) {
 	QueryCfg<K, H, B> c(m);
 	// the rest lookup's loads and the Bloom wave are independent of each other
 	const RestProbe rp = rest_begin(m.rest, v);
 	QueryHashes<K, H, B> q;
-	q.compute(c, r);
+	if (RAW) q.compute_bytes(c, raw);
+	else q.compute(c, r);
 	const bool in_back = check_km_back(c, q);
 	P.occ = check_all_bf(c, q);
 	const int rest = rest_finish(m.rest, v, rp);
@@ -375,8 +392,30 @@ __device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uin
 // 2-bit encode of ASCII k-mers (tools.hpp:63-76: bytes other than C/G/T encode as A).  A block stages the
 // contiguous bytes of its 256 k-mers in shared memory with coalesced 16-byte loads (a thread reading its own
 // k-mer straight from global memory would issue k byte loads at a stride of `stride` bytes across the warp).
+// A string with a byte outside "ACGT" (N, lower case, ...) is also listed in `dirty`: the reference hashes the RAW
+// characters of such a string when its forward orientation is the canonical one (tools.hpp:160-167), which the packed
+// path cannot reproduce; query_raw_kernel answers those afterwards.
 constexpr int kPackMaxStride = 64;
-__global__ void __launch_bounds__(256) ascii_pack_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed) {
+
+__device__ __forceinline__ uint64_t pack_bytes(const uint8_t* p, int k, bool* dirty) {
+	uint64_t v = 0;
+	bool bad = false;
+	for (int i = 0; i < k; i++) {
+		const uint8_t ch = p[i];
+		const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
+		bad |= code == 0 && ch != 'A';
+		v = (v << 2) | code;
+	}
+	*dirty = bad;
+	return v;
+}
+
+__device__ __forceinline__ void note_dirty(uint32_t index, uint32_t* dirty, unsigned int* dirty_n) {
+	dirty[atomicAdd(dirty_n, 1u)] = index;                   // rare: no aggregation
+}
+
+__global__ void __launch_bounds__(256) ascii_pack_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed,
+                                                         uint32_t* __restrict__ dirty, unsigned int* __restrict__ dirty_n) {
 	__shared__ uint4 s_buf[256 * kPackMaxStride / 16 + 1];
 	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_buf);
 	for (size_t base = (size_t)blockIdx.x * 256; base < n; base += (size_t)gridDim.x * 256) {
@@ -393,29 +432,96 @@ __global__ void __launch_bounds__(256) ascii_pack_kernel(const char* __restrict_
 		}
 		__syncthreads();
 		if (threadIdx.x < cnt) {
-			const uint8_t* p = s_bytes + head + threadIdx.x * stride;
-			uint64_t v = 0;
-			for (int i = 0; i < k; i++) {
-				const uint8_t ch = p[i];
-				const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
-				v = (v << 2) | code;
-			}
-			packed[base + threadIdx.x] = v;
+			bool bad;
+			packed[base + threadIdx.x] = pack_bytes(s_bytes + head + threadIdx.x * stride, k, &bad);
+			if (bad) note_dirty((uint32_t)(base + threadIdx.x), dirty, dirty_n);
 		}
 	}
 }
 
 // fallback for strides beyond the staging buffer: one thread per k-mer, straight from global memory
-__global__ void ascii_pack_wide_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed) {
+__global__ void ascii_pack_wide_kernel(const char* __restrict__ flat, size_t stride, size_t n, int k, uint64_t* __restrict__ packed,
+                                       uint32_t* __restrict__ dirty, unsigned int* __restrict__ dirty_n) {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		const char* p = flat + i * stride;
-		uint64_t v = 0;
-		for (int j = 0; j < k; j++) {
-			const char ch = p[j];
-			const uint64_t code = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0;
-			v = (v << 2) | code;
+		bool bad;
+		packed[i] = pack_bytes(reinterpret_cast<const uint8_t*>(flat + i * stride), k, &bad);
+		if (bad) note_dirty((uint32_t)i, dirty, dirty_n);
+	}
+}
+
+// ---- queries that keep characters outside "ACGT" --------------------------------------------------
+// The reference never validates a query.  get_min_kmer (tools.hpp:160-167) 2-bit encodes the string with every byte that
+// is not C/G/T read as A (tools.hpp:63-76), and returns THE ORIGINAL STRING when that encoding is <= its reverse
+// complement, else the decoded reverse complement.  The rest lookup re-encodes the returned string (rest.hpp:22-34,223-251),
+// but the Bloom / km_back / coupled-array hashes run over its raw bytes, N and lower case included (kmodel.hpp:373-390,
+// 625-646); the neighbours are built from the same characters (kmodel.hpp:344-359) and canonicalised again.  One thread per
+// such query, generic geometry: the path is rare (reads with N) and only has to be right.
+__device__ __forceinline__ uint64_t raw_canonical(uint8_t* s, int k) {
+	bool bad;
+	const uint64_t u = pack_bytes(s, k, &bad);
+	const uint64_t rc = (~reverse_bases(u, k)) & mask2(k);
+	if (u <= rc) return u;                                   // the string stays as it is
+	for (int i = k - 1, sh = 0; i >= 0; i--, sh += 2) s[i] = (uint8_t)("ACGT"[(rc >> sh) & 3]);   // tools.hpp:90-100
+	return rc;
+}
+
+__global__ void __launch_bounds__(64) query_raw_kernel(const __grid_constant__ DevModel m, const char* __restrict__ flat, size_t stride,
+                                                       const uint32_t* __restrict__ dirty, const unsigned int* __restrict__ dirty_n,
+                                                       int32_t* __restrict__ out) {
+	QueryCfg<0, 0, 0> c(m);
+	const int k = m.k;
+	const unsigned int n = *dirty_n;
+	for (unsigned int x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+		const uint32_t index = dirty[x];
+		uint8_t s[32], t[32];
+		for (int i = 0; i < k; i++) s[i] = (uint8_t)flat[(size_t)index * stride + i];
+		const uint64_t v = raw_canonical(s, k);
+		Primary P;
+		query_primary<0, 0, 0, true>(m, v, 0, P, s);
+		if (P.path < 5) {
+			out[index] = P.answer;
+			continue;
 		}
-		packed[i] = v;
+		// kmer_to_bin's neighbour rules (kmodel.hpp:286-323) over the 8 neighbours of the (possibly raw) canonical string
+		int n_cand = 0, n_low = 0, dist[kMaxArrays];
+		for (int i = 0; i < kMaxArrays; i++) dist[i] = 2 << 20;
+		for (int j = 0; j < 8; j++) {
+			if (j < 4) {
+				for (int i = 0; i + 1 < k; i++) t[i] = s[i + 1];
+				t[k - 1] = (uint8_t)("ACGT"[j]);
+			} else {
+				for (int i = 1; i < k; i++) t[i] = s[i - 1];
+				t[0] = (uint8_t)("ACGT"[j - 4]);
+			}
+			const uint64_t nv = raw_canonical(t, k);
+			QueryHashes<0, 0, 0> q;
+			q.compute_bytes(c, t);
+			const int cand = neighbour_candidate_q<0, 0, 0>(m, nv, q);
+			if (cand < 0) continue;
+			n_cand++;
+			n_low += cand < m.ci + m.bf_num ? 1 : 0;
+			for (int i = 0; i < P.nc; i++) {
+				int d = P.cands[i] - cand;
+				d = d < 0 ? -d : d;
+				dist[i] = d < dist[i] ? d : dist[i];
+			}
+		}
+		int bin;
+		if (P.nc == 1) {
+			bin = (n_low >= n_cand / 2) ? P.occ : P.cands[0];
+		} else if (n_cand <= 0) {
+			bin = 0;
+		} else {
+			int min_dist = 2 << 20;
+			bin = P.cands[0];
+			for (int i = 0; i < P.nc; i++) {
+				if (min_dist > dist[i]) {
+					min_dist = dist[i];
+					bin = P.cands[i];
+				}
+			}
+		}
+		out[index] = bin_to_mean(c, bin);
 	}
 }
 
@@ -554,6 +660,7 @@ __global__ void rest_quirk_kernel(const uint64_t* __restrict__ keys, uint64_t n,
 cudaError_t launch_rest_side_tables(const DevRest& R, int map_size, uint32_t* d_fine, uint64_t* d_quirk_suffix, uint32_t* d_quirk_index,
                                     cudaStream_t stream) {
 	const uint32_t n_buckets = 1u << R.fine_bits;
+	note_launch(2);
 	rest_fine_kernel<<<(n_buckets + 256) / 256, 256, 0, stream>>>(R.keys, (uint32_t)R.count, R.fine_shift, n_buckets, d_fine);
 	rest_quirk_kernel<<<(map_size + 255) / 256, 256, 0, stream>>>(R.keys, R.count, R.hash2index, R.pre_buffer, map_size, R.suffix_mask,
 	                                                              d_quirk_suffix, d_quirk_index);
@@ -566,11 +673,8 @@ static int query_grid(size_t n, int sm_count) {
 	return (int)(blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
-cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
-                                DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
-	if (n == 0) return cudaSuccess;
-	cudaError_t e = cudaMemsetAsync(d_defer_n, 0, sizeof(unsigned int), stream);
-	if (e != cudaSuccess) return e;
+static cudaError_t query_packed_launches(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
+                                         DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
 	const int grid = query_grid(n, sm_count);
 	const int slow_grid = sm_count * 2;
 	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5) {
@@ -580,19 +684,36 @@ cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size
 		query_fast_kernel<0, 0, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
 		if (d_out) query_slow_kernel<0, 0, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
 	}
+	note_launch(d_out ? 2 : 1);
 	return cudaGetLastError();
 }
 
-// ASCII batches are 2-bit encoded into d_packed (room for n words) and then take the packed path
-cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, uint64_t* d_packed,
-                               DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
+cudaError_t launch_query_packed(const DevModel& m, const uint64_t* d_kmers, size_t n, int32_t* d_out, int32_t* d_path,
+                                DeferredQuery* d_defer, unsigned int* d_counters, int sm_count, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
-	const int grid = query_grid(n, sm_count);
-	if (stride <= (size_t)kPackMaxStride) ascii_pack_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed);
-	else ascii_pack_wide_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed);
-	cudaError_t e = cudaGetLastError();
+	cudaError_t e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), stream);
 	if (e != cudaSuccess) return e;
-	return launch_query_packed(m, d_packed, n, d_out, nullptr, d_defer, d_defer_n, sm_count, stream);
+	return query_packed_launches(m, d_kmers, n, d_out, d_path, d_defer, d_counters, sm_count, stream);
+}
+
+// ASCII batches are 2-bit encoded into d_packed (room for n words) and take the packed path; strings with characters outside
+// "ACGT" are answered again, from their raw bytes, by query_raw_kernel
+cudaError_t launch_query_ascii(const DevModel& m, const char* d_flat, size_t stride, size_t n, int32_t* d_out, uint64_t* d_packed,
+                               DeferredQuery* d_defer, uint32_t* d_dirty, unsigned int* d_counters, int sm_count, cudaStream_t stream) {
+	if (n == 0) return cudaSuccess;
+	cudaError_t e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(unsigned int), stream);
+	if (e != cudaSuccess) return e;
+	const int grid = query_grid(n, sm_count);
+	if (stride <= (size_t)kPackMaxStride) ascii_pack_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed, d_dirty, d_counters + 1);
+	else ascii_pack_wide_kernel<<<grid, 256, 0, stream>>>(d_flat, stride, n, m.k, d_packed, d_dirty, d_counters + 1);
+	note_launch();
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	e = query_packed_launches(m, d_packed, n, d_out, nullptr, d_defer, d_counters, sm_count, stream);
+	if (e != cudaSuccess) return e;
+	query_raw_kernel<<<sm_count, 64, 0, stream>>>(m, d_flat, stride, d_dirty, d_counters + 1, d_out);
+	note_launch();
+	return cudaGetLastError();
 }
 
 }  // namespace kmx

@@ -3,10 +3,10 @@
 * retrieval: the finished model is REPLICATED on every rank (broadcast of the three model files'
   bytes from the rank that built it) and the query batch is SHARDED contiguously over the ranks;
   answers are gathered in batch order.  No per-query communication.
-* build: either every rank builds whole models (independent databases -- `bench.py --gpus N`), or
-  ONE model is built by all ranks (`build_array_owner`): Bloom inserts sharded by record range and
-  OR-ed through peer memory, coupled arrays split by ownership with survivors handed from owner to
-  owner through peer memory.
+* build: ONE model built by all ranks (`build_team`, the default of `bench.py --gpus N`): record range, Bloom
+  inserts and rest sort sharded over the ranks, coupled arrays split by ownership, every exchange through
+  NVLink peer memory inside libkmx.so; torch.distributed only carries 256-byte control
+  blobs between the steps.
 
 The collectives run on CUDA tensors under NCCL and on CPU tensors under gloo (the CPU tests use
 gloo with world_size 2 and the oracle standing in for the GPU model)."""
@@ -80,94 +80,54 @@ def sharded_kmer_to_occ(answer: Callable[[np.ndarray], np.ndarray], kmers: np.nd
     return out
 
 
-class _DeviceBytes:
-    """a raw device allocation of libkmx.so as something torch can wrap without copying"""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
-
-
-def _view(ptr: int, nbytes: int, dtype=torch.uint8) -> torch.Tensor:
-    t = torch.as_tensor(_DeviceBytes(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
-    return t.view(dtype)
-
-
-def or_merge_(buf: torch.Tensor, group=None) -> torch.Tensor:
-    """bitwise OR of `buf` over all ranks, in place (NCCL has no OR reduction: all-gather + local OR)"""
-    world = dist.get_world_size(group)
-    if world == 1:
-        return buf
-    parts = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(parts, buf, group=group)
-    acc = parts[0]
-    for p in parts[1:]:
-        acc |= p
-    buf.copy_(acc)
-    return buf
-
-
-def concat_ranks(local: torch.Tensor, n_local: int, group=None) -> torch.Tensor:
-    """concatenation over ranks (rank order) of the first n_local elements of `local`; every rank gets the whole"""
-    world = dist.get_world_size(group)
-    dev = local.device
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    counts[dist.get_rank(group)] = n_local
-    dist.all_reduce(counts, group=group)
-    counts = counts.tolist()
-    width = max(max(counts), 1)
-    send = torch.zeros(width, dtype=local.dtype, device=dev)
-    send[:n_local] = local[:n_local]
-    parts = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(parts, send, group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)]) if sum(counts) else torch.zeros(0, dtype=local.dtype, device=dev)
-
-
 def owner_of_array(a: int, n_active: int) -> int:
-    """array-owner decomposition: coupled array a lives on rank a % n_active"""
+    """team build: coupled array a lives on rank a % n_active (n_active = min(world, n_bits))"""
     return a % n_active
 
 
-def build_array_owner(model, db, group=None, n_active: Optional[int] = None) -> None:
-    """KModel::init over the GPUs of one node, exactly (SURVEY.md section 8e, option A).
+def exchange_blobs(mine: bytes, group=None) -> bytes:
+    """all-gather of one fixed-size blob per rank (rank order); the control plane of the team build: counts, CUDA IPC
+    handles and return codes, 256 bytes per rank and step -- bulk data never travels this way"""
+    world = dist.get_world_size(group)
+    dev = _comm_device(group)
+    send = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv.cpu().numpy().tobytes()
 
-    Every rank runs the counting pass and inserts the Bloom-bound records of its share of the
-    database; the partial Bloom filters are OR-ed over all ranks through peer memory (libkmx's own
-    kernel, kmx_dist_merge).  The coupled arrays are owned round-robin by ranks 0..n_active-1
-    (n_active <= n_bits), whose insert kernels pass survivors to the next owner through peer-mapped
-    memory; km_back is OR-ed the same way as the filters.  Afterwards the owned arrays are broadcast
-    and the survivor lists are concatenated, so that every rank holds the complete model --
-    byte-identical to a single-GPU build."""
-    from ._lib import KmxDistBuffers, check, lib
+
+def build_team(model, db, group=None) -> None:
+    """KModel::init over the GPUs of one node, exactly: ONE model built by all ranks of `group` (one GPU each).
+
+    All the work is in libkmx.so (csrc/kmx_team.cu): every rank uploads, counts and decodes only its share of the
+    records; Bloom inserts are sharded and OR-ed through peer memory; array-bound k-mers go straight into the memory of
+    the rank that owns their round-0 array (array a on rank a % min(world, n_bits)); the owners' insert kernels pass
+    survivors on through peer memory; km_back is OR-ed, the arrays are replicated and the rest table is sorted in prefix
+    ranges, one per rank -- all over NVLink peer mappings, no NCCL on the data path.  This function only carries the
+    256-byte blobs (counts, IPC handles, return codes) between the steps.  Every rank ends with the complete model,
+    byte-identical to a single-GPU build.  `db`: an opened KmcDatabase or the database base name."""
+    from ._lib import KmxError, lib
+    from .kmodel import KmcDatabase
     import ctypes as C
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    n_bits = model.info["n_bits"]
-    n_active = min(world, n_bits, 8) if n_active is None else n_active
-    dev = torch.device("cuda", torch.cuda.current_device())
-    handles = (C.c_ubyte * 128)()
-    check(lib().kmx_dist_prepare(model._h, db._h, rank, n_active, world, handles))
-    mine = torch.tensor(list(handles), dtype=torch.uint8, device=dev)
-    allh = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allh, mine, group=group)
-    blob = bytes(torch.cat(allh).cpu().numpy().tobytes())
-    check(lib().kmx_dist_connect(model._h, blob))
-    dist.barrier(group=group)                      # every rank has mapped its peers before any kernel writes
-    check(lib().kmx_dist_merge(model._h, 0))       # Bloom filters: OR of the ranks' shares
-    check(lib().kmx_dist_insert(model._h))
-    check(lib().kmx_dist_merge(model._h, 1))       # km_back: OR of what every array owner accepted
-    bufs = KmxDistBuffers()
-    check(lib().kmx_dist_buffers(model._h, C.byref(bufs)))
-    check(lib().kmx_model_sync(model._h))          # the collectives below run on torch's stream
-    for a in range(n_bits):                        # owners publish their arrays
-        dist.broadcast(_view(bufs.cells[a], bufs.cell_bytes), src=owner_of_array(a, n_active), group=group)
-    n_local = int(bufs.rest_n)
-    cap = max(n_local, 1)
-    rest_k = concat_ranks(_view(bufs.rest_kmer, cap * 8, torch.int64) if bufs.rest_kmer else torch.zeros(1, dtype=torch.int64, device=dev), n_local, group)
-    rest_o = concat_ranks(_view(bufs.rest_occ, cap * 4, torch.int32) if bufs.rest_occ else torch.zeros(1, dtype=torch.int32, device=dev), n_local, group)
-    stats = torch.tensor([bufs.insert_attempts, bufs.insert_accepted], dtype=torch.int64, device=dev)
-    dist.all_reduce(stats, group=group)
-    torch.cuda.synchronize()
-    check(lib().kmx_dist_finish(model._h, rest_k.data_ptr() if rest_k.numel() else None, rest_o.data_ptr() if rest_o.numel() else None,
-                                rest_k.numel(), int(stats[0]), int(stats[1])))
+    own_db = not isinstance(db, KmcDatabase)
+    if own_db:
+        db = KmcDatabase(str(db))
+    try:
+        n_blob = lib().kmx_team_blob_bytes()
+        blobs = None
+        for step in range(lib().kmx_team_steps()):
+            out = (C.c_ubyte * n_blob)()
+            rc = lib().kmx_team_step(model._h, db._h, rank, world, step, blobs, out)
+            msg = lib().kmx_last_error().decode(errors="replace") if rc else ""
+            blobs = exchange_blobs(bytes(out), group)          # also after a failure: the codes travel in the blobs
+            codes = [int.from_bytes(blobs[p * n_blob:p * n_blob + 4], "little", signed=True) for p in range(world)]
+            if any(codes):
+                bad = next(p for p, c in enumerate(codes) if c)
+                raise KmxError(codes[bad], msg if rc else f"team build: rank {bad} failed in step {step} (code {codes[bad]})")
+    finally:
+        if own_db:
+            db.close()
 
 
 class ShardedKModel:

@@ -27,6 +27,11 @@ class KmcDatabase:
         check(lib().kmx_db_upload(self._h))
         return self
 
+    def upload_share(self, rank: int, world: int) -> "KmcDatabase":
+        """only the tile range a team build's rank decodes (kmcex_b200.distributed.build_team)"""
+        check(lib().kmx_db_upload_share(self._h, rank, world))
+        return self
+
     @property
     def info(self) -> dict:
         i = KmxDbInfo()

@@ -46,6 +46,15 @@ def _uniform_int(idx: torch.Tensor, seed: int, stream: int, n: int) -> torch.Ten
     return _lsr(splitmix64(idx, seed, stream), 1) % n
 
 
+def _geometric_tail(x: torch.Tensor, dtype) -> torch.Tensor:
+    """floor(log(x) / log(0.45)) + 1 clamped to 1..8 for x in (0, 1], i.e. the j with 0.45^j < x <= 0.45^(j-1),
+    evaluated by comparing against the eight thresholds (exact on every device, unlike log())"""
+    c = torch.ones(x.shape, dtype=torch.int64, device=x.device)
+    for j in range(1, 8):
+        c += (x <= torch.tensor(0.45 ** j, dtype=dtype, device=x.device)).to(torch.int64)
+    return c
+
+
 def revcomp_packed(v: torch.Tensor, k: int) -> torch.Tensor:
     """reverse complement of 2-bit packed k-mers held in int64 (k <= 31)"""
     x = ~v
@@ -96,7 +105,14 @@ def synth_reads_spectrum(genome_bp: int, coverage: float, read_len: int, k: int 
         src = _uniform_int(ridx, seed, 2, G - 1000)
         dst = _uniform_int(ridx, seed, 3, G - 1000)
         off = torch.arange(500, dtype=torch.int64, device=dev)
-        genome[(dst[:, None] + off[None, :]).reshape(-1)] = genome[(src[:, None] + off[None, :]).reshape(-1)]
+        # every segment copies from the ORIGINAL genome; where destination segments overlap the segment with the
+        # highest index wins (what a sequential scatter does) -- decided with an integer max-reduction, so the
+        # result does not depend on the device or on the order a parallel scatter happens to take
+        winner = torch.full((G,), -1, dtype=torch.int64, device=dev)
+        winner.scatter_reduce_(0, (dst[:, None] + off[None, :]).reshape(-1), ridx[:, None].expand(-1, 500).reshape(-1), "amax")
+        at = torch.nonzero(winner >= 0).squeeze(1)
+        w = winner[at]
+        genome[at] = genome.clone()[src[w] + (at - dst[w])]
     gk = genome_kmers(genome, k)
     per_read = L - k + 1
     n_reads = int(G * coverage / L)
@@ -171,7 +187,7 @@ def synth_direct_spectrum(genome_bp: int, coverage: float, read_len: int, k: int
     ed = _uniform_int(eidx, seed, 22, 3) + 1
     err = src ^ (ed << (2 * epos))
     r = _lsr(splitmix64(eidx, seed, 23), 11).to(torch.float64) / float(1 << 53)
-    err_c = torch.clamp((torch.log(1 - r) / np.log(0.45)).floor().to(torch.int64) + 1, max=8)   # geometric tail 1,2,3..
+    err_c = _geometric_tail(1 - r, torch.float64)                                                # geometric tail 1,2,3..
     allk = canonical_packed(torch.cat([gk, err]), k)
     allc = torch.cat([solid_c, err_c])
     order = torch.argsort(allk, stable=True)
@@ -334,7 +350,7 @@ def make_db_streamed(base: str, genome_bp: int, coverage: float, read_len: int, 
         ed = (_lsr(r2, 32) & 0xFFFF) % 3 + 1
         err = src ^ (ed << (2 * epos))
         u = (_lsr(r2, 40) & 0xFFFFFF).to(torch.float32) / float(1 << 24)
-        err_c = torch.clamp((torch.log(1 - u) / float(np.log(0.45))).floor().to(torch.int64) + 1, min=1, max=8)
+        err_c = _geometric_tail(1 - u, torch.float32)
         m = gk.numel() + err.numel()
         assert n_all + m <= cap
         allk[n_all:n_all + m] = canonical_packed(torch.cat([gk, err]), k)

@@ -377,6 +377,105 @@ struct ModelO {
 		return ob.bin2mean[bin];
 	}
 
+	// ---- the same retrieval on STRINGS, as the reference runs it (kmodel.hpp:100-116): a query is never validated.
+	// kmers2uint64 (tools.hpp:63-76) reads every byte that is not C/G/T as A; get_min_kmer (tools.hpp:160-167) returns the
+	// ORIGINAL string when that encoding is <= its reverse complement, else the decoded reverse complement; the rest lookup
+	// re-encodes what it is given (rest.hpp:22-34,223-251), the filters hash its raw bytes (kmodel.hpp:373-390,625-671).
+	static uint64_t pack_str(const std::string& s) {
+		uint64_t v = 0;
+		for (char ch : s) { v <<= 2; v |= ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0; }
+		return v;
+	}
+	static std::string min_kmer_str(const std::string& s) {
+		int len = (int)s.size();
+		uint64_t u = pack_str(s), rc = revcomp(u, len);
+		if (u <= rc) return s;
+		std::string out(len, 'A');
+		to_ascii(rc, len, (uint8_t*)&out[0]);
+		return out;
+	}
+	bool filter_check_str(const std::vector<uint8_t>& f, const std::string& s, int nh) const {
+		uint64_t bits = (uint64_t)f.size() * 8;
+		for (int j = 0; j < nh; j++) if (!get_bit(f, murmur64a((const uint8_t*)s.data(), (int)s.size(), kSeeds[j]) % bits)) return false;
+		return true;
+	}
+	int check_all_bf_str(const std::string& s) const {
+		static const int order3[3] = { 1, 0, 2 };
+		for (int j = 0; j < bf_num; j++) {
+			int i = ci == 1 ? j : order3[j];
+			bool a = filter_check_str(bf[i], s, hb);
+			bool b = filter_check_str(bf_back[i], s.substr(1, s.size() - 2), hk);
+			if (a && b) return i + ci;
+		}
+		return 0;
+	}
+	int decode_array_str(const std::string& s, int a, bool* all_tags) const {
+		uint64_t bits = km_byte_size * 8;
+		int bin = 0; bool ok = true;
+		for (int j = 0; j < n_hash; j++) {
+			uint64_t p = murmur64a((const uint8_t*)s.data(), (int)s.size(), seeds[a][j]) % bits;
+			bin |= get_bit(val[a], p) << j;
+			if (!get_bit(tag[a], p)) ok = false;
+		}
+		*all_tags = ok;
+		return bin;
+	}
+	void candidates_of_str(const std::string& nb, std::vector<int>& c) const {
+		std::string s = min_kmer_str(nb);
+		int r = rest.check(pack_str(s));
+		if (r > 0) { c.push_back(ob.occ2bin[r]); return; }
+		int occ = check_all_bf_str(s);
+		if (occ != 0) { c.push_back(occ); return; }
+		if (filter_check_str(km_back, s.substr(1, s.size() - 2), hk)) {
+			int result = -1;
+			for (int a = 0; a < n_bits; a++) { bool ok; int bin = decode_array_str(s, a, &ok); if (ok) { result = bin; if (bin != 0) break; } }
+			if (result > -1) c.push_back(result);
+		}
+	}
+	std::vector<int> neighbour_bins_str(const std::string& s) const {
+		std::vector<int> c;
+		const char* base = "ACGT";
+		for (int b = 0; b < 4; b++) candidates_of_str(s.substr(1) + base[b], c);
+		for (int b = 0; b < 4; b++) candidates_of_str(base[b] + s.substr(0, s.size() - 1), c);
+		return c;
+	}
+	int kmer_to_occ_str(const std::string& query) const {
+		if ((int)query.size() != k) return 0;               // (the reference probes the filters with the odd length; out of scope)
+		std::string s = min_kmer_str(query);
+		int occ = rest.check(pack_str(s));
+		if (occ != 0) return occ;
+		bool in_back = filter_check_str(km_back, s.substr(1, s.size() - 2), hk);
+		occ = check_all_bf_str(s);
+		if (occ != 0 && !in_back) return occ;
+		if (!in_back) return 0;
+		std::vector<int> bins;
+		for (int a = 0; a < n_bits; a++) { bool ok; int bin = decode_array_str(s, a, &ok); if (ok && bin > 0) bins.push_back(bin); }
+		int bin;
+		if (bins.empty()) bin = occ;
+		else if (bins.size() == 1) {
+			bin = bins[0];
+			if (occ) {
+				std::vector<int> c = neighbour_bins_str(s);
+				size_t low = 0;
+				for (int x : c) if (x < ci + bf_num) low++;
+				if (low >= c.size() / 2) bin = occ;
+			}
+		} else {
+			std::vector<int> c = neighbour_bins_str(s);
+			if (c.empty()) bin = 0;
+			else {
+				int best = bins[0], best_d = 2 << 20;
+				for (int b : bins) {
+					int d = 2 << 20;
+					for (int x : c) d = std::min(d, abs(b - x));
+					if (best_d > d) { best_d = d; best = b; }
+				}
+				bin = best;
+			}
+		}
+		return ob.bin2mean[bin];
+	}
+
 	// kmodel.hpp:173-206
 	bool save(const std::string& dir) const {
 		FILE* h = fopen((dir + "/header").c_str(), "w");
@@ -628,6 +727,12 @@ int kmxo_k(void* h) { return ((ModelO*)h)->k; }
 void kmxo_query_packed(void* h, const uint64_t* kmers, int64_t n, int32_t* out) {
 	const ModelO* m = (const ModelO*)h;
 	for (int64_t i = 0; i < n; i++) out[i] = m->kmer_to_occ(kmers[i]);
+}
+
+// n strings of k characters at flat + i * stride, answered the way the reference answers strings (N / lower case included)
+void kmxo_query_ascii(void* h, const char* flat, int64_t stride, int64_t n, int32_t* out) {
+	const ModelO* m = (const ModelO*)h;
+	for (int64_t i = 0; i < n; i++) out[i] = m->kmer_to_occ_str(std::string(flat + i * stride, (size_t)m->k));
 }
 
 // path classification for tests: 1 rest, 2 bf-only/absent, 3 array no candidate, 4 single, 5 single+vote, 6 multi

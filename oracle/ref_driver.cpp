@@ -13,6 +13,7 @@
 // Sub-commands
 //   build  <db_base> <out_dir> <ci> <cs> <nh> <nb>     init + save, prints timings (JSON)
 //   query  <model_dir> <packed_u64.bin> <k> <out_i32.bin> <threads>
+//   query_ascii <model_dir> <strings.bin> <k> <out_i32.bin> <threads>    n strings of k raw bytes each (N, lower case allowed)
 //   list   <db_base> <out.bin>         (u64 kmer, u32 count) records in listing order
 //   kat    <out.txt>                   known-answer values for hash / canonical / OccuBin
 #include "kmodel.hpp"
@@ -61,6 +62,30 @@ static int cmd_query(int argc, char** argv) {
 	if (n) fwrite(occ.data(), 4, n, fo);
 	fclose(fo);
 	printf("{\"load_s\": %.6f, \"query_s\": %.6f, \"n\": %zu, \"threads\": %d}\n", t1 - t0, t2 - t1, n, threads);
+	return 0;
+}
+
+static int cmd_query_ascii(int argc, char** argv) {
+	if (argc < 7) return 2;
+	string dir = argv[2];
+	int k = atoi(argv[4]);
+	int threads = atoi(argv[6]);
+	FILE* f = fopen(argv[3], "rb");
+	if (!f) { printf("cannot open %s\n", argv[3]); return 1; }
+	fseek(f, 0, SEEK_END);
+	size_t n = ftell(f) / k;
+	fseek(f, 0, SEEK_SET);
+	vector<char> flat(n * k);
+	if (n && fread(flat.data(), k, n, f) != n) return 1;
+	fclose(f);
+	vector<string> kmers(n);
+	for (size_t i = 0; i < n; i++) kmers[i] = string(flat.data() + i * k, k);
+	KModel* m = get_model(dir);
+	vector<int> occ = m->kmer_to_occ(kmers, threads);
+	FILE* fo = fopen(argv[5], "wb");
+	if (n) fwrite(occ.data(), 4, n, fo);
+	fclose(fo);
+	printf("{\"n\": %zu}\n", n);
 	return 0;
 }
 
@@ -114,10 +139,11 @@ static int cmd_kat(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { printf("usage: ref_driver build|query|list|kat ...\n"); return 2; }
+	if (argc < 2) { printf("usage: ref_driver build|query|query_ascii|list|kat ...\n"); return 2; }
 	string c = argv[1];
 	if (c == "build") return cmd_build(argc, argv);
 	if (c == "query") return cmd_query(argc, argv);
+	if (c == "query_ascii") return cmd_query_ascii(argc, argv);
 	if (c == "list") return cmd_list(argc, argv);
 	if (c == "kat") return cmd_kat(argc, argv);
 	return 2;

@@ -30,7 +30,8 @@ def kat_lines():
 def oracle():
     """ctypes handle of the CPU restatement (oracle/libkmx_oracle.so) -- checker only"""
     path = os.path.join(ROOT, "oracle", "libkmx_oracle.so")
-    if not os.path.exists(path):
+    src = os.path.join(ROOT, "oracle", "kmx_oracle.cpp")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
         import subprocess
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
     lib = C.CDLL(path)
@@ -52,6 +53,7 @@ def oracle():
     lib.kmxo_k.argtypes = [C.c_void_p]
     lib.kmxo_query_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.kmxo_query_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.kmxo_query_ascii.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     return lib
 
 

@@ -46,3 +46,23 @@ def make_case_db(name: str, out_dir: str):
 def case_queries(sp) -> np.ndarray:
     from kmcex_b200 import synth
     return synth.neighbour_rich_queries(sp, N_PRESENT, N_ABSENT, seed=QUERY_SEED)
+
+
+N_DIRTY = 6000
+
+
+def case_ascii_queries(sp) -> np.ndarray:
+    """(N_DIRTY, k) uint8 strings the way reads deliver them: a third clean, a third with one `N`, a third with one
+    lower-case base -- the reference never validates a query (tools.hpp:63-76,160-167)"""
+    from kmcex_b200 import synth
+    q = case_queries(sp)[:N_DIRTY]
+    a = synth.to_ascii(q, sp.k).copy()
+    rng = np.random.default_rng(QUERY_SEED + 1)
+    kind = rng.integers(0, 3, a.shape[0])
+    pos = rng.integers(0, sp.k, a.shape[0])
+    rows = np.arange(a.shape[0])
+    n_rows = rows[kind == 1]
+    a[n_rows, pos[n_rows]] = ord("N")
+    l_rows = rows[kind == 2]
+    a[l_rows, pos[l_rows]] = a[l_rows, pos[l_rows]] + 32          # lower case
+    return np.ascontiguousarray(a)

@@ -51,6 +51,12 @@ def main() -> None:
         q.tofile(qf)
         subprocess.run([REF, "query", mdir, qf, "31", of, "4"], capture_output=True, text=True, check=True)
         occ = np.fromfile(of, dtype=np.int32)
+        # strings with N / lower case, answered by the reference's own kmer_to_occ(vector<string>)
+        qa = cases.case_ascii_queries(sp)
+        qaf, oaf = os.path.join(tmp, name + "_qa.bin"), os.path.join(tmp, name + "_occa.bin")
+        qa.tofile(qaf)
+        subprocess.run([REF, "query_ascii", mdir, qaf, "31", oaf, "4"], capture_output=True, text=True, check=True)
+        occ_a = np.fromfile(oaf, dtype=np.int32)
         lst = os.path.join(tmp, name + "_list.bin")
         subprocess.run([REF, "list", base, lst], capture_output=True, text=True, check=True)
         out[name] = {
@@ -63,6 +69,8 @@ def main() -> None:
             "occ_md5": hashlib.md5(occ.tobytes()).hexdigest(),
             "occ_nonzero": int((occ != 0).sum()), "occ_sum": int(occ.astype(np.int64).sum()),
             "occ_head": occ[:64].tolist(),
+            "ascii_query_md5": hashlib.md5(qa.tobytes()).hexdigest(), "ascii_occ_md5": hashlib.md5(occ_a.tobytes()).hexdigest(),
+            "ascii_occ_nonzero": int((occ_a != 0).sum()), "ascii_differs_from_clean": int((occ_a != occ[:occ_a.size]).sum()),
             "reference_stdout_tail": r.stdout.strip().splitlines()[-1],
         }
         print(name, out[name]["model_bytes"], out[name]["occ_nonzero"])

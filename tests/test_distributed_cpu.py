@@ -1,5 +1,6 @@
-"""CPU suite, part 3: the N > 1 plumbing under gloo with world_size 2 -- contiguous sharding of the
-query batch, gathering in batch order, and byte-exact replication of a model directory.  The
+"""CPU suite, part 3: the N > 1 plumbing under gloo with world_size 2 -- the team build's control plane (blob exchange,
+failure protocol), contiguous sharding of the query batch, gathering in batch order, and byte-exact replication of a
+model directory.  The
 oracle (CPU restatement) stands in for the GPU model replica; the GPU model itself is covered by
 tests/test_gpu_parity.py."""
 import ctypes as C
@@ -42,37 +43,38 @@ def _load_oracle():
     return lib
 
 
-def _collective_worker(rank, world, port, out_dir):
+def _team_worker(rank, world, port, base, out_dir):
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""               # this test is about the protocol without a device, wherever it runs
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # OR-merge of a filter every rank filled partially (km_back in the array-owner build)
-        rng = np.random.default_rng(100 + rank)
-        part = torch.from_numpy(rng.integers(0, 1 << 62, 4096, dtype=np.int64) & rng.integers(0, 1 << 62, 4096, dtype=np.int64))
-        np.save(os.path.join(out_dir, f"part{rank}.npy"), part.numpy())
-        merged = kd.or_merge_(part.clone())
-        np.save(os.path.join(out_dir, f"merged{rank}.npy"), merged.numpy())
-        # concatenation of survivor lists of different lengths (rank order)
-        n_local = 5 + 7 * rank
-        local = torch.arange(100 * rank, 100 * rank + 64, dtype=torch.int64)
-        cat = kd.concat_ranks(local, n_local)
-        np.save(os.path.join(out_dir, f"cat{rank}.npy"), cat.numpy())
-        empty = kd.concat_ranks(torch.zeros(1, dtype=torch.int32), 0)
-        assert empty.numel() == 0
+        # the control plane of the team build: one fixed-size blob per rank, gathered in rank order
+        mine = bytes([rank + 1]) * 256
+        got = kd.exchange_blobs(mine)
+        assert got == b"".join(bytes([r + 1]) * 256 for r in range(world))
+        # the step protocol without a GPU: step 0 fails on every rank with KMX_ENOGPU, the code travels in the blobs and
+        # every rank raises the same error after the same exchange -- nobody is left waiting at a barrier
+        import kmcex_b200 as kx
+        m = kx.get_model(1, 1023, 7, 5)
+        try:
+            kd.build_team(m, base)
+            outcome = "built"
+        except kx.KmxError as e:
+            outcome = f"error {e.code}"
+        with open(os.path.join(out_dir, f"outcome{rank}.txt"), "w") as f:
+            f.write(outcome)
+        dist.barrier()
     finally:
         dist.destroy_process_group()
 
 
-def test_or_merge_and_concat_world2(tmp_path):
+def test_team_control_plane_world2(case_dbs, tmp_path):
+    base, _ = case_dbs("tiny_ci1")
     world = 2
-    mp.spawn(_collective_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    parts = [np.load(str(tmp_path / f"part{r}.npy")) for r in range(world)]
-    want = parts[0] | parts[1]
+    mp.spawn(_team_worker, args=(world, _free_port(), base, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
-        assert (np.load(str(tmp_path / f"merged{r}.npy")) == want).all()
-        cat = np.load(str(tmp_path / f"cat{r}.npy"))
-        assert cat.tolist() == list(range(0, 5)) + list(range(100, 112))
+        assert open(str(tmp_path / f"outcome{r}.txt")).read() == "error 4"     # KMX_ENOGPU, on both ranks
 
 
 def test_array_ownership_covers_every_array_once():

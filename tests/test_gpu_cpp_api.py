@@ -79,3 +79,30 @@ def test_kmcex_command_line(case_dbs, golden, tmp_path):
     # unopenable database: message + exit(1) (kmodel.hpp:394-397)
     r = subprocess.run([exe, "x", str(tmp_path / "nope"), work], capture_output=True, text=True, cwd=str(tmp_path))
     assert r.returncode == 1 and "can't open the kmer_data_base" in r.stdout
+
+
+def test_user_program_over_two_gpus_in_one_process(case_dbs, golden, tmp_path):
+    """KMX_GPUS=2: the same unmodified user program, KModel::init spread over two GPUs inside the process (one host thread
+    per GPU, peer access; no NCCL, no IPC), kmer_to_occ(vector) sharded over the replicas"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    name = "multi_ci1"
+    base, sp = case_dbs(name)
+    exe = str(tmp_path / "user_program")
+    _compile(os.path.join(ROOT, "tests", "cpp", "user_program.cpp"), exe)
+    q = cases.case_queries(sp)
+    qfile, ofile, mdir = str(tmp_path / "q.txt"), str(tmp_path / "o.txt"), str(tmp_path / "model")
+    os.makedirs(mdir)
+    with open(qfile, "w") as f:
+        f.write("\n".join("".join(map(chr, row)) for row in synth.to_ascii(q, 31)) + "\n")
+    for gpus in ("2", str(min(torch.cuda.device_count(), 8))):
+        r = subprocess.run([exe, base, mdir, qfile, ofile, str(cases.CASES[name]["ci"])], capture_output=True, text=True,
+                           env=dict(os.environ, KMX_GPUS=gpus))
+        assert r.returncode == 0, r.stdout + r.stderr
+        for f in ("header", "km.bin", "rest.bin"):
+            assert cases.md5_file(os.path.join(mdir, f)) == golden[name]["model_md5"][f], (gpus, f)
+        lines = open(ofile).read().split("\n")
+        got = np.array([int(x) for x in lines[: q.size]], dtype=np.int32)
+        import hashlib
+        assert hashlib.md5(got.tobytes()).hexdigest() == golden[name]["occ_md5"]

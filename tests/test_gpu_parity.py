@@ -99,6 +99,54 @@ def test_gpu_query_equals_reference_outputs(name, built, golden, oracle):
     m2.close()
 
 
+@pytest.mark.parametrize("name", ["tiny_ci1", "small_ci2", "multi_ci1"])
+def test_ascii_queries_with_N_and_lower_case_equal_the_reference(name, built, golden, oracle):
+    """the reference never validates a query: a byte that is not C/G/T counts as A for the canonical-form decision and the
+    rest lookup, but the filters are probed with hashes of the RAW bytes when the string itself is the canonical form
+    (tools.hpp:63-76,160-167; kmodel.hpp:373-390,625-671).  Golden = the reference's own kmer_to_occ(vector<string>)."""
+    m, out, sp, base = built(name)
+    g = golden[name]
+    qa = cases.case_ascii_queries(sp)
+    assert hashlib.md5(qa.tobytes()).hexdigest() == g["ascii_query_md5"]
+    occ = m.kmer_to_occ(qa)
+    assert int((occ != 0).sum()) == g["ascii_occ_nonzero"]
+    assert hashlib.md5(occ.tobytes()).hexdigest() == g["ascii_occ_md5"]
+    h = oracle.kmxo_load(out.encode())
+    want = np.zeros(qa.shape[0], dtype=np.int32)
+    oracle.kmxo_query_ascii(h, qa.ctypes.data, qa.shape[1], qa.shape[0], want.ctypes.data)
+    oracle.kmxo_free(h)
+    assert (occ == want).all()
+    # the same strings at a wide stride (the unstaged pack kernel) and as Python strings
+    wide = np.full((qa.shape[0], 80), ord("x"), dtype=np.uint8)
+    wide[:, :31] = qa
+    assert (m.kmer_to_occ(wide) == want).all()
+    strs = [bytes(row).decode() for row in qa[:200]]
+    assert m.kmer_to_occ(strs).tolist() == want[:200].tolist()
+
+
+@pytest.mark.parametrize("d", [15_900_007, (1 << 32) + 12_345, 11_000_000_003])
+def test_device_addressing_beyond_2_to_32_bits(d, oracle):
+    """hash -> exact modulo -> word / bit addressing with array lengths no small database reaches (the NA12878 shape has
+    bit_array_length ~ 1.1e10): positions against the oracle's hash % d, and nothing aliases"""
+    import ctypes as C
+    rng = np.random.default_rng(d & 0xFFFF)
+    n, k = 150_000, 31
+    kmers = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    seeds = np.array([kx.lib().kmx_host_seed(i) for i in (0, 1, 5, 6, 7, 34, 127)], dtype=np.uint32)
+    pos = np.zeros(n * seeds.size, dtype=np.uint64)
+    counts = np.zeros(3, dtype=np.uint64)
+    kx._lib.check(kx.lib().kmx_selftest_positions(kmers.ctypes.data, n, k, d, seeds.ctypes.data, seeds.size, pos.ctypes.data, counts.ctypes.data))
+    pos = pos.reshape(n, seeds.size)
+    sample = rng.integers(0, n, 3000)
+    for i in sample:
+        for j, sd in enumerate(seeds):
+            assert int(pos[i, j]) == oracle.kmxo_hash_packed(int(kmers[i]), k, int(sd)) % d
+    assert int(pos.max()) < d and (d < (1 << 32) or int(pos.max()) >= (1 << 32))
+    distinct = np.unique(pos).size
+    assert counts[0] == n * seeds.size           # every position reads back as set (tag bit and filter bit)
+    assert counts[1] == distinct and counts[2] == distinct
+
+
 def test_every_present_kmer_and_all_its_neighbours(built, oracle):
     """all present k-mers + the 8 neighbours of a sample (drives the disambiguation path, kmodel.hpp:286-359)"""
     m, out, sp, base = built("small_ci2")

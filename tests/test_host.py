@@ -177,3 +177,66 @@ def test_compute_entry_points_fail_loudly_without_gpu(case_dbs):
     assert e.value.code == 4          # KMX_ENOGPU: no CPU fallback
     with pytest.raises(kx.KmxError):
         m.kmer_to_occ("ACGTACGTACGTACGTACGTACGTACGTACG")
+
+
+def test_team_item_routing_is_a_bijection_onto_the_owners_shards():
+    """kmx_host_route: stream position -> (owner of the round-0 array, index in the owner's shard).  Bucket i of every batch
+    goes to rank i % n_active (array-owner decomposition, kmodel.hpp:561-565); an owner keeps its buckets back to back."""
+    lib = kx.lib()
+    K = 1 << 18
+    for n_bits, n_active in ((5, 1), (5, 2), (5, 3), (5, 5), (8, 8), (3, 2), (1, 1)):
+        seen = {}
+        n_buckets = 3 * n_bits + 2                      # three full batches and a partial one
+        per_owner = [0] * n_active
+        for B in range(n_buckets):
+            i = B % n_bits
+            want_owner = i % n_active
+            for c in (0, 1, K - 1):
+                o, at = C.c_int32(-1), C.c_uint64(0)
+                lib.kmx_host_route(B * K + c, n_active, n_bits, C.byref(o), C.byref(at))
+                assert o.value == want_owner
+                assert at.value == per_owner[want_owner] * K + c, (n_bits, n_active, B, c)
+                assert (o.value, at.value) not in seen
+                seen[(o.value, at.value)] = B * K + c
+            per_owner[want_owner] += 1
+        # single GPU: the shard is the stream
+        o, at = C.c_int32(-1), C.c_uint64(0)
+        lib.kmx_host_route(123456789, 1, n_bits, C.byref(o), C.byref(at))
+        assert (o.value, at.value) == (0, 123456789)
+
+
+def test_team_prefix_cuts_partition_the_rest_table():
+    """sharded rest build: contiguous prefix ranges, balanced on the histogram, identical on every rank"""
+    lib = kx.lib()
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        map_size = int(rng.choice([64, 1024, 16384]))
+        hist = rng.integers(0, 50, map_size).astype(np.uint32)
+        if trial % 4 == 0:
+            hist[: map_size // 2] = 0                    # empty prefixes at the front
+        if trial % 5 == 0:
+            hist[:] = 0
+            hist[7] = 1000                               # everything in one group
+        for world in (1, 2, 3, 8):
+            cut = np.zeros(world + 1, dtype=np.uint32)
+            off = np.zeros(world + 1, dtype=np.uint64)
+            assert lib.kmx_host_prefix_cuts(hist.ctypes.data, map_size, world, cut.ctypes.data, off.ctypes.data) == 0
+            assert cut[0] == 0 and cut[world] == map_size and (np.diff(cut.astype(np.int64)) >= 0).all()
+            csum = np.concatenate([[0], np.cumsum(hist.astype(np.uint64))])
+            assert (off == csum[cut]).all()              # a rank's run starts where the prefixes before its range end
+            total = int(csum[-1])
+            sizes = np.diff(off.astype(np.int64))
+            assert sizes.sum() == total
+            if total and hist.max() * world < total:     # no giant group: shares stay within one group of the ideal
+                assert sizes.max() <= total // world + int(hist.max()) + 1
+
+
+def test_bench_shapes_are_pinned_by_the_reference():
+    """tests/golden/bench_shapes.json: digests of the unmodified reference's model for the named bench shapes, with the
+    oracle checked against them when they were taken"""
+    from kmcex_b200 import workloads as wl
+    for name in ("rs", "hc14"):
+        g = wl.golden_for(name)
+        assert g is not None and g["oracle_equals_reference"] is True
+        assert set(g["model_md5"]) == set(wl.MODEL_FILES) and g["occ_n"] == 1 << 22 and len(g["db_md5"]["kmc_suf"]) == 32
+        assert g["insert_attempts"] >= g["insert_accepted"] > 0 and g["workload"] == wl.WORKLOADS[name][4]

@@ -56,6 +56,16 @@ def test_oracle_matches_reference_goldens(name, oracle, case_dbs, golden, tmp_pa
     assert occ[:64].tolist() == g["occ_head"]
     assert int((occ != 0).sum()) == g["occ_nonzero"]
     assert hashlib.md5(occ.tobytes()).hexdigest() == g["occ_md5"]
+    # strings with N / lower case: the reference hashes their raw bytes when the forward orientation is canonical
+    qa = cases.case_ascii_queries(sp)
+    assert hashlib.md5(qa.tobytes()).hexdigest() == g["ascii_query_md5"]
+    h = oracle.kmxo_load(out.encode())
+    occ_a = np.zeros(qa.shape[0], dtype=np.int32)
+    oracle.kmxo_query_ascii(h, qa.ctypes.data, qa.shape[1], qa.shape[0], occ_a.ctypes.data)
+    oracle.kmxo_free(h)
+    assert int((occ_a != 0).sum()) == g["ascii_occ_nonzero"]
+    assert hashlib.md5(occ_a.tobytes()).hexdigest() == g["ascii_occ_md5"]
+    assert int((occ_a != occ[:occ_a.size]).sum()) == g["ascii_differs_from_clean"] > 0      # reading N as A would be wrong
 
 
 @pytest.mark.skipif(not os.path.exists(REF), reason="compiled reference (oracle/_ref) not present")
