@@ -115,20 +115,67 @@ __device__ __forceinline__ uint64_t decode_kmer(const DevDb& db, const uint8_t* 
 	return v;
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D) with mbarrier completion: the staging of the pure streaming pass ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done)
+		             : "r"(smem_u32(bar)), "r"(parity)
+		             : "memory");
+	} while (!done);
+}
+
 // pass 1 (kmodel.hpp:423-434).  LIST = true only counts listed records per tile (kmx_db_list).
+// The one pure streaming kernel of the build: a block keeps kCountStages tiles in flight with cp.async.bulk (one elected
+// thread issues a 16 KB bulk copy per tile, an mbarrier flips when the bytes have landed), so the HBM pipe stays full while
+// the 256 threads pick the counters out of the previous tile; one __syncthreads per tile (the partial sums alternate
+// between two shared buffers).
+constexpr int kCountStages = 3;
 template <bool LIST>
 __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevDb db, int ci, int cs, int bf_num, CountOut* out,
                                                     uint32_t* __restrict__ tile_cnt, uint64_t tile_first, uint64_t tile_end) {
-	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];
-	__shared__ unsigned long long s_sum[8];
-	const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_stage);
+	extern __shared__ __align__(128) uint8_t s_dyn[];        // kCountStages stages of stage_bytes each
+	__shared__ uint64_t s_bar[kCountStages];
+	__shared__ unsigned long long s_sum[2][2][8];             // [parity][packed word][warp]
+	const uint32_t stage_bytes = ((uint32_t)kTile * db.rec_bytes + 127u) & ~127u;
 	unsigned long long acc[6] = { 0, 0, 0, 0, 0, 0 };        // thread 0: class0..2, listed, array, bad
-	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	auto issue = [&](uint64_t tile, int stage) {              // thread 0 only
 		const uint64_t s0 = tile * kTile;
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
-		__syncthreads();
-		stage_tile(db, s0, n_rec, s_stage);
-		__syncthreads();
+		const uint32_t bytes = (n_rec * db.rec_bytes + 15u) & ~15u;          // the device buffer is padded to 16
+		mbar_expect_tx(&s_bar[stage], bytes);
+		bulk_g2s(s_dyn + (size_t)stage * stage_bytes, db.suf + s0 * db.rec_bytes, bytes, &s_bar[stage]);
+	};
+	if (threadIdx.x == 0) {
+		for (int q = 0; q < kCountStages; q++) mbar_init(&s_bar[q], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		for (int q = 0; q < kCountStages; q++) {
+			const uint64_t tile = tile_first + blockIdx.x + (uint64_t)q * gridDim.x;
+			if (tile < tile_end) issue(tile, q);
+		}
+	}
+	__syncthreads();
+	uint32_t it = 0;
+	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x, it++) {
+		const int stage = (int)(it % kCountStages);
+		const uint8_t* s_bytes = s_dyn + (size_t)stage * stage_bytes;
+		const uint64_t s0 = tile * kTile;
+		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
+		mbar_wait(&s_bar[stage], (it / kCountStages) & 1u);
 		uint32_t cls[3] = { 0, 0, 0 }, listed = 0, arr = 0, bad = 0;
 #pragma unroll
 		for (int j = 0; j < kTile / 256; j++) {
@@ -148,9 +195,24 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevD
 		// pack the six small counters into two 64-bit sums (each < 2^12 per thread, 2^20 per block)
 		unsigned long long p0 = (unsigned long long)cls[0] | ((unsigned long long)cls[1] << 21) | ((unsigned long long)cls[2] << 42);
 		unsigned long long p1 = (unsigned long long)listed | ((unsigned long long)arr << 21) | ((unsigned long long)bad << 42);
-		p0 = block_sum(p0, s_sum);
-		p1 = block_sum(p1, s_sum);
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			p0 += __shfl_down_sync(0xffffffffu, p0, d);
+			p1 += __shfl_down_sync(0xffffffffu, p1, d);
+		}
+		if (lane == 0) {
+			s_sum[it & 1][0][warp] = p0;
+			s_sum[it & 1][1][warp] = p1;
+		}
+		__syncthreads();                                     // every thread is done with the stage; the partial sums are visible
 		if (threadIdx.x == 0) {
+			const uint64_t next = tile + (uint64_t)kCountStages * gridDim.x;
+			if (next < tile_end) issue(next, stage);
+			p0 = p1 = 0;
+			for (int w = 0; w < 8; w++) {
+				p0 += s_sum[it & 1][0][w];
+				p1 += s_sum[it & 1][1][w];
+			}
 			const unsigned long long m21 = (1ULL << 21) - 1;
 			acc[0] += p0 & m21; acc[1] += (p0 >> 21) & m21; acc[2] += (p0 >> 42) & m21;
 			acc[3] += p1 & m21; acc[4] += (p1 >> 21) & m21; acc[5] += (p1 >> 42) & m21;
@@ -302,10 +364,28 @@ static int stream_grid(uint64_t n_tiles, int sm_count, int per_sm) {
 	return (int)(n_tiles < cap ? (n_tiles ? n_tiles : 1) : cap);
 }
 
+// grid and dynamic shared memory of the counting pass: kCountStages stages per block, as many blocks per SM as fit
+template <bool LIST>
+static cudaError_t count_launch_shape(const DevDb& db, uint64_t n_tiles, int sm_count, int* grid, size_t* smem) {
+	*smem = (size_t)kCountStages * (((size_t)kTile * db.rec_bytes + 127) & ~(size_t)127);
+	cudaError_t e = cudaFuncSetAttribute(count_kernel<LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+	if (e != cudaSuccess) return e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<LIST>, 256, *smem);
+	if (e != cudaSuccess) return e;
+	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+	*grid = stream_grid(n_tiles, sm_count, per_sm);
+	return cudaSuccess;
+}
+
 cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, uint64_t tile_first,
                          uint64_t tile_end, int sm_count, cudaStream_t stream) {
 	if (tile_end <= tile_first) return cudaSuccess;
-	count_kernel<false><<<stream_grid(tile_end - tile_first, sm_count, 8), 256, 0, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end);
+	int grid = 0;
+	size_t smem = 0;
+	cudaError_t e = count_launch_shape<false>(db, tile_end - tile_first, sm_count, &grid, &smem);
+	if (e != cudaSuccess) return e;
+	count_kernel<false><<<grid, 256, smem, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end);
 	note_launch();
 	return cudaGetLastError();
 }
@@ -313,7 +393,11 @@ cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* 
 cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream) {
 	if (db.total == 0) return cudaSuccess;
 	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	count_kernel<true><<<stream_grid(n_tiles, sm_count, 8), 256, 0, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles);
+	int grid = 0;
+	size_t smem = 0;
+	cudaError_t e = count_launch_shape<true>(db, n_tiles, sm_count, &grid, &smem);
+	if (e != cudaSuccess) return e;
+	count_kernel<true><<<grid, 256, smem, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles);
 	note_launch();
 	return cudaGetLastError();
 }

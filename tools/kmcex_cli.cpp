@@ -7,6 +7,7 @@
 //
 //   g++ -std=c++11 -O2 -Iinclude tools/kmcex_cli.cpp -Lkmcex_b200 -lkmx -Wl,-rpath,$PWD/kmcex_b200 -o kmcEx
 #include <sys/stat.h>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -17,13 +18,56 @@ struct Options {
 	std::string input, output, workdir = "/tmp";
 };
 
+// the reference's read_me() (main.cpp:30-55): same sections, options, defaults and examples -- the command line is part of the
+// interface; the note at the end is what differs here
 static void usage() {
-	std::cout << "kmcEx (B200 build path) [options] <input_file_name> <output_file_name> <working_directory>\n"
-	             "  -k<len> k-mer length (31)   -t<value> threads for the kmc stage (4)\n"
-	             "  -ci<value> minimum count (1)   -cs<value> counter ceiling (1023)\n"
-	             "  -nh<value> number of hash functions (7)   -nb<value> number of coupled bit arrays (5)\n"
-	             "  input_file_name may be a FASTQ file or @list, as for the reference; when ./kmc_api/kmc is absent\n"
-	             "  the database <output_file_name>.kmc_pre/.kmc_suf must already exist\n";
+	const char* bar = "----------------------------------------------------------------------";
+	std::cout << bar << "\n           kmcEx: counted k-mer encoding & decoding                   \n" << bar << "\n";
+	std::cout << "VERSION: 1.5 (B200 build path, libkmx " << kmx_version() << ")\nDATE   : Nov 2nd, 2019\n" << bar << "\n\n";
+	std::cout << "1. USAGE\n"
+	             "     kmcEx [options] <input_file_name> <output_file_name> <working_directory>\n"
+	             "     kmcEx [options] <@input_file_names> <output_file_name> <working_directory>\n"
+	             "2. OPTIONS\n"
+	             "     1) REQUIRED\n"
+	             "        input_file_name    - single file in FASTQ format (gziped or not)\n"
+	             "        @input_file_names  - file name with list of input files in FASTQ format (gziped or not)\n"
+	             "        working_directory  - save temporary files\n"
+	             "     2) OPTIONAL\n"
+	             "        -k<len>            - k-mer length (default: 31)\n"
+	             "        -t<value>          - total number of threads (default: 4)\n"
+	             "        -ci<value>         - exclude k-mers occurring less than <value> times (default: 1)\n"
+	             "        -cs<value>         - maximal value of a counter (default: 1023)\n"
+	             "        -nh<value>         - number of hash (default: 7)\n"
+	             "        -nb<value>         - number of bit array (default: 5)\n"
+	             "3. EXAMPLES\n"
+	             "     kmcEx -k31 -nh7 -nb5  rs.fastq rs.res /tmp\n"
+	             "     kmcEx -k31 -nh7 -nb5  @rs.lst rs.res /tmp\n\n"
+	             "   (the k-mer counting stage is ./kmc_api/kmc when that binary exists; otherwise an existing\n"
+	             "    <output_file_name>.kmc_pre/.kmc_suf database is used, and if there is none plain-text FASTQ input\n"
+	             "    is counted on the GPU; KMX_GPUS=<n> spreads the model build over n GPUs)\n\n";
+}
+
+// a path as ONE shell word: the kmc command line goes through system() as in main.cpp:136-140
+static std::string shell_quote(const std::string& s) {
+	std::string q = "'";
+	for (char c : s) {
+		if (c == '\'') q += "'\\''";
+		else q += c;
+	}
+	return q + "'";
+}
+
+// mkdir -p without a shell (main.cpp:148 uses system("mkdir -p ..."))
+static bool make_dirs(const std::string& path) {
+	std::string cur;
+	for (size_t i = 0; i <= path.size(); i++) {
+		if (i == path.size() || path[i] == '/') {
+			if (!cur.empty() && cur != "/" && mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST) return false;
+		}
+		if (i < path.size()) cur += path[i];
+	}
+	struct stat st;
+	return stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
 }
 
 static bool parse(int argc, char** argv, Options& o) {
@@ -54,14 +98,23 @@ int main(int argc, char** argv) {
 	}
 	struct stat st;
 	if (stat("./kmc_api/kmc", &st) == 0) {
-		char cmd[2048];
-		snprintf(cmd, sizeof(cmd), "./kmc_api/kmc -k%d -t%d -ci%d -cs%d %s %s %s", o.k, o.t, o.ci, o.cs, o.input.c_str(), o.output.c_str(),
-		         o.workdir.c_str());
+		char opts[256];
+		snprintf(opts, sizeof(opts), "./kmc_api/kmc -k%d -t%d -ci%d -cs%d ", o.k, o.t, o.ci, o.cs);
+		const std::string cmd = std::string(opts) + shell_quote(o.input) + " " + shell_quote(o.output) + " " + shell_quote(o.workdir);
 		std::cout << cmd << std::endl;
-		if (system(cmd) != 0) std::cout << "kmc returned a non-zero status" << std::endl;
+		if (system(cmd.c_str()) != 0) std::cout << "kmc returned a non-zero status" << std::endl;
 		std::cout << std::endl;
 	} else if (stat((o.output + ".kmc_pre").c_str(), &st) == 0) {
 		std::cout << "./kmc_api/kmc not found: using the existing database " << o.output << std::endl;
+		// a database left by an earlier run may have been counted with other options: say so instead of silently building from it
+		if (kmx_db* db = kmx_db_open(o.output.c_str())) {
+			kmx_db_info_t di;
+			kmx_db_info(db, &di);
+			kmx_db_close(db);
+			if ((int)di.k != o.k || (int)di.min_count != o.ci || (int)di.max_count > o.cs)
+				std::cout << "   WARNING: that database holds k=" << di.k << " -ci" << di.min_count << " -cs" << di.max_count << ", the command line asks for k=" << o.k
+				          << " -ci" << o.ci << " -cs" << o.cs << std::endl;
+		}
 	} else {
 		// the counting stage on the GPU (kmx_count_fastq): plain-text FASTQ, or @file listing one path per line
 		std::vector<std::string> files;
@@ -94,7 +147,10 @@ int main(int argc, char** argv) {
 	kmodel->show_kmodel_info();
 	size_t slash = o.output.find_last_of('/');
 	std::string save_dir = o.workdir + "/" + (slash == std::string::npos ? o.output : o.output.substr(slash + 1));
-	if (system(("mkdir -p " + save_dir).c_str()) != 0) return 1;        // main.cpp:148
+	if (!make_dirs(save_dir)) {                                          // main.cpp:148
+		std::cout << "cannot create " << save_dir << std::endl;
+		return 1;
+	}
 	kmodel->save(save_dir);
 	return 0;
 }

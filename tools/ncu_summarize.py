@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Turn ncu outputs brought back in gpurun_out/ into the text summaries kept under profiles/.
   ncu_summarize.py launches <launches.csv> <out.txt>     per-kernel totals and shares of a launch list
-  ncu_summarize.py full <report.ncu-rep> <out.txt>       key metrics of every captured launch of a --set full report"""
+  ncu_summarize.py full <report.ncu-rep> <out.txt>       key metrics of every captured launch of a --set full report
+  ncu_summarize.py traffic <report.ncu-rep> <workload> <kernel substring> <profiles/r2_ncu_traffic.json>
+                                                         mean dram read + write bytes per launch of that kernel -> the json bench.py reads"""
 import collections
 import csv
 import subprocess
@@ -57,5 +59,27 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, workload, kernel, dst):
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+
+    def val(r, k):
+        i = hdr.index(k)
+        x = float(r[i].replace(",", ""))
+        u = units[i].lower()
+        return x * (1e9 if u.startswith("gbyte") else 1e6 if u.startswith("mbyte") else 1e3 if u.startswith("kbyte") else 1)
+    per = [val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") for r in rows[2:] if kernel in r[hdr.index("Kernel Name")]]
+    out = json.load(open(dst)) if os.path.exists(dst) else {}
+    out[workload] = {"kernel": kernel, "launches_captured": len(per), "dram_bytes_per_launch": sum(per) / len(per), "source": os.path.basename(src)}
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+    print(out[workload])
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:6])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -9,7 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
-import bench  # noqa: E402
+from kmcex_b200 import workloads as bench  # noqa: E402
 import kmcex_b200 as kx  # noqa: E402
 
 w = sys.argv[1] if len(sys.argv) > 1 else "rs"

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import kmcex_b200 as kx
-    import bench
+    from kmcex_b200 import workloads as bench
     meta = bench.ensure_db(sys.argv[2])
     for i in range(4):
         t0 = time.perf_counter()
