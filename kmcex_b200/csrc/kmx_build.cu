@@ -732,6 +732,8 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					}
 				}
 			}
+			// (diagnostic: slots 2 / 4 hold the part of phases 0 / 1 block 0 spent in its own loop, the rest is barrier wait)
+			if (tid == 0 && a.merged && (a.phase_round < 0 || a.phase_round == t)) vctl->phase_cycles[2] += (unsigned long long)(clock64() - tick);
 			GSYNC();
 			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();
@@ -786,6 +788,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					append(a.list[1], &ctl->list_n[1], id);
 				}
 			}
+			if (tid == 0 && a.merged && (a.phase_round < 0 || a.phase_round == t)) vctl->phase_cycles[4] += (unsigned long long)(clock64() - tick);
 			gsync_fetch(par);
 			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
 				long long now = clock64();

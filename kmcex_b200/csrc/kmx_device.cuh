@@ -40,6 +40,7 @@ struct DevModel {
 	uint32_t arr_seed[kMaxArrays][kMaxHash];   // kmodel.hpp:450-453
 	const uint16_t* occ2bin;         // [cs+1]      occu_bin.hpp:67-77
 	const int32_t* bin2mean;         // [1<<n_hash] occu_bin.hpp:79-83
+	int query_l2;                    // L2 policy of the query probes for models beyond the L2: 1 km_back evict-last, 2 arrays evict-first, 4 Bloom evict-first
 	DevRest rest;
 };
 
@@ -78,6 +79,11 @@ KMX_D unsigned long long make_evict_last_policy() {
 	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
 	return pol;
 }
+KMX_D unsigned long long make_evict_normal_policy() {
+	unsigned long long pol;
+	asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
 KMX_D unsigned long long ld_stream64(const unsigned long long* p, unsigned long long pol) {
 	unsigned long long v;
 	asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
@@ -90,10 +96,26 @@ KMX_D void red_or32_stream(uint32_t* p, uint32_t v, unsigned long long pol) {
 	asm volatile("red.global.or.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(__cvta_generic_to_global(p)), "r"(v), "l"(pol) : "memory");
 }
 
+// read-only probes with an L2 eviction policy (query kernels; models that do not fit the L2)
+KMX_D uint32_t ldg_hint32(const uint32_t* p, unsigned long long pol) {
+	uint32_t v;
+	asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+	return v;
+}
+KMX_D unsigned long long ldg_hint64(const unsigned long long* p, unsigned long long pol) {
+	unsigned long long v;
+	asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(__cvta_generic_to_global(p)), "l"(pol));
+	return v;
+}
+
 // ---- bit probes -------------------------------------------------------------------------
 KMX_D bool filter_test(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);
 	return (__ldg(f.words + (pos >> 5)) & bit_mask32(pos)) != 0;
+}
+KMX_D bool filter_test_hint(const DevFilter& f, uint64_t h, unsigned long long pol) {
+	uint64_t pos = fastmod(h, f.mod);
+	return (ldg_hint32(f.words + (pos >> 5), pol) & bit_mask32(pos)) != 0;
 }
 KMX_D void filter_set(const DevFilter& f, uint64_t h) {
 	uint64_t pos = fastmod(h, f.mod);

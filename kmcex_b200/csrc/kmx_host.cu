@@ -113,6 +113,8 @@ int require_gpu(int* sm_count) {
 
 #define fail kmx::set_error
 
+constexpr int kQueryL2Default = 0;            // set from the A/B on the HC14 shape (KMX_QUERY_L2)
+
 // =========================================================================================
 // OccuBin (occu_bin.hpp:27-83) as two lookup tables
 // =========================================================================================
@@ -322,6 +324,9 @@ void kmx::fill_dev_model(kmx_model* m) {
 	}
 	d.occ2bin = m->d_occ2bin;
 	d.bin2mean = m->d_bin2mean;
+	// query probes of a model beyond the L2: km_back stays resident, arrays and Bloom filters stream
+	d.query_l2 = (2ULL * m->n_bits * m->bytes[6] + m->bytes[7] + m->bytes[0] + m->bytes[1] + m->bytes[2]) > (192ULL << 20) ? kQueryL2Default : 0;
+	if (const char* e = getenv("KMX_QUERY_L2")) d.query_l2 = atoi(e) & 7;
 	d.rest.hash2index = m->d_hash2index;
 	d.rest.pre_buffer = m->d_pre_buffer;
 	d.rest.keys = m->d_rest_keys;

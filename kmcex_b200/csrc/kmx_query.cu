@@ -27,7 +27,16 @@ namespace kmx {
 template <int K, int H, int B>
 struct QueryCfg {
 	const DevModel& m;
-	__device__ __forceinline__ explicit QueryCfg(const DevModel& mm) : m(mm) {}
+	// L2 policy of the probes (m.query_l2, set for models beyond the L2): km_back is touched by every query and small enough
+	// to stay resident (evict-last), the coupled arrays and the Bloom filters are far larger than the L2 and stream through it
+	// (evict-first); otherwise the default policy.  Every probe carries its structure's policy: no branch in the hot path.
+	unsigned long long pol_back, pol_cells, pol_bloom;
+	__device__ __forceinline__ explicit QueryCfg(const DevModel& mm) : m(mm) {
+		const unsigned long long normal = make_evict_normal_policy();
+		pol_back = (mm.query_l2 & 1) ? make_evict_last_policy() : normal;
+		pol_cells = (mm.query_l2 & 2) ? make_evict_first_policy() : normal;
+		pol_bloom = (mm.query_l2 & 4) ? make_evict_first_policy() : normal;
+	}
 	__device__ __forceinline__ int k() const { return K ? K : m.k; }
 	__device__ __forceinline__ int h() const { return H ? H : m.n_hash; }
 	__device__ __forceinline__ int b() const { return B ? B : m.n_bits; }
@@ -83,7 +92,7 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 			bool ok = true;
 #pragma unroll
 			for (int j = 0; j < kStageA; j++)
-				if (j < hb) ok &= filter_test(m.bf[i], q.h31[j]);
+				if (j < hb) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
 			hit[i] = ok;
 		}
 	}
@@ -99,9 +108,9 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 			pending &= pending - 1;
 			bool ok = true;
 #pragma unroll
-			for (int j = kStageA; j < kHmax(H) - 1; j++) ok &= filter_test(m.bf[i], q.h31[j]);
+			for (int j = kStageA; j < kHmax(H) - 1; j++) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
 #pragma unroll
-			for (int j = 0; j < kHmax(H) - 2; j++) ok &= filter_test(m.bf_back[i], q.h29[j]);
+			for (int j = 0; j < kHmax(H) - 2; j++) ok &= filter_test_hint(m.bf_back[i], q.h29[j], c.pol_bloom);
 			okmask |= (ok ? 1u : 0u) << i;
 		}
 #pragma unroll
@@ -113,10 +122,10 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 				bool ok = true;
 #pragma unroll
 				for (int j = kStageA; j < kHmax(H) - 1; j++)
-					if (j < hb) ok &= filter_test(m.bf[i], q.h31[j]);
+					if (j < hb) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
 #pragma unroll
 				for (int j = 0; j < kHmax(H) - 2; j++)
-					if (j < hk) ok &= filter_test(m.bf_back[i], q.h29[j]);
+					if (j < hk) ok &= filter_test_hint(m.bf_back[i], q.h29[j], c.pol_bloom);
 				hit[i] = ok;
 			}
 		}
@@ -134,7 +143,7 @@ __device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B>& c, const 
 	bool ok = true;
 #pragma unroll
 	for (int j = 0; j < kHmax(H) - 2; j++)
-		if (j < hk) ok &= filter_test(c.m.km_back, q.h29[j]);
+		if (j < hk) ok &= filter_test_hint(c.m.km_back, q.h29[j], c.pol_back);
 	return ok;
 }
 
@@ -160,7 +169,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 			if (i < c.b() && j < c.h()) {
 				const uint64_t pos = position(i, j);
 				shA[i][j] = ((uint32_t)pos & 31u) ^ 7u;
-				cellA[i][j] = __ldg(m.cells[i] + (pos >> 5));
+				cellA[i][j] = ldg_hint64(m.cells[i] + (pos >> 5), c.pol_cells);
 			}
 		}
 	}
@@ -201,7 +210,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 			for (int j = kStageA; j < kHmax(H); j++) {
 				const uint64_t pos = fastmod(hash_finish(q.p31, c.k(), m.arr_seed[i][j]), m.arr_mod);
 				sh[j] = ((uint32_t)pos & 31u) ^ 7u;
-				cell[j] = __ldg(cells + (pos >> 5));
+				cell[j] = ldg_hint64(cells + (pos >> 5), c.pol_cells);
 			}
 			uint32_t bin = 0;
 			bool ok = true;
@@ -233,7 +242,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 				if (j < c.h()) {
 					const uint64_t pos = position(i, j);
 					sh[j] = ((uint32_t)pos & 31u) ^ 7u;
-					cell[j] = __ldg(m.cells[i] + (pos >> 5));
+					cell[j] = ldg_hint64(m.cells[i] + (pos >> 5), c.pol_cells);
 				}
 			}
 			int bin = bins[i];
