@@ -995,10 +995,20 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					const uint32_t tb = c_base / kIdTile, tiles_used = (nw + kIdTile - 1) / kIdTile;
 					const uint32_t* tf = a.tile_fail + i * kTilesPerBucket;
 					uint32_t before = 0, F = 0;
-					for (uint32_t k = lane; k < tiles_used; k += 32u) {
-						const uint32_t v = __ldcg(tf + k);
-						F += v;
-						before += k < tb ? v : 0u;
+					// (a lane sums up to 32 counters: eight independent loads in flight at a time instead of one L2 round trip each)
+					for (uint32_t q0 = 0; q0 * 32u < tiles_used; q0 += 8u) {
+						uint32_t v[8];
+#pragma unroll
+						for (uint32_t u = 0; u < 8u; u++) {
+							const uint32_t k = lane + 32u * (q0 + u);
+							v[u] = k < tiles_used ? __ldcg(tf + k) : 0u;
+						}
+#pragma unroll
+						for (uint32_t u = 0; u < 8u; u++) {
+							const uint32_t k = lane + 32u * (q0 + u);
+							F += v[u];
+							before += k < tb ? v[u] : 0u;
+						}
 					}
 #pragma unroll
 					for (int d = 16; d > 0; d >>= 1) {
@@ -1074,12 +1084,16 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					const uint32_t i = id >> kBucketLog, c = id & (kBucket - 1);
 					const uint32_t F = n_next[i];
 					if (c < F) continue;
-					if ((__ldcg(a.status + id) >> kStateShift) != 2u) continue;
-					const uint32_t d = F - __ldcg(a.excl_rank + id) - 1;
-					const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + d);
+					// status, rank and the item itself are independent loads (one L2 round trip); only the hole position depends on the rank
+					const uint32_t st = __ldcg(a.status + id);
+					const uint32_t er = __ldcg(a.excl_rank + id);
+					const uint64_t v = __ldcg(src_kmer + src_at(id));
+					const uint32_t occ = __ldcg(src_occ + src_at(id));
+					if ((st >> kStateShift) != 2u) continue;
+					const uint32_t to = __ldcg(a.holepos + (i << kBucketLog) + (F - er - 1));
 					const int nx = ((int)(i + (uint32_t)t + 1u) % nb) % a.n_active;
-					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_kmer + src_at(id));
-					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = __ldcg(src_occ + src_at(id));
+					a.peer_buf_kmer[t & 1][nx][(i << kBucketLog) + to] = v;
+					a.peer_buf_occ[t & 1][nx][(i << kBucketLog) + to] = occ;
 				}
 			}
 			for (uint32_t x = tid; x < n_id_tiles; x += T) a.tile_fail[x] = 0;

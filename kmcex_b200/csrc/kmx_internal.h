@@ -86,7 +86,7 @@ struct DevCtx {
 	cudaStream_t stream = nullptr, stream2 = nullptr;
 	cudaStream_t reader[16] = {};
 	cudaEvent_t reader_ev[16][2] = {};
-	cudaEvent_t ev_build[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	cudaEvent_t ev_build[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };   // [6]: team build, start of the rest stage
 	struct Pinned {                   // small device->host results, pinned so the copies are truly asynchronous
 		CountOut count;
 		InsertCtl ctl;

@@ -428,6 +428,7 @@ static int team_step2(kmx_model* m, const TeamBlob1* in, size_t stride, TeamBlob
 		CU(launch_or_allreduce(r, m->sm_count, s));           // its entry barrier: every owner's insert is complete
 		t->seq += 2;
 	}
+	CU(cudaEventRecord(ev[6], s));                        // everything after this is the rest table
 	TRACE(b.wall0, "team: build queued");
 	CU(cudaStreamSynchronize(s));
 	TRACE(b.wall0, "team: arrays built and replicated");
@@ -592,10 +593,9 @@ static int team_step3(kmx_model* m, const TeamBlob2* in, size_t stride) {
 	f.ms_count = t->ms_count;
 	f.ms_encode = ms_encode;
 	f.ms_insert = ms_insert;
-	float since_encode = 0, to_insert_end = 0;
+	float since_encode = 0;
 	CU(cudaEventElapsedTime(&since_encode, ev[1], ev[4]));
-	CU(cudaEventElapsedTime(&to_insert_end, ev[1], ev[3]));
-	f.ms_rest = since_encode - to_insert_end;               // includes the host side of the step-2 / step-3 exchange
+	CU(cudaEventElapsedTime(&f.ms_rest, ev[6], ev[4]));     // includes the host side of the step-2 / step-3 exchange
 	f.ms_total_device = t->ms_count + since_encode;
 	f.build_time_cost = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - b.wall0).count();
 	build_state_free(m);
