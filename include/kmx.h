@@ -136,7 +136,7 @@ uint64_t kmx_host_fastmod(uint64_t h, uint64_t d);                     /* the de
 int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm);
 
 /* ---- k-mer counting: the stage the reference delegates to the external `kmc` binary (main.cpp:136-140)
- * Plain-text 4-line FASTQ files -> <out_base>.kmc_pre/.kmc_suf (KMC 2/3 layout, one bin): canonical k-mers, windows
+ * 4-line FASTQ files (plain text or gzip) -> <out_base>.kmc_pre/.kmc_suf (KMC 2/3 layout, one bin): canonical k-mers, windows
  * with a non-ACGT base skipped, k-mers seen fewer than ci times dropped, counters saturated at cs.            */
 typedef struct kmx_count_info_t {
 	uint64_t n_reads, n_windows, n_unique, n_kept;

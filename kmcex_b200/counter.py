@@ -8,7 +8,7 @@ from ._lib import KmxCountInfo, check, lib
 
 
 def count_fastq(paths, out_base: str, k: int = 31, ci: int = 1, cs: int = 1023) -> dict:
-    """paths: one plain-text FASTQ file or a list of them.  Writes <out_base>.kmc_pre/.kmc_suf."""
+    """paths: one FASTQ file (plain text or gzip) or a list of them.  Writes <out_base>.kmc_pre/.kmc_suf."""
     if isinstance(paths, (str, bytes)):
         paths = [paths]
     arr = (C.c_char_p * len(paths))(*[p.encode() if isinstance(p, str) else p for p in paths])

@@ -12,20 +12,19 @@
 //
 // Pipeline: file bytes -> HBM; newline index (count / scan / scatter); one thread per read rolls
 // the forward and reverse-complement words over the sequence line and emits one u64 per window
-// (sentinel for invalid windows); radix sort + run-length encode (CUB); filter/clamp; records
-// and prefix LUT are packed on the device and written by the host.
+// (sentinel for invalid windows); the library's own radix sort (kmx_sort.cu, keys only); run heads and the -ci filter
+// are two stream compactions (count per tile / scan / write); records and prefix LUT are packed on the device and
+// written by the host.  Input files may be gzip-compressed (zlib on the host).  No library kernels.
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_run_length_encode.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/device/device_select.cuh>
+#include <zlib.h>
 #include <string>
 #include <vector>
 #include "../../include/kmx.h"
 #include "kmx_core.cuh"
+#include "kmx_launch.h"
 
 namespace kmx {
 int set_error(int code, const char* fmt, ...);   // kmx_host.cu
@@ -36,7 +35,7 @@ namespace {
 
 constexpr int kTextTile = 4096;
 
-__global__ void newline_count_kernel(const uint8_t* __restrict__ text, uint64_t n, uint32_t* __restrict__ tile_cnt) {
+__global__ void newline_count_kernel(const uint8_t* __restrict__ text, uint64_t n, uint64_t* __restrict__ tile_cnt) {
 	const uint64_t tiles = (n + kTextTile - 1) / kTextTile;
 	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 		const uint64_t lo = tile * kTextTile, hi = min(n, lo + kTextTile);
@@ -115,15 +114,126 @@ __global__ void extract_kernel(const uint8_t* __restrict__ text, const uint64_t*
 	}
 }
 
-struct KeepCount {
-	uint32_t ci, cx;
-	__host__ __device__ bool operator()(const uint32_t& c) const { return c >= ci && c <= cx; }
-};
+// ---- exclusive scan of n 64-bit values (n + 1 outputs: out[n] = total): block sums, one-block scan of the sums, block scans ----
+constexpr int kScanTile = 2048;
 
-__global__ void flag_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n, uint32_t ci, uint32_t cx,
-                            uint8_t* __restrict__ flags) {
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long x, unsigned long long* s_warp /*[9]*/, unsigned long long* total) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long incl = x;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	__syncthreads();
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	unsigned long long before = 0, all = 0;
+#pragma unroll
+	for (int w = 0; w < 8; w++) {
+		const unsigned long long v = s_warp[w];
+		before += w < warp ? v : 0;
+		all += v;
+	}
+	*total = all;
+	return before + incl - x;
+}
+
+__global__ void __launch_bounds__(256) scan_sums_kernel(const uint64_t* __restrict__ in, uint64_t n, uint64_t* __restrict__ sums) {
+	__shared__ unsigned long long s_warp[9];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+	unsigned long long x = 0;
+	for (int j = 0; j < kScanTile / 256; j++) {
+		const uint64_t i = base + (uint64_t)j * 256 + threadIdx.x;
+		x += i < n ? in[i] : 0;
+	}
+	unsigned long long total;
+	block_excl_scan_u64(x, s_warp, &total);
+	if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(256) scan_of_sums_kernel(uint64_t* __restrict__ sums, uint64_t n_tiles, uint64_t* __restrict__ grand_total) {
+	__shared__ unsigned long long s_warp[9];
+	unsigned long long carry = 0;
+	for (uint64_t b = 0; b < n_tiles; b += 256) {
+		const uint64_t i = b + threadIdx.x;
+		const unsigned long long x = i < n_tiles ? sums[i] : 0;
+		unsigned long long total;
+		const unsigned long long ex = block_excl_scan_u64(x, s_warp, &total);
+		if (i < n_tiles) sums[i] = carry + ex;
+		carry += total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(256) scan_write_kernel(const uint64_t* __restrict__ in, uint64_t n, const uint64_t* __restrict__ sums,
+                                                         uint64_t* __restrict__ out) {
+	__shared__ unsigned long long s_warp[9];
+	const uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+	// thread t takes 8 consecutive elements
+	unsigned long long v[kScanTile / 256], x = 0;
+#pragma unroll
+	for (int j = 0; j < kScanTile / 256; j++) {
+		const uint64_t i = base + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
+		v[j] = i < n ? in[i] : 0;
+		x += v[j];
+	}
+	unsigned long long total;
+	unsigned long long ex = block_excl_scan_u64(x, s_warp, &total) + sums[blockIdx.x];
+#pragma unroll
+	for (int j = 0; j < kScanTile / 256; j++) {
+		const uint64_t i = base + (uint64_t)threadIdx.x * (kScanTile / 256) + j;
+		if (i < n) out[i] = ex;
+		ex += v[j];
+	}
+}
+
+// out[0 .. n) = exclusive prefix sums of in, out[n] = total (also copied to *total_h); d_sums needs n / 2048 + 2 words
+cudaError_t exclusive_scan_u64(const uint64_t* d_in, uint64_t n, uint64_t* d_out, uint64_t* d_sums, uint64_t* total_h) {
+	const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+	if (n_tiles) {
+		scan_sums_kernel<<<(unsigned)n_tiles, 256>>>(d_in, n, d_sums);
+		scan_of_sums_kernel<<<1, 256>>>(d_sums, n_tiles, d_out + n);
+		scan_write_kernel<<<(unsigned)n_tiles, 256>>>(d_in, n, d_sums, d_out);
+		note_launch(3);
+	} else {
+		cudaError_t e = cudaMemset(d_out, 0, 8);
+		if (e != cudaSuccess) return e;
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	return cudaMemcpy(total_h, d_out + n, 8, cudaMemcpyDeviceToHost);
+}
+
+// ---- stream compaction in two passes around a scan: flags[i] (0 / 1 as u64) -> positions --------------------------------
+// run heads of the sorted window list: head[i] = keys[i] != keys[i - 1]
+__global__ void head_flag_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ flag) {
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-		flags[i] = keys[i] != kInvalid && counts[i] >= ci && counts[i] <= cx;
+		flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// run j starts at head_at[j]; its length is the distance to the next head (head_at[n_runs] = n)
+__global__ void head_write_kernel(const uint64_t* __restrict__ flag, const uint64_t* __restrict__ pos, uint64_t n, uint64_t n_runs,
+                                  uint64_t* __restrict__ head_at) {
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		if (flag[i]) head_at[pos[i]] = i;
+	if (blockIdx.x == 0 && threadIdx.x == 0) head_at[n_runs] = n;
+}
+// keep[j] = run j is a k-mer (not the invalid-window sentinel) seen at least ci times
+__global__ void keep_flag_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ head_at, uint64_t n_runs, uint32_t ci,
+                                 uint64_t* __restrict__ flag) {
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_runs; j += (uint64_t)gridDim.x * blockDim.x)
+		flag[j] = (keys[head_at[j]] != kInvalid && head_at[j + 1] - head_at[j] >= (uint64_t)ci) ? 1 : 0;
+}
+__global__ void keep_write_kernel(const uint64_t* __restrict__ keys, const uint64_t* __restrict__ head_at, const uint64_t* __restrict__ flag,
+                                  const uint64_t* __restrict__ pos, uint64_t n_runs, uint64_t* __restrict__ kept, uint32_t* __restrict__ kept_cnt) {
+	for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_runs; j += (uint64_t)gridDim.x * blockDim.x) {
+		if (flag[j]) {
+			const uint64_t len = head_at[j + 1] - head_at[j];
+			kept[pos[j]] = keys[head_at[j]];
+			kept_cnt[pos[j]] = len > 0xFFFFFFFFULL ? 0xFFFFFFFFu : (uint32_t)len;
+		}
+	}
 }
 
 // record bytes (big-endian suffix + little-endian counter, kmc_file.cpp:447-494) of every kept k-mer
@@ -179,29 +289,31 @@ extern "C" int kmx_count_fastq(const char* const* fastq_paths, int n_files, int 
 	if (!fastq_paths || n_files < 1 || !out_base) return set_error(KMX_EARG, "null argument");
 	if (k < 3 || k > 32 || ci < 1 || cs < ci || cs > 65535) return set_error(KMX_EARG, "unsupported k=%d ci=%d cs=%d (3 <= k <= 32, 1 <= ci <= cs <= 65535)", k, ci, cs);
 	if (kmx_device_count() < 1) return set_error(KMX_ENOGPU, "no usable CUDA device (libkmx has no CPU path)");
-	// ---- read the files (plain-text 4-line FASTQ) ----
+	// ---- read the files: 4-line FASTQ, plain text or gzip (zlib reads both transparently) ----
 	std::vector<uint8_t> text;
 	for (int f = 0; f < n_files; f++) {
-		FILE* fp = fopen(fastq_paths[f], "rb");
-		if (!fp) return set_error(KMX_EIO, "cannot open %s (%s)", fastq_paths[f], strerror(errno));
-		unsigned char magic[2] = { 0, 0 };
-		size_t got = fread(magic, 1, 2, fp);
-		if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-			fclose(fp);
-			return set_error(KMX_EFORMAT, "%s is gzip-compressed; decompress it first (only plain-text FASTQ is read)", fastq_paths[f]);
-		}
-		fseeko(fp, 0, SEEK_END);
-		const uint64_t sz = (uint64_t)ftello(fp);
-		rewind(fp);
+		gzFile gz = gzopen(fastq_paths[f], "rb");
+		if (!gz) return set_error(KMX_EIO, "cannot open %s (%s)", fastq_paths[f], strerror(errno));
+		gzbuffer(gz, 1u << 20);
 		const size_t old = text.size();
-		text.resize(old + sz + 1);
-		if (sz && fread(text.data() + old, 1, sz, fp) != sz) {
-			fclose(fp);
-			return set_error(KMX_EIO, "short read on %s", fastq_paths[f]);
+		size_t at = old;
+		for (;;) {
+			if (text.size() < at + (8u << 20)) text.resize(at + (64u << 20));
+			const int got = gzread(gz, text.data() + at, 8u << 20);
+			if (got < 0) {
+				int errnum = 0;
+				const char* msg = gzerror(gz, &errnum);
+				std::string m = msg ? msg : "read error";
+				gzclose(gz);
+				return set_error(KMX_EIO, "%s: %s", fastq_paths[f], m.c_str());
+			}
+			if (got == 0) break;
+			at += (size_t)got;
 		}
-		fclose(fp);
-		if (sz && text[old + sz - 1] != '\n') text[old + sz] = '\n';      // every file ends with a newline
-		else text.resize(old + sz);
+		gzclose(gz);
+		text.resize(at + 1);
+		if (at > old && text[at - 1] != '\n') text[at] = '\n';           // every file ends with a newline
+		else text.resize(at);
 	}
 	const uint64_t n_bytes = text.size();
 	int dev = 0, sms = 148;
@@ -214,88 +326,80 @@ extern "C" int kmx_count_fastq(const char* const* fastq_paths, int n_files, int 
 	std::vector<uint8_t>().swap(text);
 	// ---- newline index ----
 	const uint64_t tiles = (n_bytes + kTextTile - 1) / kTextTile;
-	uint32_t* d_tile_cnt = nullptr;
+	uint64_t* d_tile_cnt = nullptr;
 	uint64_t* d_tile_off = nullptr;
-	CUC(S.alloc(&d_tile_cnt, (tiles + 1) * 4));
+	uint64_t* d_sums = nullptr;
+	CUC(S.alloc(&d_tile_cnt, (tiles + 1) * 8));
 	CUC(S.alloc(&d_tile_off, (tiles + 1) * 8));
+	CUC(S.alloc(&d_sums, (tiles / kScanTile + 2) * 8));
 	const int grid = sms * 8;
 	uint64_t n_lines = 0;
 	if (tiles) {
 		newline_count_kernel<<<grid, 256>>>(d_text, n_bytes, d_tile_cnt);
-		void* d_tmp = nullptr;
-		size_t tmp_bytes = 0;
-		CUC(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_tile_cnt, d_tile_off, (int64_t)tiles + 1));
-		CUC(S.alloc(&d_tmp, tmp_bytes));
-		CUC(cudaMemset(d_tile_cnt + tiles, 0, 4));
-		CUC(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_tile_cnt, d_tile_off, (int64_t)tiles + 1));
-		CUC(cudaMemcpy(&n_lines, d_tile_off + tiles, 8, cudaMemcpyDeviceToHost));
+		note_launch();
+		CUC(exclusive_scan_u64(d_tile_cnt, tiles, d_tile_off, d_sums, &n_lines));
 	}
 	const uint64_t n_reads = n_lines / 4;
 	uint64_t* d_line = nullptr;
 	CUC(S.alloc(&d_line, (n_lines + 2) * 8));
 	CUC(cudaMemset(d_line, 0, 8));
-	if (tiles) newline_scatter_kernel<<<grid, 256>>>(d_text, n_bytes, d_tile_off, d_line);
+	if (tiles) {
+		newline_scatter_kernel<<<grid, 256>>>(d_text, n_bytes, d_tile_off, d_line);
+		note_launch();
+	}
 	// ---- windows ----
 	uint64_t* d_win = nullptr;
 	uint64_t* d_win_off = nullptr;
+	uint64_t* d_sums2 = nullptr;
 	CUC(S.alloc(&d_win, (n_reads + 1) * 8));
 	CUC(S.alloc(&d_win_off, (n_reads + 1) * 8));
+	CUC(S.alloc(&d_sums2, (n_reads / kScanTile + 2) * 8));
 	uint64_t n_windows = 0;
 	if (n_reads) {
 		window_count_kernel<<<grid, 256>>>(d_text, d_line, n_reads, k, d_win);
-		CUC(cudaMemset(d_win + n_reads, 0, 8));
-		void* d_tmp = nullptr;
-		size_t tmp_bytes = 0;
-		CUC(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_win, d_win_off, (int64_t)n_reads + 1));
-		CUC(S.alloc(&d_tmp, tmp_bytes));
-		CUC(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_win, d_win_off, (int64_t)n_reads + 1));
-		CUC(cudaMemcpy(&n_windows, d_win_off + n_reads, 8, cudaMemcpyDeviceToHost));
+		note_launch();
+		CUC(exclusive_scan_u64(d_win, n_reads, d_win_off, d_sums2, &n_windows));
 	}
+	if (n_windows >= (1ULL << 32)) return set_error(KMX_ERANGE, "%llu k-mer windows: this single-pass counter holds every window on the device (< 2^32)", (unsigned long long)n_windows);
 	uint64_t* d_keys = nullptr;
 	uint64_t* d_sorted = nullptr;
 	CUC(S.alloc(&d_keys, (n_windows + 1) * 8));
 	CUC(S.alloc(&d_sorted, (n_windows + 1) * 8));
-	if (n_windows) extract_kernel<<<grid, 256>>>(d_text, d_line, d_win_off, n_reads, k, d_keys);
-	// ---- sort + run-length encode ----
-	uint64_t* d_unique = nullptr;
-	uint32_t* d_counts = nullptr;
-	uint64_t* d_runs = nullptr;
-	CUC(S.alloc(&d_unique, (n_windows + 1) * 8));
-	CUC(S.alloc(&d_counts, (n_windows + 1) * 4));
-	CUC(S.alloc(&d_runs, 8));
-	uint64_t n_unique = 0;
 	if (n_windows) {
-		void* d_tmp = nullptr;
-		size_t tmp_bytes = 0;
-		CUC(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_sorted, (int64_t)n_windows, 0, 64));
-		CUC(S.alloc(&d_tmp, tmp_bytes));
-		CUC(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_sorted, (int64_t)n_windows, 0, 64));
-		void* d_tmp2 = nullptr;
-		size_t tmp2 = 0;
-		CUC(cub::DeviceRunLengthEncode::Encode(nullptr, tmp2, d_sorted, d_unique, d_counts, d_runs, (int64_t)n_windows));
-		CUC(S.alloc(&d_tmp2, tmp2));
-		CUC(cub::DeviceRunLengthEncode::Encode(d_tmp2, tmp2, d_sorted, d_unique, d_counts, d_runs, (int64_t)n_windows));
-		CUC(cudaMemcpy(&n_unique, d_runs, 8, cudaMemcpyDeviceToHost));
+		extract_kernel<<<grid, 256>>>(d_text, d_line, d_win_off, n_reads, k, d_keys);
+		note_launch();
 	}
-	// ---- filter (ci <= count), keep order ----
-	uint8_t* d_flags = nullptr;
+	// ---- sort; run heads; runs that are k-mers seen at least ci times (order kept) ----
+	uint64_t n_unique = 0, n_kept = 0;
 	uint64_t* d_kept = nullptr;
 	uint32_t* d_kept_cnt = nullptr;
-	uint64_t* d_nkept = nullptr;
-	CUC(S.alloc(&d_flags, n_unique + 1));
-	CUC(S.alloc(&d_kept, (n_unique + 1) * 8));
-	CUC(S.alloc(&d_kept_cnt, (n_unique + 1) * 4));
-	CUC(S.alloc(&d_nkept, 8));
-	uint64_t n_kept = 0;
-	if (n_unique) {
-		flag_kernel<<<grid, 256>>>(d_unique, d_counts, n_unique, (uint32_t)ci, 0xFFFFFFFFu, d_flags);
+	if (n_windows) {
 		void* d_tmp = nullptr;
-		size_t tmp_bytes = 0;
-		CUC(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, d_unique, d_flags, d_kept, d_nkept, (int64_t)n_unique));
-		CUC(S.alloc(&d_tmp, tmp_bytes));
-		CUC(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_unique, d_flags, d_kept, d_nkept, (int64_t)n_unique));
-		CUC(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, d_counts, d_flags, d_kept_cnt, d_nkept, (int64_t)n_unique));
-		CUC(cudaMemcpy(&n_kept, d_nkept, 8, cudaMemcpyDeviceToHost));
+		CUC(S.alloc(&d_tmp, radix_sort_temp_bytes(n_windows)));
+		CUC(launch_radix_sort_pairs(d_tmp, d_keys, d_sorted, nullptr, nullptr, n_windows, 64, nullptr));
+		uint64_t* d_flag = d_keys;                              // the unsorted windows are not needed any more
+		uint64_t* d_pos = nullptr;
+		uint64_t* d_sums3 = nullptr;
+		CUC(S.alloc(&d_pos, (n_windows + 1) * 8));
+		CUC(S.alloc(&d_sums3, (n_windows / kScanTile + 2) * 8));
+		head_flag_kernel<<<grid, 256>>>(d_sorted, n_windows, d_flag);
+		note_launch();
+		CUC(exclusive_scan_u64(d_flag, n_windows, d_pos, d_sums3, &n_unique));
+		uint64_t* d_head = nullptr;
+		CUC(S.alloc(&d_head, (n_unique + 1) * 8));
+		head_write_kernel<<<grid, 256>>>(d_flag, d_pos, n_windows, n_unique, d_head);
+		keep_flag_kernel<<<grid, 256>>>(d_sorted, d_head, n_unique, (uint32_t)ci, d_flag);
+		note_launch(2);
+		CUC(exclusive_scan_u64(d_flag, n_unique, d_pos, d_sums3, &n_kept));
+		CUC(S.alloc(&d_kept, (n_kept + 1) * 8));
+		CUC(S.alloc(&d_kept_cnt, (n_kept + 1) * 4));
+		keep_write_kernel<<<grid, 256>>>(d_sorted, d_head, d_flag, d_pos, n_unique, d_kept, d_kept_cnt);
+		note_launch();
+		CUC(cudaGetLastError());
+		// n_unique counts k-mers: the sentinel run of the invalid windows is not one
+		uint64_t last = 0;
+		CUC(cudaMemcpy(&last, d_sorted + n_windows - 1, 8, cudaMemcpyDeviceToHost));
+		if (last == kInvalid) n_unique--;
 	}
 	// ---- KMC 2/3 files ----
 	int lut = k % 4 == 0 ? 4 : k % 4;                       // (k - lut) % 4 == 0
@@ -311,6 +415,7 @@ extern "C" int kmx_count_fastq(const char* const* fastq_paths, int n_files, int 
 	CUC(S.alloc(&d_lut, (n_prefix + 1) * 8));
 	if (n_kept) pack_records_kernel<<<grid, 256>>>(d_kept, d_kept_cnt, n_kept, suffix_bytes, counter_bytes, (uint32_t)cs, d_rec);
 	lut_kernel<<<(int)((n_prefix + 256) / 256), 256>>>(d_kept, n_kept, 8 * suffix_bytes, n_prefix, d_lut);
+	note_launch(2);
 	CUC(cudaDeviceSynchronize());
 	std::vector<uint8_t> rec((size_t)n_kept * rb);
 	std::vector<uint64_t> lut_h(n_prefix + 1);

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(uint32_t* __re
 	if (threadIdx.x == 0) total[blockIdx.x] = s_carry;
 }
 
+template <bool VALS>
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                                                                      int shift, uint32_t n_chunks, const uint32_t* __restrict__ hist,
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 			const uint32_t x = (uint32_t)warp * (kSortPer * 32) + (uint32_t)j * 32 + (uint32_t)lane;
 			const bool valid = x < n_sub;
 			key[j] = valid ? keys_in[sub_base + x] : 0;
-			val[j] = valid ? vals_in[sub_base + x] : 0;
+			val[j] = (VALS && valid) ? vals_in[sub_base + x] : 0;
 			dig[j] = valid ? ((uint32_t)(key[j] >> shift) & (kRadix - 1)) : (uint32_t)kRadix;   // 256 = not a key
 			const uint32_t peers = __match_any_sync(0xffffffffu, dig[j]);
 			const int leader = __ffs((int)peers) - 1;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 			if (dig[j] < (uint32_t)kRadix) {
 				const uint32_t at = s_start[dig[j]] + s_wcnt[warp][dig[j]] + rnk[j];
 				s_keys[at] = key[j];
-				s_vals[at] = val[j];
+				if (VALS) s_vals[at] = val[j];
 			}
 		}
 		__syncthreads();
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint6
 			const uint32_t d = (uint32_t)(kx >> shift) & (kRadix - 1);
 			const unsigned long long dst = s_base[d] + (x - s_start[d]);
 			keys_out[dst] = kx;
-			vals_out[dst] = s_vals[x];
+			if (VALS) vals_out[dst] = s_vals[x];
 		}
 		__syncthreads();
 		s_base[threadIdx.x] += s_cnt[threadIdx.x];
@@ -186,10 +187,12 @@ size_t radix_sort_temp_bytes(size_t n) {
 	return align256(n * 8) + align256(n * 4) + align256((size_t)kRadix * sort_chunks(n) * 4) + align256(kRadix * 4);
 }
 
+// d_vals_in == nullptr: keys only (the k-mer counting stage)
 cudaError_t launch_radix_sort_pairs(void* d_temp, const uint64_t* d_keys_in, uint64_t* d_keys_out, const uint32_t* d_vals_in,
                                     uint32_t* d_vals_out, size_t n, int key_bits, cudaStream_t stream) {
 	if (n == 0) return cudaSuccess;
 	if (n >= ((size_t)1 << 32)) return cudaErrorInvalidValue;   // 32-bit chunk histograms (the rest table's indices are int anyway, rest.hpp:66-70)
+	const bool vals = d_vals_in != nullptr;
 	uint8_t* t = (uint8_t*)d_temp;
 	uint64_t* alt_keys = (uint64_t*)t;
 	uint32_t* alt_vals = (uint32_t*)(t + align256(n * 8));
@@ -207,7 +210,8 @@ cudaError_t launch_radix_sort_pairs(void* d_temp, const uint64_t* d_keys_in, uin
 		const int shift = 8 * p;
 		radix_hist_kernel<<<n_chunks, kSortThreads, 0, stream>>>(src_k, n, shift, n_chunks, hist);
 		radix_scan_kernel<<<kRadix, kSortThreads, 0, stream>>>(hist, n_chunks, total);
-		radix_scatter_kernel<<<n_chunks, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, shift, n_chunks, hist, total);
+		if (vals) radix_scatter_kernel<true><<<n_chunks, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n, shift, n_chunks, hist, total);
+		else radix_scatter_kernel<false><<<n_chunks, kSortThreads, 0, stream>>>(src_k, nullptr, dst_k, nullptr, n, shift, n_chunks, hist, total);
 		note_launch(3);
 		src_k = dst_k;
 		src_v = dst_v;
