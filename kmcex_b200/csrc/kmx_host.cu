@@ -35,6 +35,7 @@ static thread_local int g_err_code = 0;
 static int g_device = 0;                       // process-wide default (kmx_set_device)
 static thread_local int t_device = -1;         // per-thread override (threads of an in-process team build)
 static std::atomic<unsigned long long> g_launches{ 0 };
+constexpr size_t kL2FetchDefault = 0;         // 0: leave the device's setting alone (set from the A/B, KMX_L2_FETCH)
 
 namespace kmx {
 
@@ -104,6 +105,14 @@ int require_gpu(int* sm_count) {
 		CU(cudaGetDeviceProperties(&prop, dev));
 		if (prop.major < 10) return set_error(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
 		cached_sm[dev] = prop.multiProcessorCount;
+		// The path is random 8-byte probes of arrays far larger than the L2: by default the L2 fetches 64 bytes from DRAM per
+		// missing 32-byte sector (ncu on the HC14 shape: 59.6 DRAM bytes read per probe), i.e. half of the DRAM traffic is never
+		// used.  Ask for 32-byte fetches (a hint the driver may ignore); KMX_L2_FETCH=64|128 restores larger ones.
+		size_t fetch = kL2FetchDefault;
+		if (const char* e = getenv("KMX_L2_FETCH")) fetch = (size_t)atoi(e);
+		if (fetch == 32 || fetch == 64 || fetch == 128) {
+			if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, fetch) != cudaSuccess) cudaGetLastError();
+		}
 	}
 	if (sm_count) *sm_count = cached_sm[dev];
 	return KMX_OK;
@@ -113,7 +122,7 @@ int require_gpu(int* sm_count) {
 
 #define fail kmx::set_error
 
-constexpr int kQueryL2Default = 0;            // set from the A/B on the HC14 shape (KMX_QUERY_L2)
+constexpr int kQueryL2Default = 7;            // A/B on the HC14 shape (profiles/r2_d_query_l2_ab.log): 2.55 -> 2.79 G queries/s
 
 // =========================================================================================
 // OccuBin (occu_bin.hpp:27-83) as two lookup tables
@@ -384,7 +393,7 @@ extern "C" int kmx_set_device(int ordinal) {
 	g_device = ordinal;
 	t_device = -1;
 	CU(cudaSetDevice(ordinal));
-	return KMX_OK;
+	return require_gpu(nullptr);                          // architecture check + per-device settings, once
 }
 
 // the GPUs one KModel::init is spread over inside this process (kmx_set_devices; default from the environment: KMX_GPUS=N)

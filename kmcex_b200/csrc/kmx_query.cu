@@ -24,19 +24,26 @@
 
 namespace kmx {
 
-template <int K, int H, int B>
+template <int K, int H, int B, int L = 0>
 struct QueryCfg {
 	const DevModel& m;
-	// L2 policy of the probes (m.query_l2, set for models beyond the L2): km_back is touched by every query and small enough
-	// to stay resident (evict-last), the coupled arrays and the Bloom filters are far larger than the L2 and stream through it
-	// (evict-first); otherwise the default policy.  Every probe carries its structure's policy: no branch in the hot path.
+	// L = 1 (models beyond the L2, m.query_l2 != 0): every probe carries an L2 eviction policy chosen per structure -- km_back is
+	// touched by every query and small enough to stay resident (evict-last), the coupled arrays and the Bloom filters are far
+	// larger than the L2 and stream through it (evict-first).  L = 0: plain read-only loads, no policy operand.
 	unsigned long long pol_back, pol_cells, pol_bloom;
 	__device__ __forceinline__ explicit QueryCfg(const DevModel& mm) : m(mm) {
-		const unsigned long long normal = make_evict_normal_policy();
-		pol_back = (mm.query_l2 & 1) ? make_evict_last_policy() : normal;
-		pol_cells = (mm.query_l2 & 2) ? make_evict_first_policy() : normal;
-		pol_bloom = (mm.query_l2 & 4) ? make_evict_first_policy() : normal;
+		if (L) {
+			const unsigned long long normal = make_evict_normal_policy();
+			pol_back = (mm.query_l2 & 1) ? make_evict_last_policy() : normal;
+			pol_cells = (mm.query_l2 & 2) ? make_evict_first_policy() : normal;
+			pol_bloom = (mm.query_l2 & 4) ? make_evict_first_policy() : normal;
+		} else {
+			pol_back = pol_cells = pol_bloom = 0;
+		}
 	}
+	__device__ __forceinline__ bool test_bloom(const DevFilter& f, uint64_t h) const { return L ? filter_test_hint(f, h, pol_bloom) : filter_test(f, h); }
+	__device__ __forceinline__ bool test_back(const DevFilter& f, uint64_t h) const { return L ? filter_test_hint(f, h, pol_back) : filter_test(f, h); }
+	__device__ __forceinline__ unsigned long long load_cell(const unsigned long long* p) const { return L ? ldg_hint64(p, pol_cells) : __ldg(p); }
 	__device__ __forceinline__ int k() const { return K ? K : m.k; }
 	__device__ __forceinline__ int h() const { return H ? H : m.n_hash; }
 	__device__ __forceinline__ int b() const { return B ? B : m.n_bits; }
@@ -50,20 +57,23 @@ template <int K, int H, int B>
 struct QueryHashes {
 	HashPrep p31;
 	uint64_t h31[kHmax(H) - 1], h29[kHmax(H) - 2];
-	__device__ __forceinline__ void compute(const QueryCfg<K, H, B>& c, uint64_t r) {
+	template <int L>
+	__device__ __forceinline__ void compute(const QueryCfg<K, H, B, L>& c, uint64_t r) {
 		HashPrep p29;
 		hash_prepare(r, c.k(), p31);
 		hash_prepare(middle_r(r, c.k()), c.k() - 2, p29);
 		finish(c, p29);
 	}
 	// from the raw characters of the string: kmer and kmer.substr(1, k - 2) (kmodel.hpp:388)
-	__device__ __forceinline__ void compute_bytes(const QueryCfg<K, H, B>& c, const uint8_t* s) {
+	template <int L>
+	__device__ __forceinline__ void compute_bytes(const QueryCfg<K, H, B, L>& c, const uint8_t* s) {
 		HashPrep p29;
 		hash_prepare_bytes(s, c.k(), p31);
 		hash_prepare_bytes(s + 1, c.k() - 2, p29);
 		finish(c, p29);
 	}
-	__device__ __forceinline__ void finish(const QueryCfg<K, H, B>& c, const HashPrep& p29) {
+	template <int L>
+	__device__ __forceinline__ void finish(const QueryCfg<K, H, B, L>& c, const HashPrep& p29) {
 #pragma unroll
 		for (int j = 0; j < kHmax(H) - 1; j++)
 			if (j < c.h() - 1) h31[j] = hash_finish(p31, c.k(), c_seeds[j]);
@@ -80,8 +90,8 @@ struct QueryHashes {
 // costs ~2 + 0.25 * 9 sector loads per pair instead of 11 (the reference short-circuits too).
 constexpr int kStageA = 2;
 
-template <int K, int H, int B>
-__device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q) {
+template <int K, int H, int B, int L>
+__device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B, L>& c, const QueryHashes<K, H, B>& q) {
 	const DevModel& m = c.m;
 	const int hb = c.h() - 1, hk = c.h() - 2;
 	bool hit[kMaxBf];
@@ -92,7 +102,7 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 			bool ok = true;
 #pragma unroll
 			for (int j = 0; j < kStageA; j++)
-				if (j < hb) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
+				if (j < hb) ok &= c.test_bloom(m.bf[i], q.h31[j]);
 			hit[i] = ok;
 		}
 	}
@@ -108,9 +118,9 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 			pending &= pending - 1;
 			bool ok = true;
 #pragma unroll
-			for (int j = kStageA; j < kHmax(H) - 1; j++) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
+			for (int j = kStageA; j < kHmax(H) - 1; j++) ok &= c.test_bloom(m.bf[i], q.h31[j]);
 #pragma unroll
-			for (int j = 0; j < kHmax(H) - 2; j++) ok &= filter_test_hint(m.bf_back[i], q.h29[j], c.pol_bloom);
+			for (int j = 0; j < kHmax(H) - 2; j++) ok &= c.test_bloom(m.bf_back[i], q.h29[j]);
 			okmask |= (ok ? 1u : 0u) << i;
 		}
 #pragma unroll
@@ -122,10 +132,10 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 				bool ok = true;
 #pragma unroll
 				for (int j = kStageA; j < kHmax(H) - 1; j++)
-					if (j < hb) ok &= filter_test_hint(m.bf[i], q.h31[j], c.pol_bloom);
+					if (j < hb) ok &= c.test_bloom(m.bf[i], q.h31[j]);
 #pragma unroll
 				for (int j = 0; j < kHmax(H) - 2; j++)
-					if (j < hk) ok &= filter_test_hint(m.bf_back[i], q.h29[j], c.pol_bloom);
+					if (j < hk) ok &= c.test_bloom(m.bf_back[i], q.h29[j]);
 				hit[i] = ok;
 			}
 		}
@@ -137,13 +147,13 @@ __device__ __forceinline__ int check_all_bf(const QueryCfg<K, H, B>& c, const Qu
 	return 0;
 }
 
-template <int K, int H, int B>
-__device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q) {
+template <int K, int H, int B, int L>
+__device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B, L>& c, const QueryHashes<K, H, B>& q) {
 	const int hk = c.h() - 2;
 	bool ok = true;
 #pragma unroll
 	for (int j = 0; j < kHmax(H) - 2; j++)
-		if (j < hk) ok &= filter_test_hint(c.m.km_back, q.h29[j], c.pol_back);
+		if (j < hk) ok &= c.test_back(c.m.km_back, q.h29[j]);
 	return ok;
 }
 
@@ -153,8 +163,8 @@ __device__ __forceinline__ bool check_km_back(const QueryCfg<K, H, B>& c, const 
 // kStageA positions of every array, then the rest only for arrays whose first tags are all set
 // (a k-mer that does not live in an array passes with probability fill^2, about 0.15): an
 // answer needs all n_hash tags anyway, so skipping the rest cannot change it.
-template <int K, int H, int B>
-__device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const QueryHashes<K, H, B>& q, int* bins, bool* full) {
+template <int K, int H, int B, int L>
+__device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B, L>& c, const QueryHashes<K, H, B>& q, int* bins, bool* full) {
 	const DevModel& m = c.m;
 	auto position = [&](int i, int j) -> uint64_t {
 		const uint64_t h = (i == 0 && j < c.h() - 1) ? q.h31[j < kHmax(H) - 1 ? j : 0] : hash_finish(q.p31, c.k(), m.arr_seed[i][j]);
@@ -169,7 +179,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 			if (i < c.b() && j < c.h()) {
 				const uint64_t pos = position(i, j);
 				shA[i][j] = ((uint32_t)pos & 31u) ^ 7u;
-				cellA[i][j] = ldg_hint64(m.cells[i] + (pos >> 5), c.pol_cells);
+				cellA[i][j] = c.load_cell(m.cells[i] + (pos >> 5));
 			}
 		}
 	}
@@ -210,7 +220,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 			for (int j = kStageA; j < kHmax(H); j++) {
 				const uint64_t pos = fastmod(hash_finish(q.p31, c.k(), m.arr_seed[i][j]), m.arr_mod);
 				sh[j] = ((uint32_t)pos & 31u) ^ 7u;
-				cell[j] = ldg_hint64(cells + (pos >> 5), c.pol_cells);
+				cell[j] = c.load_cell(cells + (pos >> 5));
 			}
 			uint32_t bin = 0;
 			bool ok = true;
@@ -242,7 +252,7 @@ __device__ __forceinline__ void probe_arrays(const QueryCfg<K, H, B>& c, const Q
 				if (j < c.h()) {
 					const uint64_t pos = position(i, j);
 					sh[j] = ((uint32_t)pos & 31u) ^ 7u;
-					cell[j] = ldg_hint64(m.cells[i] + (pos >> 5), c.pol_cells);
+					cell[j] = c.load_cell(m.cells[i] + (pos >> 5));
 				}
 			}
 			int bin = bins[i];
@@ -308,9 +318,9 @@ __device__ __forceinline__ int rest_finish(const DevRest& R, uint64_t v, const R
 __device__ __forceinline__ int rest_lookup_indexed(const DevRest& R, uint64_t v) { return rest_finish(R, v, rest_begin(R, v)); }
 
 // get_candidates (kmodel.hpp:326-342) for one neighbour in canonical form v with its hashes q; returns -1 when it adds nothing
-template <int K, int H, int B>
+template <int K, int H, int B, int L = 0>
 __device__ __forceinline__ int neighbour_candidate_q(const DevModel& m, uint64_t v, const QueryHashes<K, H, B>& q) {
-	QueryCfg<K, H, B> c(m);
+	QueryCfg<K, H, B, L> c(m);
 	int occ = rest_lookup_indexed(m.rest, v);
 	if (occ > 0) return (int)__ldg(m.occ2bin + (occ > m.cs ? m.cs : occ));   // occ > cs is out of bounds in the reference
 	occ = check_all_bf(c, q);
@@ -327,14 +337,14 @@ __device__ __forceinline__ int neighbour_candidate_q(const DevModel& m, uint64_t
 	return result;
 }
 
-template <int K, int H, int B>
+template <int K, int H, int B, int L = 0>
 __device__ __forceinline__ int neighbour_candidate(const DevModel& m, uint64_t nb) {
-	QueryCfg<K, H, B> c(m);
+	QueryCfg<K, H, B, L> c(m);
 	uint64_t r;
 	const uint64_t v = canonical(nb, c.k(), &r);
 	QueryHashes<K, H, B> q;
 	q.compute(c, r);
-	return neighbour_candidate_q<K, H, B>(m, v, q);
+	return neighbour_candidate_q<K, H, B, L>(m, v, q);
 }
 
 // neighbour number j of the canonical k-mer v (kmodel.hpp:344-359): j < 4 successors (drop the
@@ -352,15 +362,15 @@ struct Primary {
 	int answer;       // final occurrence when path is not 5 / 6
 };
 
-template <int K, int H, int B>
-__device__ __forceinline__ int bin_to_mean(const QueryCfg<K, H, B>& c, int bin) {
+template <int K, int H, int B, int L>
+__device__ __forceinline__ int bin_to_mean(const QueryCfg<K, H, B, L>& c, int bin) {
 	if (bin < c.m.end1) return bin;
 	return bin < (1 << c.h()) ? __ldg(c.m.bin2mean + bin) : 0;   // unordered_map::operator[] yields 0 for a missing bin
 }
 
-template <int K, int H, int B, bool RAW = false>
+template <int K, int H, int B, bool RAW = false, int L = 0>
 __device__ __forceinline__ void query_primary(const DevModel& m, uint64_t v, uint64_t r, Primary& P, const uint8_t* raw = nullptr) {
-	QueryCfg<K, H, B> c(m);
+	QueryCfg<K, H, B, L> c(m);
 	// the rest lookup's loads and the Bloom wave are independent of each other
 	const RestProbe rp = rest_begin(m.rest, v);
 	QueryHashes<K, H, B> q;
@@ -537,7 +547,7 @@ __global__ void __launch_bounds__(64) query_raw_kernel(const __grid_constant__ D
 #ifndef KMX_QUERY_BLOCKS
 #define KMX_QUERY_BLOCKS 2
 #endif
-template <int K, int H, int B>
+template <int K, int H, int B, int L>
 __global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const __grid_constant__ DevModel m, const uint64_t* __restrict__ input,
                                                             size_t n, int32_t* __restrict__ out, int32_t* __restrict__ path_out,
                                                             DeferredQuery* __restrict__ defer, unsigned int* __restrict__ defer_n) {
@@ -547,7 +557,7 @@ __global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const
 		uint64_t r;
 		const uint64_t v = canonical(raw & mask2(k), k, &r);
 		Primary P;
-		query_primary<K, H, B>(m, v, r, P);
+		query_primary<K, H, B, false, L>(m, v, r, P);
 		if (path_out) path_out[i] = P.path;
 		if (P.path >= 5) {
 			// warp-aggregated append
@@ -567,10 +577,10 @@ __global__ void __launch_bounds__(256, KMX_QUERY_BLOCKS) query_fast_kernel(const
 }
 
 // kmer_to_bin's neighbour rules (kmodel.hpp:286-323), 8 lanes per deferred query
-template <int K, int H, int B>
+template <int K, int H, int B, int L>
 __global__ void __launch_bounds__(256, 2) query_slow_kernel(const __grid_constant__ DevModel m, const DeferredQuery* __restrict__ defer,
                                                             const unsigned int* __restrict__ defer_n, int32_t* __restrict__ out) {
-	QueryCfg<K, H, B> c(m);
+	QueryCfg<K, H, B, L> c(m);
 	const int k = c.k();
 	const unsigned int n = *defer_n;
 	const unsigned int groups_per_grid = gridDim.x * (blockDim.x / 8);
@@ -584,8 +594,8 @@ __global__ void __launch_bounds__(256, 2) query_slow_kernel(const __grid_constan
 		P.occ = 0;
 		int x = -1;
 		if (live) {
-			query_primary<K, H, B>(m, v, reverse_bases(v, k), P);           // the same decision the fast kernel took
-			x = neighbour_candidate<K, H, B>(m, neighbour_of(v, sub, k));
+			query_primary<K, H, B, false, L>(m, v, reverse_bases(v, k), P);   // the same decision the fast kernel took
+			x = neighbour_candidate<K, H, B, L>(m, neighbour_of(v, sub, k));
 		}
 		// reductions over the 8 lanes of the group
 		int n_cand = x >= 0 ? 1 : 0, n_low = (x >= 0 && x < m.ci + m.bf_num) ? 1 : 0;
@@ -686,12 +696,15 @@ static cudaError_t query_packed_launches(const DevModel& m, const uint64_t* d_km
                                          DeferredQuery* d_defer, unsigned int* d_defer_n, int sm_count, cudaStream_t stream) {
 	const int grid = query_grid(n, sm_count);
 	const int slow_grid = sm_count * 2;
-	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5) {
-		query_fast_kernel<31, 7, 5><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
-		if (d_out) query_slow_kernel<31, 7, 5><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
+	if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5 && m.query_l2 == 0) {
+		query_fast_kernel<31, 7, 5, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
+		if (d_out) query_slow_kernel<31, 7, 5, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
+	} else if (m.k == 31 && m.n_hash == 7 && m.n_bits == 5) {
+		query_fast_kernel<31, 7, 5, 1><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
+		if (d_out) query_slow_kernel<31, 7, 5, 1><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
 	} else {
-		query_fast_kernel<0, 0, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
-		if (d_out) query_slow_kernel<0, 0, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
+		query_fast_kernel<0, 0, 0, 0><<<grid, 256, 0, stream>>>(m, d_kmers, n, d_out, d_path, d_defer, d_defer_n);
+		if (d_out) query_slow_kernel<0, 0, 0, 0><<<slow_grid, 256, 0, stream>>>(m, d_defer, d_defer_n, d_out);
 	}
 	note_launch(d_out ? 2 : 1);
 	return cudaGetLastError();
