@@ -105,9 +105,9 @@ int require_gpu(int* sm_count) {
 		CU(cudaGetDeviceProperties(&prop, dev));
 		if (prop.major < 10) return set_error(KMX_ENOGPU, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
 		cached_sm[dev] = prop.multiProcessorCount;
-		// The path is random 8-byte probes of arrays far larger than the L2: by default the L2 fetches 64 bytes from DRAM per
-		// missing 32-byte sector (ncu on the HC14 shape: 59.6 DRAM bytes read per probe), i.e. half of the DRAM traffic is never
-		// used.  Ask for 32-byte fetches (a hint the driver may ignore); KMX_L2_FETCH=64|128 restores larger ones.
+		// The path is random 8-byte probes of arrays far larger than the L2, and the L2 fetches at least 64 bytes from DRAM per
+		// missing 32-byte sector (ncu on the HC14 shape: 60-95 DRAM bytes read per probe).  KMX_L2_FETCH=32|64|128 passes the
+		// cudaLimitMaxL2FetchGranularity hint; on B200 it changes nothing (profiles/r2_e_l2_fetch_ab.log), so it is left alone.
 		size_t fetch = kL2FetchDefault;
 		if (const char* e = getenv("KMX_L2_FETCH")) fetch = (size_t)atoi(e);
 		if (fetch == 32 || fetch == 64 || fetch == 128) {

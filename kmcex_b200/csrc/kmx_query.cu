@@ -41,6 +41,8 @@ struct QueryCfg {
 			pol_back = pol_cells = pol_bloom = 0;
 		}
 	}
+	// (the ordinary load path instead of the read-only one makes no difference: same rate, same DRAM bytes per probe --
+	// profiles/r2_f_query_ld_ab.log)
 	__device__ __forceinline__ bool test_bloom(const DevFilter& f, uint64_t h) const { return L ? filter_test_hint(f, h, pol_bloom) : filter_test(f, h); }
 	__device__ __forceinline__ bool test_back(const DevFilter& f, uint64_t h) const { return L ? filter_test_hint(f, h, pol_back) : filter_test(f, h); }
 	__device__ __forceinline__ unsigned long long load_cell(const unsigned long long* p) const { return L ? ldg_hint64(p, pol_cells) : __ldg(p); }
