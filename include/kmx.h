@@ -56,8 +56,10 @@ typedef struct kmx_info_t {
 	uint64_t insert_accepted;
 	uint64_t insert_iterations;  /* reservation iterations summed over all rounds            */
 	uint64_t batches;
-	uint64_t insert_phase_cycles[8];  /* SM cycles per phase of the insert kernel (diagnostic): reserve/commit of
-	                                      the first iteration, of later iterations, tile scan, place, move */
+	uint64_t insert_phase_cycles[12]; /* SM cycles per phase of the insert kernel as seen by one thread (diagnostic): [0] phase 0,
+	                                     [1] phase 1, [3] contested passes, [5] place, [6] move, [7] cross-GPU wait; the part spent
+	                                     in the thread's own loop, the rest being barrier wait: [2] phase 0, [4] phase 1, [8] place,
+	                                     [9] move, [10] contested passes; [11] contested passes run */
 	/* device times of the last build, milliseconds (CUDA events on the build stream) */
 	float ms_upload, ms_count, ms_encode, ms_insert, ms_rest, ms_total_device;
 	double build_time_cost;      /* host wall seconds of init, as the reference reports it   */
@@ -189,6 +191,8 @@ int kmx_microbench_grid_barrier(int mode, int threads, int blocks_per_sm, int re
 /* nanoseconds per returning atomicAdd when every warp of a full grid hammers n_counters addresses (list appends) */
 int kmx_microbench_hot_atomic(int n_counters, int per_warp, float* ns_out);
 int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out);
+/* milliseconds per pass of a read-only streaming kernel over `bytes` of device memory: the ceiling of the counting pass */
+int kmx_microbench_stream_read(uint64_t bytes, int blocks_per_sm, int reps, float* ms_out);
 
 #ifdef __cplusplus
 }

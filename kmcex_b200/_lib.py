@@ -16,7 +16,7 @@ class KmxInfo(C.Structure):
         ("kmer_counts", C.c_uint64 * 3),
         ("bf_bytes", C.c_uint64), ("km_bytes", C.c_uint64), ("km_back_bytes", C.c_uint64), ("rest_bytes", C.c_uint64),
         ("insert_attempts", C.c_uint64), ("insert_accepted", C.c_uint64), ("insert_iterations", C.c_uint64), ("batches", C.c_uint64),
-        ("insert_phase_cycles", C.c_uint64 * 8),
+        ("insert_phase_cycles", C.c_uint64 * 12),
         ("ms_upload", C.c_float), ("ms_count", C.c_float), ("ms_encode", C.c_float), ("ms_insert", C.c_float), ("ms_rest", C.c_float),
         ("ms_total_device", C.c_float),
         ("build_time_cost", C.c_double),
@@ -92,6 +92,7 @@ SIGNATURES = {
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_grid_barrier": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_hot_atomic": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "kmx_microbench_stream_read": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_windowed": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }
 

@@ -809,6 +809,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				int cur = 1;
 				uint32_t tab = 0;
 				bool fresh = true;                                // status words are current: no need to re-read the cells
+				long long pass_tick = clock64();
 				while (n_list != 0) {
 					if (epoch + 2 >= kEpochMax) {
 						// keys can get no smaller: clear the tables and let every undecided item reserve again before
@@ -872,7 +873,12 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 							append(a.list[nxt], &ctl->list_n[nxt], id);
 						}
 					}
+					if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
+						vctl->phase_cycles[10] += (unsigned long long)(clock64() - pass_tick);
+						vctl->phase_cycles[11] += 1;
+					}
 					gsync_fetch(par);
+					pass_tick = clock64();
 					n_list = s_hot[nxt];
 					cur = nxt;
 					tab ^= 1u;
@@ -1065,6 +1071,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 					}
 				}
 			}
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) vctl->phase_cycles[8] += (unsigned long long)(clock64() - tick);
 			gsync_fetch(par);
 			if (s_hot[3]) return;                               // uniform over the grid (survivor list overflow)
 			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) {
@@ -1126,6 +1133,7 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 				vctl->accepted += att - fail;
 				vctl->iterations += iter;
 			}
+			if (tid == 0 && (a.phase_round < 0 || a.phase_round == t)) vctl->phase_cycles[9] += (unsigned long long)(clock64() - tick);
 			if (a.n_active > 1) __threadfence_system();          // survivors written into a peer's buffers
 			if (a.n_active > 1) GSYNC();
 			else gsync_fetch(par);

@@ -858,7 +858,13 @@ int kmx::slab_acquire(void** out, size_t bytes, int device) {
 				return KMX_OK;
 			}
 		}
-		// nothing of this size: give the memory of other cached sizes on this device back before asking for more
+	}
+	if (cudaMalloc(out, bytes) == cudaSuccess) return KMX_OK;
+	cudaGetLastError();
+	{
+		// out of memory: give the cached slabs of other sizes on this device back and try once more (a peer process may still
+		// hold a mapping of them from an earlier build of another geometry; it no longer touches it)
+		std::lock_guard<std::mutex> lock(g_slab_mu);
 		for (size_t q = 0; q < g_slab_free.size();) {
 			if (g_slab_free[q].device == device) {
 				cudaFree(g_slab_free[q].ptr);
@@ -1128,7 +1134,7 @@ static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const u
 	f.insert_accepted = ctl.accepted;
 	f.insert_iterations = ctl.iterations;
 	f.batches = b.n_batches;
-	for (int i = 0; i < 8; i++) f.insert_phase_cycles[i] = ctl.phase_cycles[i];
+	for (int i = 0; i < 12; i++) f.insert_phase_cycles[i] = ctl.phase_cycles[i];
 	f.ms_upload = b.ms_upload;
 	CU(cudaEventElapsedTime(&f.ms_count, ev[0], ev[1]));
 	CU(cudaEventElapsedTime(&f.ms_encode, ev[1], ev[2]));

@@ -93,7 +93,9 @@ struct InsertCtl {                    // lives in device memory, survives across
 	unsigned long long slot0_kmer[kMaxArrays];   // buffer slot 0 of each bucket after the last full batch
 	unsigned int slot0_occ[kMaxArrays];
 	unsigned int slot0_valid[kMaxArrays];
-	unsigned long long phase_cycles[8];   // SM cycles seen by thread 0: reserve/commit (first iteration, later), scan, place, move
+	unsigned long long phase_cycles[12];  // SM cycles seen by thread 0 of block 0: [0] phase 0, [1] phase 1, [3] contested passes, [5] place, [6] move,
+	                                      // [7] cross-GPU wait; the part of it spent in its own loop (the rest is barrier wait): [2] phase 0, [4] phase 1,
+	                                      // [8] place, [9] move, [10] contested passes; [11] contested passes run
 };
 
 struct InsertArgs {

@@ -184,3 +184,54 @@ extern "C" int kmx_microbench_hot_atomic(int n_counters, int per_warp, float* ns
 	cudaFree(sink);
 	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
 }
+
+// ---- read-only streaming ceiling: what a pure HBM read kernel reaches (the denominator of the counting pass) --------------
+namespace {
+__global__ void __launch_bounds__(256) stream_read_kernel(const uint4* __restrict__ buf, uint64_t n_vec, unsigned long long* sink) {
+	const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+	uint32_t acc = 0;
+	uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	for (; v + 3 * T < n_vec; v += 4 * T) {                     // four independent 16-byte loads in flight per thread
+		const uint4 a = __ldg(buf + v), b = __ldg(buf + v + T), c = __ldg(buf + v + 2 * T), d = __ldg(buf + v + 3 * T);
+		acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+	}
+	for (; v < n_vec; v += T) {
+		const uint4 a = __ldg(buf + v);
+		acc ^= a.x ^ a.y ^ a.z ^ a.w;
+	}
+	if (acc == 0x12345677u) *sink = acc;
+}
+}  // namespace
+
+// milliseconds per pass of a read-only grid-stride kernel over `bytes` of device memory (16-byte loads, 4 in flight per thread)
+extern "C" int kmx_microbench_stream_read(uint64_t bytes, int blocks_per_sm, int reps, float* ms_out) {
+	if (bytes < 4096 || !ms_out || reps < 1 || blocks_per_sm < 1 || blocks_per_sm > 8) return KMX_EARG;
+	uint4* buf = nullptr;
+	unsigned long long* sink = nullptr;
+	if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) {
+		cudaGetLastError();
+		cudaFree(buf);
+		return KMX_ECUDA;
+	}
+	cudaMemset(buf, 1, bytes);
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	for (int r = -1; r < reps; r++) {
+		if (r == 0) cudaEventRecord(e0);
+		stream_read_kernel<<<sms * blocks_per_sm, 256>>>(buf, bytes / 16, sink);
+	}
+	cudaEventRecord(e1);
+	cudaError_t e = cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	*ms_out = ms / reps;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(buf);
+	cudaFree(sink);
+	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
+}

@@ -88,7 +88,7 @@ struct TeamBlob2 {
 	cudaIpcMemHandle_t hr;
 	uint64_t ptr_r;
 	uint64_t attempts, accepted, iterations;
-	uint64_t phase_cycles[8];
+	uint64_t phase_cycles[12];
 	float ms_encode, ms_insert;
 };
 static_assert(sizeof(TeamBlob0) <= kTeamBlob && sizeof(TeamBlob1) <= kTeamBlob && sizeof(TeamBlob2) <= kTeamBlob, "a step's blob is 256 bytes");
@@ -481,7 +481,7 @@ static int team_step2(kmx_model* m, const TeamBlob1* in, size_t stride, TeamBlob
 	out->attempts = t->ctl.attempts;
 	out->accepted = t->ctl.accepted;
 	out->iterations = t->ctl.iterations;
-	for (int i = 0; i < 8; i++) out->phase_cycles[i] = t->ctl.phase_cycles[i];
+	for (int i = 0; i < 12; i++) out->phase_cycles[i] = t->ctl.phase_cycles[i];
 	CU(cudaEventElapsedTime(&out->ms_encode, ev[1], ev[2]));
 	CU(cudaEventElapsedTime(&out->ms_insert, ev[5], ev[3]));
 	return KMX_OK;
@@ -496,14 +496,14 @@ static int team_step3(kmx_model* m, const TeamBlob2* in, size_t stride) {
 	cudaEvent_t* ev = m->x->ev_build;
 	CU(cudaSetDevice(m->device));
 	int rc;
-	uint64_t attempts = 0, accepted = 0, iterations = 0, cycles[8] = { 0 };
+	uint64_t attempts = 0, accepted = 0, iterations = 0, cycles[12] = { 0 };
 	float ms_encode = 0, ms_insert = 0;
 	for (int p = 0; p < t->world; p++) {
 		const TeamBlob2* q = (const TeamBlob2*)((const uint8_t*)in + (size_t)p * stride);
 		attempts += q->attempts;
 		accepted += q->accepted;
 		iterations = std::max<uint64_t>(iterations, q->iterations);
-		for (int i = 0; i < 8; i++) cycles[i] = std::max<uint64_t>(cycles[i], q->phase_cycles[i]);
+		for (int i = 0; i < 12; i++) cycles[i] = std::max<uint64_t>(cycles[i], q->phase_cycles[i]);
 		ms_encode = std::max(ms_encode, q->ms_encode);
 		ms_insert = std::max(ms_insert, q->ms_insert);
 		if (p == t->rank) t->peer_r[p] = m->rslab;
@@ -588,7 +588,7 @@ static int team_step3(kmx_model* m, const TeamBlob2* in, size_t stride) {
 	f.insert_accepted = accepted;
 	f.insert_iterations = iterations;
 	f.batches = b.n_batches;
-	for (int i = 0; i < 8; i++) f.insert_phase_cycles[i] = cycles[i];
+	for (int i = 0; i < 12; i++) f.insert_phase_cycles[i] = cycles[i];
 	f.ms_upload = b.ms_upload;
 	f.ms_count = t->ms_count;
 	f.ms_encode = ms_encode;

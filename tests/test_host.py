@@ -240,3 +240,19 @@ def test_bench_shapes_are_pinned_by_the_reference():
         assert g is not None and g["oracle_equals_reference"] is True
         assert set(g["model_md5"]) == set(wl.MODEL_FILES) and g["occ_n"] == 1 << 22 and len(g["db_md5"]["kmc_suf"]) == 32
         assert g["insert_attempts"] >= g["insert_accepted"] > 0 and g["workload"] == wl.WORKLOADS[name][4]
+
+
+def test_device_selection_fails_loudly_without_a_gpu():
+    """kmx_set_devices validates its list against the devices present; on a box without a GPU every ordinal is refused
+    (KMX_ENOGPU), an empty list (= single-GPU behaviour) is accepted"""
+    lib = kx.lib()
+    n = lib.kmx_device_count()
+    assert lib.kmx_set_devices(None, 0) == 0
+    bad = (C.c_int * 2)(n, n + 1)                       # ordinals beyond what is present
+    assert lib.kmx_set_devices(bad, 2) == 4             # KMX_ENOGPU
+    assert lib.kmx_set_devices(bad, 9) == 1             # KMX_EARG: more than 8 devices
+    if n >= 1:
+        twice = (C.c_int * 2)(0, 0)
+        assert lib.kmx_set_devices(twice, 2) == 1       # the same device listed twice
+    assert lib.kmx_team_steps() == 4 and lib.kmx_team_blob_bytes() == 256
+    assert lib.kmx_set_devices(None, 0) == 0
