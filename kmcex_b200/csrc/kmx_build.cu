@@ -143,15 +143,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // thread issues a 16 KB bulk copy per tile, an mbarrier flips when the bytes have landed), so the HBM pipe stays full while
 // the 256 threads pick the counters out of the previous tile; one __syncthreads per tile (the partial sums alternate
 // between two shared buffers).
+// The consume side is kept to ~12 instructions per record so that the kernel stays bandwidth-bound (at 7 TB/s an SM has
+// ~700 cycles for a 16 KB tile): FAST = the record is one aligned 8-byte word (6 suffix bytes + 2 counter bytes: k = 31 with
+// a 7-symbol LUT prefix, the layout of every large database) read with one LDS.64; the class counters live in registers
+// across tiles and are reduced once at the end; per tile only the array-bound count (what the scan needs) is reduced, with
+// one REDUX per warp.
 constexpr int kCountStages = 3;
-template <bool LIST>
+template <bool LIST, bool FAST>
 __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevDb db, int ci, int cs, int bf_num, CountOut* out,
                                                     uint32_t* __restrict__ tile_cnt, uint64_t tile_first, uint64_t tile_end) {
 	extern __shared__ __align__(128) uint8_t s_dyn[];        // kCountStages stages of stage_bytes each
 	__shared__ uint64_t s_bar[kCountStages];
-	__shared__ unsigned long long s_sum[2][2][8];             // [parity][packed word][warp]
+	__shared__ uint32_t s_sum[2][8];                          // [parity][warp]: records of the tile that go on (listed / array-bound)
+	__shared__ unsigned long long s_fin[8];
 	const uint32_t stage_bytes = ((uint32_t)kTile * db.rec_bytes + 127u) & ~127u;
-	unsigned long long acc[6] = { 0, 0, 0, 0, 0, 0 };        // thread 0: class0..2, listed, array, bad
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	auto issue = [&](uint64_t tile, int stage) {              // thread 0 only
 		const uint64_t s0 = tile * kTile;
@@ -169,6 +174,8 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevD
 		}
 	}
 	__syncthreads();
+	const uint32_t lo = db.min_count, hi = db.max_count, bf_end = (uint32_t)(ci + bf_num);
+	uint32_t cls0 = 0, cls1 = 0, cls2 = 0, listed_all = 0, arr_all = 0, bad_all = 0;   // this thread's records, all tiles (< 2^32 per thread)
 	uint32_t it = 0;
 	for (uint64_t tile = tile_first + blockIdx.x; tile < tile_end; tile += gridDim.x, it++) {
 		const int stage = (int)(it % kCountStages);
@@ -176,55 +183,50 @@ __global__ void __launch_bounds__(256) count_kernel(const __grid_constant__ DevD
 		const uint64_t s0 = tile * kTile;
 		const uint32_t n_rec = (uint32_t)min((uint64_t)kTile, db.total - s0);
 		mbar_wait(&s_bar[stage], (it / kCountStages) & 1u);
-		uint32_t cls[3] = { 0, 0, 0 }, listed = 0, arr = 0, bad = 0;
+		uint32_t on = 0;                                      // records of this tile that go on: listed (LIST) / array-bound
 #pragma unroll
 		for (int j = 0; j < kTile / 256; j++) {
-			uint32_t t = threadIdx.x + j * 256;
-			if (t < n_rec) {
-				uint32_t c = decode_count(db, s_bytes + t * db.rec_bytes);
-				if (c >= db.min_count && c <= db.max_count) {
-					listed++;
-					if (!LIST) {
-						if (c < (uint32_t)ci || c > (uint32_t)cs) bad++;
-						else if (c < (uint32_t)(ci + bf_num)) cls[c - ci]++;
-						else arr++;
-					}
-				}
+			const uint32_t t = threadIdx.x + j * 256;
+			uint32_t c;
+			if (FAST) c = (uint32_t)(reinterpret_cast<const unsigned long long*>(s_bytes)[t] >> 48);    // bytes 6, 7: little-endian counter
+			else c = decode_count(db, s_bytes + t * db.rec_bytes);
+			const bool is_listed = t < n_rec && c >= lo && c <= hi;
+			if (LIST) {
+				on += is_listed ? 1u : 0u;
+			} else {
+				const bool is_bad = is_listed && (c < (uint32_t)ci || c > (uint32_t)cs);
+				const bool is_arr = is_listed && !is_bad && c >= bf_end;
+				const uint32_t k = c - (uint32_t)ci;          // Bloom class when listed, not bad, not array-bound
+				const bool is_bf = is_listed && !is_bad && !is_arr;
+				cls0 += (is_bf && k == 0) ? 1u : 0u;
+				cls1 += (is_bf && k == 1) ? 1u : 0u;
+				cls2 += (is_bf && k == 2) ? 1u : 0u;
+				bad_all += is_bad ? 1u : 0u;
+				on += is_arr ? 1u : 0u;
 			}
+			listed_all += is_listed ? 1u : 0u;
 		}
-		// pack the six small counters into two 64-bit sums (each < 2^12 per thread, 2^20 per block)
-		unsigned long long p0 = (unsigned long long)cls[0] | ((unsigned long long)cls[1] << 21) | ((unsigned long long)cls[2] << 42);
-		unsigned long long p1 = (unsigned long long)listed | ((unsigned long long)arr << 21) | ((unsigned long long)bad << 42);
-#pragma unroll
-		for (int d = 16; d > 0; d >>= 1) {
-			p0 += __shfl_down_sync(0xffffffffu, p0, d);
-			p1 += __shfl_down_sync(0xffffffffu, p1, d);
-		}
-		if (lane == 0) {
-			s_sum[it & 1][0][warp] = p0;
-			s_sum[it & 1][1][warp] = p1;
-		}
+		arr_all += on;
+		on = __reduce_add_sync(0xffffffffu, on);
+		if (lane == 0) s_sum[it & 1][warp] = on;
 		__syncthreads();                                     // every thread is done with the stage; the partial sums are visible
 		if (threadIdx.x == 0) {
 			const uint64_t next = tile + (uint64_t)kCountStages * gridDim.x;
 			if (next < tile_end) issue(next, stage);
-			p0 = p1 = 0;
-			for (int w = 0; w < 8; w++) {
-				p0 += s_sum[it & 1][0][w];
-				p1 += s_sum[it & 1][1][w];
-			}
-			const unsigned long long m21 = (1ULL << 21) - 1;
-			acc[0] += p0 & m21; acc[1] += (p0 >> 21) & m21; acc[2] += (p0 >> 42) & m21;
-			acc[3] += p1 & m21; acc[4] += (p1 >> 21) & m21; acc[5] += (p1 >> 42) & m21;
-			tile_cnt[tile - tile_first] = LIST ? (uint32_t)(p1 & m21) : (uint32_t)((p1 >> 21) & m21);
+			uint32_t sum = 0;
+#pragma unroll
+			for (int w = 0; w < 8; w++) sum += s_sum[it & 1][w];
+			tile_cnt[tile - tile_first] = sum;
 		}
 	}
-	if (threadIdx.x == 0 && out) {
-		for (int i = 0; i < 3; i++)
-			if (acc[i]) atomicAdd(&out->class_count[i], acc[i]);
-		if (acc[3]) atomicAdd(&out->listed, acc[3]);
-		if (acc[4]) atomicAdd(&out->array_bound, acc[4]);
-		if (acc[5]) atomicAdd(&out->bad_count, acc[5]);
+	if (out) {
+		// the six totals of the block, one after the other (once per kernel)
+		const unsigned long long v[6] = { cls0, cls1, cls2, listed_all, LIST ? 0u : arr_all, bad_all };
+		unsigned long long* dst[6] = { &out->class_count[0], &out->class_count[1], &out->class_count[2], &out->listed, &out->array_bound, &out->bad_count };
+		for (int q = 0; q < 6; q++) {
+			const unsigned long long tot = block_sum(v[q], s_fin);
+			if (threadIdx.x == 0 && tot) atomicAdd(dst[q], tot);
+		}
 	}
 }
 
@@ -365,41 +367,37 @@ static int stream_grid(uint64_t n_tiles, int sm_count, int per_sm) {
 }
 
 // grid and dynamic shared memory of the counting pass: kCountStages stages per block, as many blocks per SM as fit
-template <bool LIST>
-static cudaError_t count_launch_shape(const DevDb& db, uint64_t n_tiles, int sm_count, int* grid, size_t* smem) {
-	*smem = (size_t)kCountStages * (((size_t)kTile * db.rec_bytes + 127) & ~(size_t)127);
-	cudaError_t e = cudaFuncSetAttribute(count_kernel<LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+template <bool LIST, bool FAST>
+static cudaError_t count_launch(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, uint64_t tile_first,
+                                uint64_t tile_end, int sm_count, cudaStream_t stream) {
+	const size_t smem = (size_t)kCountStages * (((size_t)kTile * db.rec_bytes + 127) & ~(size_t)127);
+	cudaError_t e = cudaFuncSetAttribute(count_kernel<LIST, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<LIST>, 256, *smem);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, count_kernel<LIST, FAST>, 256, smem);
 	if (e != cudaSuccess) return e;
 	if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-	*grid = stream_grid(n_tiles, sm_count, per_sm);
-	return cudaSuccess;
+	const int grid = stream_grid(tile_end - tile_first, sm_count, per_sm);
+	count_kernel<LIST, FAST><<<grid, 256, smem, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end);
+	note_launch();
+	return cudaGetLastError();
 }
+
+// one aligned 8-byte word per record with the counter in its top two bytes
+static bool fast_records(const DevDb& db) { return db.rec_bytes == 8 && db.counter_bytes == 2 && db.suffix_bytes == 6; }
 
 cudaError_t launch_count(const DevDb& db, int ci, int cs, int bf_num, CountOut* d_out, uint32_t* d_tile_cnt, uint64_t tile_first,
                          uint64_t tile_end, int sm_count, cudaStream_t stream) {
 	if (tile_end <= tile_first) return cudaSuccess;
-	int grid = 0;
-	size_t smem = 0;
-	cudaError_t e = count_launch_shape<false>(db, tile_end - tile_first, sm_count, &grid, &smem);
-	if (e != cudaSuccess) return e;
-	count_kernel<false><<<grid, 256, smem, stream>>>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end);
-	note_launch();
-	return cudaGetLastError();
+	if (fast_records(db)) return count_launch<false, true>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end, sm_count, stream);
+	return count_launch<false, false>(db, ci, cs, bf_num, d_out, d_tile_cnt, tile_first, tile_end, sm_count, stream);
 }
 
 cudaError_t launch_list_count(const DevDb& db, uint32_t* d_tile_cnt, int sm_count, cudaStream_t stream) {
 	if (db.total == 0) return cudaSuccess;
-	uint64_t n_tiles = (db.total + kTile - 1) / kTile;
-	int grid = 0;
-	size_t smem = 0;
-	cudaError_t e = count_launch_shape<true>(db, n_tiles, sm_count, &grid, &smem);
-	if (e != cudaSuccess) return e;
-	count_kernel<true><<<grid, 256, smem, stream>>>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles);
-	note_launch();
-	return cudaGetLastError();
+	const uint64_t n_tiles = (db.total + kTile - 1) / kTile;
+	if (fast_records(db)) return count_launch<true, true>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles, sm_count, stream);
+	return count_launch<true, false>(db, 0, 0, 0, nullptr, d_tile_cnt, 0, n_tiles, sm_count, stream);
 }
 
 cudaError_t launch_tile_scan(const uint32_t* d_tile_cnt, uint64_t n_tiles, uint64_t* d_tile_off, cudaStream_t stream) {
