@@ -1117,6 +1117,22 @@ static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const u
 	cudaEvent_t* ev = m->x->ev_build;
 	const InsertCtl ctl = m->x->h_pinned->ctl;
 	int32_t& groups = m->x->h_pinned->groups;
+	// the item stream and the insert's scratch are dead: give them back to the pool first, so that the sort buffers of a
+	// large build (NA12878 shape: 4 GB) come out of that memory instead of growing the pool between two timed events
+	dev_free(b.d_item_kmer, s);
+	dev_free(b.d_item_occ, s);
+	b.d_item_kmer = nullptr;
+	b.d_item_occ = nullptr;
+	for (int q = 0; q < 2; q++) {
+		dev_free(b.a.buf_kmer[q], s);
+		dev_free(b.a.buf_occ[q], s);
+		b.a.buf_kmer[q] = nullptr;
+		b.a.buf_occ[q] = nullptr;
+	}
+	dev_free(b.a.resv, s);
+	dev_free(b.a.claim, s);
+	b.a.resv = nullptr;
+	b.a.claim = nullptr;
 	int rc = build_rest_table(m, d_rest_kmer, d_rest_occ, rest_n, &groups);
 	if (rc) return rc;
 	rc = build_rest_side_tables(m);
