@@ -266,11 +266,14 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const uint32_t* __restr
 	if (threadIdx.x == 0) off[n] = s_carry;
 }
 
+#ifndef KMX_ENCODE_BLOCKS
+#define KMX_ENCODE_BLOCKS 3                  // A/B on B200: 4 blocks per SM (64 registers) is 10 % slower on the HC14 shape
+#endif
 // pass 2.  Each thread decodes 8 CONSECUTIVE records so that the compaction keeps file order.
 // LIST = true: write every listed record (kmx_db_list).  LIST = false: Bloom-bound records are
 // inserted into their filters (kmodel.hpp:473-477,498-506), array-bound ones go to the stream.
 template <bool LIST, int K, int H>
-__global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ DevDb db, const __grid_constant__ DevModel m,
+__global__ void __launch_bounds__(256, KMX_ENCODE_BLOCKS) encode_kernel(const __grid_constant__ DevDb db, const __grid_constant__ DevModel m,
                                                      const uint64_t* __restrict__ tile_off, const __grid_constant__ ItemRoute route,
                                                      uint64_t tile_first, uint64_t tile_end) {
 	__shared__ uint4 s_stage[kTile * kMaxRecBytes / 16];

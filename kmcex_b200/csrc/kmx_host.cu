@@ -14,6 +14,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <algorithm>
 #include <atomic>
@@ -662,6 +663,20 @@ int kmx::db_upload_range(kmx_db* db, uint64_t rec_lo, uint64_t rec_hi, int reade
 	CU(cudaStreamSynchronize(x->stream));                // the allocation is usable from the reader streams now
 	TRACE(t0, "upload: buffers ready");
 	const uint64_t n_chunks = (bytes + kChunk - 1) / kChunk;
+	// KMX_UPLOAD_MMAP=1: the readers copy out of a shared mapping of the file instead of calling pread() (no system call and no
+	// page-cache accounting per chunk; an A/B switch)
+	const uint8_t* map = nullptr;
+	size_t map_len = 0, map_skew = 0;
+	if (const char* e = getenv("KMX_UPLOAD_MMAP")) {
+		if (atoi(e) && bytes) {
+			const uint64_t file_off = 4 + byte_lo;
+			const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+			map_skew = (size_t)(file_off % page);
+			map_len = (size_t)bytes + map_skew;
+			void* p = mmap(nullptr, map_len, PROT_READ, MAP_SHARED, db->fd, (off_t)(file_off - map_skew));
+			if (p != MAP_FAILED) map = (const uint8_t*)p;
+		}
+	}
 	int want_thr = std::max(1, std::min<int>(kReaders, reader_threads > 0 ? reader_threads : (int)std::thread::hardware_concurrency()));
 	if (const char* e = getenv("KMX_READERS")) want_thr = std::max(1, std::min(kReaders, atoi(e)));
 	const int n_thr = (int)std::min<uint64_t>(want_thr, n_chunks);
@@ -675,6 +690,10 @@ int kmx::db_upload_range(kmx_db* db, uint64_t rec_lo, uint64_t rec_hi, int reade
 			cudaEventSynchronize(x->reader_ev[t][slot]);       // the previous copy out of this slot is done
 			uint8_t* b = g_bounce.buf[t][slot];
 			uint64_t got = 0;
+			if (map) {
+				memcpy(b, map + map_skew + off, len);
+				got = len;
+			}
 			while (got < len) {
 				ssize_t r = pread(db->fd, b + got, len - got, (off_t)(4 + byte_lo + off + got));
 				if (r <= 0) { status[t] = KMX_EIO; break; }
@@ -690,6 +709,7 @@ int kmx::db_upload_range(kmx_db* db, uint64_t rec_lo, uint64_t rec_hi, int reade
 	for (int t = 1; t < n_thr; t++) pool.emplace_back(work, t);
 	if (n_thr > 0) work(0);
 	for (auto& th : pool) th.join();
+	if (map) munmap((void*)map, map_len);
 	for (int t = 0; t < n_thr; t++) {
 		if (status[t] != KMX_OK) {
 			dev_free(db->d_suf, x->stream);
