@@ -191,6 +191,9 @@ int kmx_microbench_grid_barrier(int mode, int threads, int blocks_per_sm, int re
 /* nanoseconds per returning atomicAdd when every warp of a full grid hammers n_counters addresses (list appends) */
 int kmx_microbench_hot_atomic(int n_counters, int per_warp, float* ns_out);
 int kmx_microbench_windowed(int kind, uint64_t footprint_bytes, uint64_t window_bytes, uint64_t n_items, int reps, float* ms_out);
+/* the same random accesses issued by device `src` into a buffer on device `dst` over NVLink (peer access): what routing every
+ * Bloom bit to an address-range owner would cost, against OR-reducing replicated filters */
+int kmx_microbench_peer_random(int kind, int src, int dst, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out);
 /* milliseconds per pass of a read-only streaming kernel over `bytes` of device memory: the ceiling of the counting pass */
 int kmx_microbench_stream_read(uint64_t bytes, int blocks_per_sm, int reps, float* ms_out);
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     "kmx_microbench_random": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_grid_barrier": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_hot_atomic": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "kmx_microbench_peer_random": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_stream_read": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "kmx_microbench_windowed": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_float)]),
 }

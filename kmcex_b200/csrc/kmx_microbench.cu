@@ -235,3 +235,59 @@ extern "C" int kmx_microbench_stream_read(uint64_t bytes, int blocks_per_sm, int
 	cudaFree(sink);
 	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
 }
+
+// ---- owner-routed bits over NVLink: what a remote fire-and-forget reduction costs -------------------------------------
+// kind as kmx_microbench_random; the kernel runs on device `src`, the buffer lives on device `dst` (peer access).  The number
+// behind the team build's choice to OR-reduce replicated filters instead of routing every bit to an address-range owner.
+extern "C" int kmx_microbench_peer_random(int kind, int src, int dst, uint64_t footprint_bytes, uint64_t n_items, int reps, float* ms_out) {
+	if (kind < 0 || kind > 2 || footprint_bytes < 4096 || !ms_out || reps < 1 || src == dst) return KMX_EARG;
+	int n_dev = 0;
+	if (cudaGetDeviceCount(&n_dev) != cudaSuccess || src < 0 || dst < 0 || src >= n_dev || dst >= n_dev) {
+		cudaGetLastError();
+		return KMX_ENOGPU;
+	}
+	unsigned long long* buf = nullptr;
+	unsigned long long* sink = nullptr;
+	cudaSetDevice(dst);
+	if (cudaMalloc(&buf, footprint_bytes) != cudaSuccess) {
+		cudaGetLastError();
+		return KMX_ECUDA;
+	}
+	cudaMemset(buf, 0, footprint_bytes);
+	cudaDeviceSynchronize();
+	cudaSetDevice(src);
+	cudaError_t pe = cudaDeviceEnablePeerAccess(dst, 0);
+	if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) {
+		cudaGetLastError();
+		cudaSetDevice(dst);
+		cudaFree(buf);
+		return KMX_ECUDA;
+	}
+	cudaGetLastError();
+	cudaMalloc(&sink, 8);
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, src);
+	const uint64_t n_words = footprint_bytes / 8;
+	const int grid = sms * 8;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0);
+	cudaEventCreate(&e1);
+	for (int r = -1; r < reps; r++) {
+		if (r == 0) cudaEventRecord(e0);
+		if (kind == 0) random_sector_kernel<0><<<grid, 256>>>(buf, n_words, n_items, sink, 0);
+		else if (kind == 1) random_sector_kernel<1><<<grid, 256>>>(buf, n_words, n_items, sink, 0);
+		else random_sector_kernel<2><<<grid, 256>>>(buf, n_words, n_items, sink, 0);
+	}
+	cudaEventRecord(e1);
+	cudaError_t e = cudaEventSynchronize(e1);
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	*ms_out = ms / reps;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(sink);
+	cudaSetDevice(dst);
+	cudaFree(buf);
+	cudaSetDevice(src);
+	return e == cudaSuccess ? KMX_OK : KMX_ECUDA;
+}
