@@ -178,6 +178,11 @@ int kmx_host_prefix_cuts(const uint32_t* hist, int map_size, int world, uint32_t
 int kmx_selftest_positions(const uint64_t* kmers, size_t n, int k, uint64_t d, const uint32_t* seeds, int n_seeds, uint64_t* pos_out,
                            uint64_t counts[3]);
 
+/* position-sensitive 64-bit checksums of the model's device arrays: sums[0] Bloom filters + km_back, [1] coupled arrays, [2] rest
+ * keys, [3] rest counts + group index.  Equal on every replica of a team build (bench.py compares them across the ranks when
+ * the model is too large to save on every rank; rank 0's files are compared with the reference's byte for byte). */
+int kmx_model_checksum(kmx_model* m, uint64_t sums[4]);
+
 /* kernels launched by this process's libkmx so far (bench.py reports the launches inside its timed region) */
 unsigned long long kmx_launch_count(void);
 

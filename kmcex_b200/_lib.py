@@ -86,6 +86,7 @@ SIGNATURES = {
     "kmx_team_blob_bytes": (C.c_int, []),
     "kmx_team_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "kmx_launch_count": (C.c_ulonglong, []),
+    "kmx_model_checksum": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "kmx_selftest_positions": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "kmx_host_route": (None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "kmx_host_prefix_cuts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

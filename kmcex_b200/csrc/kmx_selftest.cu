@@ -90,3 +90,55 @@ extern "C" int kmx_selftest_positions(const uint64_t* kmers, size_t n, int k, ui
 	for (int i = 0; i < 3; i++) counts[i] = h[i];
 	return KMX_OK;
 }
+
+// ---- position-sensitive 64-bit checksum of a device region: lets the ranks of a team build compare their replicas of a
+// large model without writing 15 GB of files each (rank 0's files are compared with the reference's, byte for byte) ------
+namespace kmx {
+__global__ void checksum_kernel(const unsigned long long* __restrict__ words, uint64_t n, unsigned long long salt, unsigned long long* __restrict__ out) {
+	unsigned long long acc = 0;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		unsigned long long z = words[i] + (i + salt) * 0x9E3779B97F4A7C15ULL;
+		z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+		z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+		acc += z ^ (z >> 31);
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+	if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+}  // namespace kmx
+
+// sums[0] Bloom filters + km_back, [1] coupled arrays (device layout), [2] rest keys, [3] rest counts + group index
+extern "C" int kmx_model_checksum(kmx_model* m, uint64_t sums[4]) {
+	if (!m || !sums) return set_error(KMX_EARG, "null argument");
+	if (!m->built) return set_error(KMX_ESTATE, "model is not initialised");
+	CU(cudaSetDevice(m->device));
+	cudaStream_t s = m->x->stream;
+	unsigned long long* d_out = nullptr;
+	DevScope scope(s);
+	int rc = scope.alloc(&d_out, 32);
+	if (rc) return rc;
+	CU(cudaMemsetAsync(d_out, 0, 32, s));
+	const int grid = m->sm_count * 8;
+	auto add = [&](const void* p, uint64_t bytes, int slot, unsigned long long salt) {
+		if (!p || bytes < 8) return;
+		checksum_kernel<<<grid, 256, 0, s>>>((const unsigned long long*)p, bytes / 8, salt << 40, d_out + slot);
+		note_launch();
+	};
+	for (int i = 0; i < m->bf_num; i++) {
+		add(m->d_bf[i], m->bytes[i] & ~7ULL, 0, 1 + i);
+		add(m->d_bf_back[i], m->bytes[3 + i] & ~7ULL, 0, 4 + i);
+	}
+	add(m->d_km_back, m->bytes[7] & ~7ULL, 0, 7);
+	for (int i = 0; i < m->n_bits; i++) add(m->d_cells[i], cell_words(m->bytes[6]) * 8, 1, 8 + i);
+	add(m->d_rest_keys, m->rest.count * 8, 2, 16);
+	add(m->d_rest_counts, (m->rest.count * 4) & ~7ULL, 3, 17);
+	add(m->d_hash2index, (uint64_t)m->rest.map_size * 4, 3, 18);
+	add(m->d_pre_buffer, ((uint64_t)m->rest.pre_buffer_size * 4) & ~7ULL, 3, 19);
+	CU(cudaGetLastError());
+	unsigned long long h[4];
+	CU(cudaMemcpyAsync(h, d_out, 32, cudaMemcpyDeviceToHost, s));
+	CU(cudaStreamSynchronize(s));
+	for (int i = 0; i < 4; i++) sums[i] = h[i];
+	return KMX_OK;
+}

@@ -114,6 +114,12 @@ class KModel:
         check(lib().kmx_query_path_packed(self._h, q.ctypes.data, q.size, out.ctypes.data))
         return out
 
+    def checksum(self) -> list:
+        """four position-sensitive 64-bit checksums of the device arrays (filters, coupled arrays, rest keys, rest counts + index)"""
+        sums = (C.c_uint64 * 4)()
+        check(lib().kmx_model_checksum(self._h, sums))
+        return [int(x) for x in sums]
+
     def sync(self) -> None:
         check(lib().kmx_model_sync(self._h))
 

@@ -90,9 +90,10 @@ def _team_worker(rank, world, port, base, ci, work_dir, q_path):
             q = np.fromfile(q_path, dtype=np.uint64)
             np.save(os.path.join(work_dir, f"team{attempt}_occ{rank}.npy"), kd.ShardedKModel(m).kmer_to_occ(q))
             info = m.info
+            sums = m.checksum()
             m.close()
         with open(os.path.join(work_dir, f"info{rank}.txt"), "w") as f:
-            f.write(f"{info['insert_attempts']} {info['insert_accepted']} {info['rest_kmers']} {info['batches']}")
+            f.write(f"{info['insert_attempts']} {info['insert_accepted']} {info['rest_kmers']} {info['batches']} {sums}")
     finally:
         dist.destroy_process_group()
 
@@ -119,4 +120,4 @@ def test_team_build_is_byte_identical(name, ranks, case_dbs, golden, tmp_path):
             occ = np.load(str(tmp_path / f"team{attempt}_occ{r}.npy"))
             assert hashlib.md5(occ.tobytes()).hexdigest() == golden[name]["occ_md5"]
     infos = {open(str(tmp_path / f"info{r}.txt")).read() for r in range(world)}
-    assert len(infos) == 1                      # every rank reports the same totals
+    assert len(infos) == 1                      # every rank reports the same totals and the same device checksums

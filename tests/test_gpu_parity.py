@@ -79,9 +79,10 @@ def test_gpu_query_equals_reference_outputs(name, built, golden, oracle):
     occ = m.kmer_to_occ(q)
     assert occ[:64].tolist() == g["occ_head"]
     assert hashlib.md5(occ.tobytes()).hexdigest() == g["occ_md5"]
-    # a model LOADED from the files answers the same (get_model(dir), kmodel.hpp:680-696)
+    # a model LOADED from the files answers the same (get_model(dir), kmodel.hpp:680-696) and holds the same device arrays
     m2 = kx.get_model(out)
     assert (m2.kmer_to_occ(q) == occ).all()
+    assert m2.checksum() == m.checksum() and len(set(m.checksum())) == 4
     # ASCII entry point == packed entry point (the 2-bit encode happens on the device)
     sub = q[:5000]
     assert (m2.kmer_to_occ(synth.to_ascii(sub, 31)) == occ[:5000]).all()
