@@ -446,7 +446,7 @@ class Bench:
         # a model of several GB is saved by rank 0 only (8 x 15 GB would not fit the scratch disk): the other ranks prove that
         # their replica equals rank 0's with position-sensitive checksums of the device arrays, and answer the queries
         info = m.info
-        big = self.world > 1 and (info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"]) > (4 << 30)
+        big = self.world > 1 and (info["km_bytes"] + info["km_back_bytes"] + info["bf_bytes"]) > int(os.environ.get("KMX_BENCH_BIG_MODEL_BYTES", 4 << 30))
         sums = m.checksum()
         replicas_equal = True
         if self.world > 1:
