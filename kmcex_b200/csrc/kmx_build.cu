@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(kInsThreads, 1024 / kInsThreads) insert_kernel
 	const uint32_t slot_mask = a.resv_slots - 1;
 	InsertCtl* ctl = a.ctl;
 	volatile InsertCtl* vctl = a.ctl;
-	__shared__ uint32_t s_warp[kInsThreads / 32 + 1];
 
 	uint32_t epoch = vctl->epoch;
 	uint32_t seq = vctl->seq;
