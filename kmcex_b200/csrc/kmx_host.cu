@@ -75,6 +75,21 @@ int dev_alloc_impl(void** p, size_t bytes, cudaStream_t s) {
 		CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 		pool_ready[dev].store(true);
 	}
+	if (trace_on() && bytes >= (256ULL << 20)) {
+		// KMX_TRACE: large requests that the pool could not serve from what it holds show up as milliseconds of host time here
+		const auto t0 = std::chrono::high_resolution_clock::now();
+		CU(cudaMallocAsync(p, bytes, s));
+		const double ms = 1e3 * std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+		cudaMemPool_t pool;
+		uint64_t reserved = 0, used = 0;
+		if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+			cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+			cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+		}
+		fprintf(stderr, "[kmx]   alloc %8.1f MB at %p took %.3f ms (pool: %.1f MB reserved, %.1f MB in use)\n", bytes / 1048576.0, *p, ms, reserved / 1048576.0,
+		        used / 1048576.0);
+		return KMX_OK;
+	}
 	CU(cudaMallocAsync(p, bytes ? bytes : 8, s));
 	return KMX_OK;
 }
@@ -840,7 +855,8 @@ int kmx::build_rest_side_tables(kmx_model* m) {
 	return KMX_OK;
 }
 
-static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups) {
+// scratch / scratch_bytes: dead device memory the sort may use instead of allocating its temporary buffers (may be null / 0)
+static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uint32_t* d_surv_occ, uint64_t n, int32_t* h_groups, void* scratch, size_t scratch_bytes) {
 	RestHost& r = m->rest;
 	cudaStream_t s = m->x->stream;
 	r.k = m->k;
@@ -861,7 +877,8 @@ static int build_rest_table(kmx_model* m, const uint64_t* d_surv_kmer, const uin
 	if ((rc = scope.alloc(&d_first, (size_t)r.map_size * 4))) return rc;
 	if ((rc = scope.alloc(&d_groups, 4))) return rc;
 	const size_t temp_bytes = radix_sort_temp_bytes(n);
-	if (temp_bytes && (rc = scope.alloc(&d_temp, temp_bytes))) return rc;
+	if (temp_bytes && temp_bytes <= scratch_bytes) d_temp = scratch;
+	else if (temp_bytes && (rc = scope.alloc(&d_temp, temp_bytes))) return rc;
 	CU(launch_radix_sort_pairs(d_temp, d_surv_kmer, m->d_rest_keys, d_surv_occ, (uint32_t*)m->d_rest_counts, n, 2 * m->k, s));
 	CU(launch_rest_index(m->d_rest_keys, n, 2 * (m->k - r.pre_len), r.map_size, d_first, m->d_hash2index, m->d_pre_buffer, d_groups, s));
 	CU(cudaMemcpyAsync(h_groups, d_groups, 4, cudaMemcpyDeviceToHost, s));
@@ -923,6 +940,10 @@ void kmx::build_state_free(kmx_model* m) {
 	const bool team = b.team != nullptr;
 	if (team) team_state_free(m);                         // item shard, ping-pong buffers, control block, survivor list live in its slab
 	if (!team) {
+		if (a.rest_kmer != b.d_item_kmer) {               // n_bits == 1: a list of its own (see build_stage_insert_setup)
+			dev_free(a.rest_kmer, s);
+			dev_free(a.rest_occ, s);
+		}
 		dev_free(b.d_item_kmer, s);
 		dev_free(b.d_item_occ, s);
 		for (int q = 0; q < 2; q++) {
@@ -930,8 +951,6 @@ void kmx::build_state_free(kmx_model* m) {
 			dev_free(a.buf_occ[q], s);
 		}
 		dev_free(a.ctl, s);
-		dev_free(a.rest_kmer, s);
-		dev_free(a.rest_occ, s);
 	}
 	dev_free(a.status, s); dev_free(a.excl_rank, s); dev_free(a.holepos, s); dev_free(a.list[0], s); dev_free(a.list[1], s); dev_free(a.list[2], s);
 	dev_free(a.tile_fail, s); dev_free(a.resv, s); dev_free(a.claim, s);
@@ -994,8 +1013,9 @@ static int build_stage_encode(kmx_model* m, kmx_db* db) {
 	fill_dev_model(m);
 
 	b.n_items = cnt.array_bound;
-	DA(&b.d_item_kmer, (b.n_items + 1) * 8, s);
-	DA(&b.d_item_occ, (b.n_items + 1) * 4, s);
+	// + n_bits: the stream doubles as the survivor list (build_stage_insert_setup), which can hold that many stale-slot duplicates
+	DA(&b.d_item_kmer, (b.n_items + m->n_bits + 1) * 8, s);
+	DA(&b.d_item_occ, (b.n_items + m->n_bits + 1) * 4, s);
 	ItemRoute route;
 	memset(&route, 0, sizeof(route));
 	route.kmer[0] = b.d_item_kmer;
@@ -1083,11 +1103,20 @@ int kmx::build_stage_insert_setup(kmx_model* m, int rank, int n_active, bool tea
 	if (const char* e = getenv("KMX_PHASE_ROUND")) a.phase_round = atoi(e);
 	CU(insert_grid_size(&b.grid, m->sm_count));
 	if (!team) {
-		// Survivor list: sized for the worst case (nothing accepted) while that is cheap, which lets
-		// all launches queue without a host round trip; beyond that it grows between launches.
-		b.worst_case = b.n_items <= (1ULL << 28) && !getenv("KMX_TEST_GROW_REST");   // the env var lets a small test take the growing path
-		b.rest_cap = b.worst_case ? b.n_items + m->n_bits : 0;
-		if (b.worst_case) {
+		// Survivor list.  Batch b appends its survivors after its last round, when every item of the batch has long been read
+		// from the stream (round 0 reads the stream, later rounds the ping-pong buffers), and at most as many items survive as
+		// were read: survivors of the batches up to b never reach the items of batch b + 1.  So the list lives IN the item
+		// stream, from its start -- no second allocation of the worst-case size (NA12878 shape: 36 GB), no list that grows
+		// between launches with a host round trip each, and every launch of a build can be queued at once.  The stale-slot
+		// duplicates of the last, partial batch (kmodel.hpp:520-540; fewer than n_bits) are written before that batch is
+		// read: at least n_bits items of batch 0 were accepted (the first item of every bucket meets an empty array), so they
+		// stay below its first item too.  With n_bits == 1 the last round IS round 0 and reads the stream while survivors are
+		// appended: that geometry gets a list of its own.
+		b.rest_cap = b.n_items + m->n_bits;
+		if (m->n_bits >= 2) {
+			a.rest_kmer = b.d_item_kmer;
+			a.rest_occ = b.d_item_occ;
+		} else {
 			DA(&a.rest_kmer, b.rest_cap * 8, s);
 			DA(&a.rest_occ, b.rest_cap * 4, s);
 		}
@@ -1102,39 +1131,15 @@ int kmx::build_stage_insert_run(kmx_model* m) {
 	InsertArgs& a = b.a;
 	InsertCtl& ctl = m->x->h_pinned->ctl;
 	memset(&ctl, 0, sizeof(ctl));
-	const uint64_t batch_items = (uint64_t)m->n_bits << kBucketLog;
 	const bool participates = a.rank < a.n_active;
 	CU(cudaEventRecord(m->x->ev_build[5], s));
 	if (b.n_items > 0 && participates) {
 		const uint64_t chunk = 64;                         // batches per launch
+		a.rest_cap = b.rest_cap;
 		for (uint64_t b0 = 0; b0 < b.n_batches; b0 += chunk) {
-			const uint64_t nb = std::min<uint64_t>(chunk, b.n_batches - b0);
-			const uint64_t need = ctl.rest_n + nb * batch_items + m->n_bits;
-			if (!b.worst_case && need > b.rest_cap) {
-				uint64_t new_cap = std::max<uint64_t>(need, b.rest_cap * 2);
-				uint64_t* nk = nullptr;
-				uint32_t* no = nullptr;
-				DA(&nk, new_cap * 8, s);
-				DA(&no, new_cap * 4, s);
-				if (ctl.rest_n) {
-					CU(cudaMemcpyAsync(nk, a.rest_kmer, ctl.rest_n * 8, cudaMemcpyDeviceToDevice, s));
-					CU(cudaMemcpyAsync(no, a.rest_occ, ctl.rest_n * 4, cudaMemcpyDeviceToDevice, s));
-				}
-				dev_free(a.rest_kmer, s);
-				dev_free(a.rest_occ, s);
-				a.rest_kmer = nk;
-				a.rest_occ = no;
-				b.rest_cap = new_cap;
-			}
-			a.rest_cap = b.rest_cap;
 			a.first_batch = b0;
-			a.n_batches = nb;
+			a.n_batches = std::min<uint64_t>(chunk, b.n_batches - b0);
 			CU(launch_insert(m->dm, a, b.grid, s));
-			if (!b.worst_case) {
-				CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
-				CU(cudaStreamSynchronize(s));
-				if (ctl.error) return fail(KMX_ECUDA, "insert kernel stopped with error %u (1: iteration cap, 2: survivor list overflow, 3: peer GPU timed out)", ctl.error);
-			}
 		}
 		CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, s));
 	}
@@ -1149,12 +1154,9 @@ static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const u
 	cudaEvent_t* ev = m->x->ev_build;
 	const InsertCtl ctl = m->x->h_pinned->ctl;
 	int32_t& groups = m->x->h_pinned->groups;
-	// the item stream and the insert's scratch are dead: give them back to the pool first, so that the sort buffers of a
-	// large build (NA12878 shape: 4 GB) come out of that memory instead of growing the pool between two timed events
-	dev_free(b.d_item_kmer, s);
-	dev_free(b.d_item_occ, s);
-	b.d_item_kmer = nullptr;
-	b.d_item_occ = nullptr;
+	// the insert's scratch is dead: back to the pool first, the rest table's allocations come out of it.  The survivors sit at
+	// the head of the item stream (build_stage_insert_setup); its tail is dead too and serves as the sort's temporary storage
+	// (NA12878 shape: 1.9 GB that would otherwise be a pool allocation between two timed events)
 	for (int q = 0; q < 2; q++) {
 		dev_free(b.a.buf_kmer[q], s);
 		dev_free(b.a.buf_occ[q], s);
@@ -1165,7 +1167,19 @@ static int build_stage_finish(kmx_model* m, const uint64_t* d_rest_kmer, const u
 	dev_free(b.a.claim, s);
 	b.a.resv = nullptr;
 	b.a.claim = nullptr;
-	int rc = build_rest_table(m, d_rest_kmer, d_rest_occ, rest_n, &groups);
+	void* scratch = nullptr;
+	size_t scratch_bytes = 0;
+	if (b.d_item_kmer && d_rest_kmer == b.d_item_kmer) {
+		const size_t stream_bytes = (size_t)(b.n_items + m->n_bits + 1) * 8, head = up256((size_t)rest_n * 8);
+		if (stream_bytes > head) {
+			scratch = (uint8_t*)b.d_item_kmer + head;
+			scratch_bytes = stream_bytes - head;
+		}
+	} else if (b.d_item_kmer) {                           // n_bits == 1: the list is a buffer of its own, the whole stream is dead
+		scratch = b.d_item_kmer;
+		scratch_bytes = (size_t)(b.n_items + m->n_bits + 1) * 8;
+	}
+	int rc = build_rest_table(m, d_rest_kmer, d_rest_occ, rest_n, &groups, scratch, scratch_bytes);
 	if (rc) return rc;
 	rc = build_rest_side_tables(m);
 	if (rc) return rc;

@@ -141,7 +141,6 @@ struct BuildState {
 	uint32_t* d_item_occ = nullptr;
 	InsertArgs a = {};
 	int grid = 0;
-	bool worst_case = true;
 	float ms_upload = 0;
 	TeamState* team = nullptr;        // non-null while a team build is in flight
 };

@@ -383,7 +383,6 @@ static int team_step2(kmx_model* m, const TeamBlob1* in, size_t stride, TeamBlob
 			a.peer_flags[p] = (uint32_t*)(pb + P.flags);
 		}
 	}
-	b.worst_case = true;
 	b.rest_cap = X.rest_cap;
 	if ((rc = build_stage_insert_setup(m, t->rank, t->n_active, true))) return rc;
 

@@ -259,7 +259,7 @@ def test_empty_and_tiny_batches(built):
     assert (occ[-12345:] == m.kmer_to_occ(big[-12345:])).all()
 
 
-@pytest.mark.parametrize("env", [{"KMX_TEST_EPOCH_START": "16370"}, {"KMX_TEST_GROW_REST": "1"}, {"KMX_RESV_LOG2": "12", "KMX_CLAIM_LOG2": "15"},
+@pytest.mark.parametrize("env", [{"KMX_TEST_EPOCH_START": "16370"}, {"KMX_RESV_LOG2": "12", "KMX_CLAIM_LOG2": "15"},
                                  {"KMX_CLAIM_FIRST": "1"}, {"KMX_CLAIM_FIRST": "1", "KMX_RESV_LOG2": "12", "KMX_CLAIM_LOG2": "15"},
                                  {"KMX_STREAM_CELLS": "7"}, {"KMX_STREAM_CELLS": "3", "KMX_CLAIM_FIRST": "1"},
                                  {"KMX_MERGED_PASSES": "1"}, {"KMX_MERGED_PASSES": "0"}, {"KMX_MERGED_PASSES": "1", "KMX_TEST_EPOCH_START": "16370"},
@@ -267,7 +267,7 @@ def test_empty_and_tiny_batches(built):
                                  {"KMX_MERGED_PASSES": "1", "KMX_RESV_LOG2": "12", "KMX_CLAIM_LOG2": "15"},
                                  {"KMX_MERGED_PASSES": "1", "KMX_CLAIM_FIRST": "1", "KMX_STREAM_CELLS": "3"}])
 def test_rare_paths_keep_parity(env, case_dbs, golden, tmp_path, monkeypatch):
-    """paths that only large inputs reach: reservation-epoch wrap-around, survivor list grown between launches,
+    """paths that only large inputs reach: reservation-epoch wrap-around,
     heavily aliased reservation / claim tables (aliasing may only delay decisions, never change them), the
     claim-first phase order, the L2 evict-first probes used for models that do not fit the L2, and both ways of
     resolving contested items (classic two-barrier iterations, merged reserve/commit passes)"""
