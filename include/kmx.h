@@ -72,6 +72,7 @@ typedef struct kmx_db_info_t {
 	uint64_t suffix_bytes;       /* record bytes of .kmc_suf (markers excluded)              */
 	uint32_t record_bytes;
 	int32_t on_device;
+	uint32_t both_strands;       /* 1: the database holds canonical k-mers (kmc_file.cpp:208-209) */
 } kmx_db_info_t;
 
 /* ---- process-wide ---------------------------------------------------------------------- */
@@ -123,6 +124,20 @@ void kmx_db_info(const kmx_db* db, kmx_db_info_t* info);
 int kmx_db_list(kmx_db* db, uint64_t* kmers, uint32_t* counts, uint64_t* n_out);
 void kmx_db_close(kmx_db* db);
 
+/* ---- KMC random access on the device-resident database: CKMCFile::OpenForRA / CheckKmer
+ * kmc_file.cpp:27-58,320-356,1358-1436 and GetCountersForRead kmc_file.cpp:879-897,1130-1352.  Not used by kmcEx itself; it is
+ * the exact-count ground truth for accuracy reports on kmer_to_occ (tools/accuracy_report.py).
+ * kmx_db_check_kmers: one CheckKmer per packed k-mer (first base most significant; NOT canonicalised, like CheckKmer): the bin
+ * comes from the k-mer's signature and the database's signature map, the LUT slot from its first lut_prefix_length bases, the
+ * record from a binary search over the suffixes; counts[i] = the counter, or 0 when the k-mer is absent or its counter lies
+ * outside [min_count, max_count].  All pointers are host pointers.
+ * kmx_db_counters_for_reads: GetCountersForRead for n_reads reads stored back to back in `bases` (read r = bytes
+ * offsets[r] .. offsets[r+1]); a read of length L yields max(0, L - k + 1) counters, all reads' counters back to back in
+ * `counters` (room for the sum); a window with a byte other than ACGTacgt counts 0; canonical k-mers are looked up when the
+ * database holds both strands.  *n_counters_out (may be NULL) = counters written.                                          */
+int kmx_db_check_kmers(kmx_db* db, const uint64_t* kmers, int64_t n, uint32_t* counts);
+int kmx_db_counters_for_reads(kmx_db* db, const char* bases, const int64_t* offsets, int64_t n_reads, uint32_t* counters, int64_t* n_counters_out);
+
 /* ---- host-side pieces of the path, exposed for known-answer tests (no GPU needed) --------- */
 uint64_t kmx_host_murmur64(const void* key, int len, uint32_t seed);   /* tools.hpp:16-50    */
 uint64_t kmx_host_hash_packed(uint64_t kmer, int len, uint32_t seed);  /* same, on the ASCII expansion */
@@ -133,6 +148,7 @@ int kmx_host_occubin(int max_counter, int n_hash, int32_t* occ2bin, int32_t* bin
  * bytes[3..5]=byte_bf_back, bytes[6]=km_byte_size, bytes[7]=byte_km_back                     */
 void kmx_host_sizes(const uint64_t kmer_counts[3], int bf_num, uint64_t km_kmers, int n_hash, uint64_t bytes[8]);
 uint64_t kmx_host_fastmod(uint64_t h, uint64_t d);                     /* the device's exact h % d */
+uint32_t kmx_host_signature(uint64_t kmer, int k, int signature_len);  /* CKmerAPI::get_signature, kmer_api.h:653-673 (len 5..11) */
 /* survivor permutation of reorder_buffer (kmodel.hpp:529-540) in closed form: failed[i] != 0
  * keeps item i; perm[j] = source index of output slot j; returns the new length            */
 int kmx_host_reorder(const uint8_t* failed, int n, int32_t* perm);

@@ -35,7 +35,7 @@ class KmxDbInfo(C.Structure):
         ("k", C.c_uint32), ("mode", C.c_uint32), ("counter_size", C.c_uint32), ("lut_prefix_length", C.c_uint32),
         ("signature_len", C.c_uint32), ("min_count", C.c_uint32), ("max_count", C.c_uint32), ("kmc_version", C.c_uint32),
         ("total_kmers", C.c_uint64), ("lut_entries", C.c_uint64), ("suffix_bytes", C.c_uint64),
-        ("record_bytes", C.c_uint32), ("on_device", C.c_int32),
+        ("record_bytes", C.c_uint32), ("on_device", C.c_int32), ("both_strands", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -71,6 +71,8 @@ SIGNATURES = {
     "kmx_db_info": (None, [C.c_void_p, C.POINTER(KmxDbInfo)]),
     "kmx_db_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "kmx_db_close": (None, [C.c_void_p]),
+    "kmx_db_check_kmers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kmx_db_counters_for_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
     "kmx_host_murmur64": (C.c_uint64, [C.c_char_p, C.c_int, C.c_uint32]),
     "kmx_host_hash_packed": (C.c_uint64, [C.c_uint64, C.c_int, C.c_uint32]),
     "kmx_host_canonical": (C.c_uint64, [C.c_uint64, C.c_int]),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "kmx_host_occubin": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "kmx_host_sizes": (None, [C.POINTER(C.c_uint64), C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     "kmx_host_fastmod": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "kmx_host_signature": (C.c_uint32, [C.c_uint64, C.c_int, C.c_int]),
     "kmx_host_reorder": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "kmx_count_fastq": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(KmxCountInfo)]),
     "kmx_set_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),

@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "kmcex_b200", "csrc")
 LIB = os.path.join(ROOT, "kmcex_b200", "libkmx.so")
-SOURCES = ["kmx_host.cu", "kmx_team.cu", "kmx_build.cu", "kmx_sort.cu", "kmx_query.cu", "kmx_microbench.cu", "kmx_count.cu", "kmx_dist.cu", "kmx_selftest.cu"]
+SOURCES = ["kmx_host.cu", "kmx_team.cu", "kmx_build.cu", "kmx_sort.cu", "kmx_query.cu", "kmx_microbench.cu", "kmx_count.cu", "kmx_dist.cu", "kmx_selftest.cu", "kmx_ra.cu"]
 HEADERS = ["kmx_core.cuh", "kmx_device.cuh", "kmx_launch.h", "kmx_gridbar.cuh", "kmx_internal.h", os.path.join(ROOT, "include", "kmx.h")]
 NVCC_FLAGS = ["--threads", "4", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=default", "-shared", "-cudart", "static", "-lz"]

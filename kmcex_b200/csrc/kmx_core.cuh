@@ -93,6 +93,37 @@ KMX_HD uint64_t canonical(uint64_t v, int k, uint64_t* r_out) {
 	return rc;
 }
 
+// ---------------------------------------------------------------------------------------
+// KMC signatures (minimisers with exclusions).  Only the random-access lookups need them: the bin of a k-mer is
+// signature_map[min over its m-mers of norm(m)] (kmer_api.h:653-673, kmc_file.cpp:339-340), where norm(m) is the smaller
+// of m and its reverse complement among those that are allowed, and 4^len when neither is (mmer.h:33-88).  Not allowed:
+// a TTT, TGT or TT* ending, an ACA beginning, and AA anywhere except as the first two bases.  m-mers are packed like
+// k-mers (first base most significant); len is 5..11.
+// ---------------------------------------------------------------------------------------
+KMX_HD bool mmer_allowed(uint32_t m, int len) {
+	const uint32_t tail = m & 0x3Fu;
+	if (tail == 0x3Fu || tail == 0x3Bu || (m & 0x3Cu) == 0x3Cu) return false;
+	const uint32_t is_a = ~(m | (m >> 1)) & 0x55555555u & (uint32_t)mask2(len);   // bit 2j: base j, counted from the end, is A
+	if (is_a & (is_a >> 2) & (uint32_t)mask2(len - 2)) return false;              // bases j and j + 1 are A, j <= len - 3
+	return (m >> (2 * (len - 3))) != 4u;                                          // ACA in front
+}
+
+KMX_HD uint32_t mmer_norm(uint32_t m, int len) {
+	const uint32_t none = 1u << (2 * len);
+	const uint32_t rc = (uint32_t)((~reverse_bases((uint64_t)m, len)) & mask2(len));
+	const uint32_t a = mmer_allowed(m, len) ? m : none, b = mmer_allowed(rc, len) ? rc : none;
+	return a < b ? a : b;
+}
+
+KMX_HD uint32_t kmer_signature(uint64_t v, int k, int len) {
+	uint32_t best = 0xFFFFFFFFu;
+	for (int shift = 2 * (k - len); shift >= 0; shift -= 2) {
+		const uint32_t n = mmer_norm((uint32_t)(v >> shift) & (uint32_t)mask2(len), len);
+		best = n < best ? n : best;
+	}
+	return best;
+}
+
 // 8 bases (16 bits, base j in bits [2j,2j+1]) -> 8 ASCII bytes, byte j = "ACGT"[base j]
 KMX_HD uint64_t ascii8(uint32_t x) {
 #ifdef __CUDA_ARCH__

@@ -587,6 +587,8 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	memcpy(&h.min_count, p + 20, 4);
 	memcpy(&h.max_count, p + 24, 4);
 	memcpy(&h.total_kmers, p + 28, 8);
+	db->both_strands = p[36] == 0;                        // kmc_file.cpp:208-209: the byte says "forward strand only"
+	h.both_strands = db->both_strands ? 1 : 0;
 	const uint64_t body = pre_size - 12;                  // two markers and the header_offset word removed
 	const uint64_t sig_bytes = ((1ULL << (2 * (h.signature_len & 31))) + 1) * 4;
 	if (h.signature_len > 11 || sig_bytes + header_offset + 8 > body) {
@@ -624,6 +626,8 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 		}
 	}
 	db->lut[h.lut_entries] = h.total_kmers + 1;           // kmc_file.cpp:223
+	db->pre_name = pre_name;
+	db->sig_offset = 4 + (h.lut_entries + 1) * 8;         // kmc_file.cpp:224-226: the map follows the LUT and its guard word
 	h.record_bytes = (h.k - h.lut_prefix_length) / 4 + h.counter_size;   // kmc_file.cpp:230-232
 	h.suffix_bytes = (uint64_t)h.record_bytes * h.total_kmers;
 
@@ -774,6 +778,7 @@ extern "C" void kmx_db_close(kmx_db* db) {
 		cudaDeviceSynchronize();
 		dev_free(db->d_suf, nullptr);
 		dev_free(db->d_lut, nullptr);
+		dev_free(db->d_sigmap, nullptr);
 	}
 	if (db->fd >= 0) close(db->fd);
 	delete db;

@@ -122,6 +122,11 @@ struct kmx_db {
 	uint64_t* d_lut = nullptr;
 	int device = 0, sm_count = 0;
 	float ms_upload = 0;
+	// random access (kmx_ra.cu): the signature map is read from .kmc_pre at the first CheckKmer, not at open
+	std::string pre_name;
+	uint64_t sig_offset = 0;          // byte offset of the signature map in .kmc_pre
+	bool both_strands = true;         // kmc_file.cpp:208-209
+	uint32_t* d_sigmap = nullptr;     // [4^signature_len + 1] bin of every signature
 };
 
 namespace kmx {

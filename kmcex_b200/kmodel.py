@@ -47,6 +47,30 @@ class KmcDatabase:
         check(lib().kmx_db_list(self._h, kmers.ctypes.data, counts.ctypes.data, C.byref(n)))
         return kmers[: n.value], counts[: n.value]
 
+    # ---- random access (CKMCFile::OpenForRA / CheckKmer / GetCountersForRead, kmc_file.cpp:27-58,320-356,879-897) ----
+    def check_kmers(self, kmers) -> np.ndarray:
+        """exact counter of every packed k-mer (as given, not canonicalised): 0 when absent or outside [min_count, max_count]"""
+        q = np.ascontiguousarray(kmers, dtype=np.uint64)
+        out = np.zeros(q.size, dtype=np.uint32)
+        check(lib().kmx_db_check_kmers(self._h, q.ctypes.data, q.size, out.ctypes.data))
+        return out
+
+    def counters_for_reads(self, reads) -> list[np.ndarray]:
+        """one array of len(read) - k + 1 counters per read (empty for reads shorter than k); windows holding a byte other
+        than ACGTacgt count 0; canonical k-mers are looked up when the database holds both strands"""
+        raw = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+        offsets = np.zeros(len(raw) + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in raw], out=offsets[1:])
+        flat = np.frombuffer(b"".join(raw) or b"\0", dtype=np.uint8)
+        k = self.info["k"]
+        sizes = [max(0, len(r) - k + 1) for r in raw]
+        out = np.zeros(max(1, sum(sizes)), dtype=np.uint32)
+        n = C.c_int64(0)
+        check(lib().kmx_db_counters_for_reads(self._h, flat.ctypes.data, offsets.ctypes.data, len(raw), out.ctypes.data, C.byref(n)))
+        assert n.value == sum(sizes)
+        cuts = np.cumsum([0] + sizes)
+        return [out[cuts[i]: cuts[i + 1]] for i in range(len(raw))]
+
     def close(self) -> None:
         if self._h:
             lib().kmx_db_close(self._h)

@@ -202,22 +202,58 @@ def synth_direct_spectrum(genome_bp: int, coverage: float, read_len: int, k: int
                     genome=genome.to(torch.uint8).cpu().numpy())
 
 
+def kmc_signatures(kmers: np.ndarray, k: int, signature_len: int) -> np.ndarray:
+    """KMC's signature of every packed k-mer: the smallest normalised m-mer (m = signature_len); an m-mer normalises to the
+    smaller of itself and its reverse complement among those that are allowed, to 4^m when neither is.  Not allowed: a TTT,
+    TGT or TT? ending, an ACA beginning, AA anywhere but in front.  (What a real KMC run bins its records by; used to write
+    test databases that CKMCFile::CheckKmer can search, kmc_file.cpp:339-340.)"""
+    m = signature_len
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    none = np.uint32(1 << (2 * m))
+
+    def allowed(x: np.ndarray) -> np.ndarray:
+        ok = ((x & 0x3F) != 0x3F) & ((x & 0x3F) != 0x3B) & ((x & 0x3C) != 0x3C)
+        for j in range(m - 2):                                  # bases j and j + 1 (from the end) both A
+            ok &= ((x >> (2 * j)) & 0xF) != 0
+        ok &= (x >> (2 * (m - 3))) != 4
+        return ok
+
+    best = np.full(kmers.size, 0xFFFFFFFF, dtype=np.uint32)
+    for i in range(k - m + 1):
+        x = ((kmers >> np.uint64(2 * (k - m - i))) & np.uint64((1 << (2 * m)) - 1)).astype(np.uint32)
+        rc = np.zeros_like(x)
+        t = x.copy()
+        for _ in range(m):
+            rc = (rc << 2) | (3 - (t & 3))
+            t >>= 2
+        cand = np.minimum(np.where(allowed(x), x, none), np.where(allowed(rc), rc, none))
+        best = np.minimum(best, cand)
+    return best
+
+
 def write_kmc_db(base: str, kmers: np.ndarray, counts: np.ndarray, k: int = 31, lut_prefix_length: int = 3,
                  n_bins: int = 1, counter_size: int = 2, min_count: int = 1, max_count: int = 1023,
-                 signature_len: int = 7) -> int:
+                 signature_len: int = 7, signature_bins: bool = False, one_strand: bool = False) -> int:
     """Write <base>.kmc_pre / <base>.kmc_suf (KMC2/3 layout, version word 0x200).
 
     kmers must be unique packed values; they are split over n_bins by a hash of the value (KMC
     bins by minimiser signature; the listing reader only needs sorted records per bin and a
-    per-bin LUT, kmc_file.cpp:439-449) and sorted within each bin. Returns the record count."""
+    per-bin LUT, kmc_file.cpp:439-449) and sorted within each bin. Returns the record count.
+    signature_bins: bin by KMC signature and write the signature map, as a real KMC run does, so that the
+    random-access API (CheckKmer) finds the records; one_strand sets the header's "forward strand only" byte."""
     assert (k - lut_prefix_length) % 4 == 0 and 1 <= k <= 32
     kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
     counts = np.ascontiguousarray(counts, dtype=np.uint32)
     n = kmers.size
     suf_bytes = (k - lut_prefix_length) // 4
-    if n >= (1 << 23) and torch.cuda.is_available():
+    sig_map = np.zeros(4 ** signature_len + 1, dtype=np.uint32)
+    if n >= (1 << 23) and torch.cuda.is_available() and not signature_bins and not one_strand:
         return _write_kmc_db_cuda(base, kmers, counts, k, lut_prefix_length, n_bins, counter_size, min_count, max_count, signature_len)
-    if n_bins > 1:
+    if signature_bins:
+        all_sigs = np.arange(4 ** signature_len + 1, dtype=np.uint64)
+        sig_map = (((all_sigs * np.uint64(2654435761)) >> np.uint64(9)) % np.uint64(n_bins)).astype(np.uint32)
+        bins = sig_map[kmc_signatures(kmers, k, signature_len)].astype(np.int64)
+    elif n_bins > 1:
         h = (kmers * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(40)
         bins = (h % np.uint64(n_bins)).astype(np.int64)
     else:
@@ -241,11 +277,11 @@ def write_kmc_db(base: str, kmers: np.ndarray, counts: np.ndarray, k: int = 31, 
         f.write(rec.tobytes())
         f.write(b"KMCS")
     header = struct.pack("<7IQB7x5I I", k, 0, counter_size, lut_prefix_length, signature_len, min_count, max_count,
-                         n, 0, 0, 0, 0, 0, 0, 0x200)
+                         n, 1 if one_strand else 0, 0, 0, 0, 0, 0, 0x200)
     with open(base + ".kmc_pre", "wb") as f:
         f.write(b"KMCP")
         f.write(lut.tobytes())
-        f.write(np.zeros(4 ** signature_len + 1, dtype=np.uint32).tobytes())
+        f.write(sig_map.tobytes())
         f.write(header)
         f.write(struct.pack("<I", len(header)))
         f.write(b"KMCP")

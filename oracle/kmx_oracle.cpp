@@ -527,6 +527,8 @@ struct KmcDbO {
 	uint64_t total = 0;
 	std::vector<uint64_t> lut;      // n entries + guard
 	std::vector<uint8_t> suf;       // record bytes (markers stripped)
+	std::vector<uint32_t> signature_map;   // 4^signature_len + 1 bin numbers (kmc_file.cpp:211,224-226)
+	bool both_strands = true;       // kmc_file.cpp:208-209
 	uint32_t sufix_size = 0, rec_size = 0;
 
 	static bool slurp(const std::string& path, const char* marker, std::vector<uint8_t>& out) {
@@ -559,6 +561,9 @@ struct KmcDbO {
 		lut.resize(n + 1);
 		memcpy(lut.data(), &pre[4], (n + 1) * 8);
 		lut[n] = total + 1;                                       // kmc_file.cpp:223
+		both_strands = h[36] == 0;                                // kmc_file.cpp:208-209 (the byte means "one strand only")
+		signature_map.resize(sig_bytes / 4);
+		memcpy(signature_map.data(), &pre[4 + (n + 1) * 8], sig_bytes);   // kmc_file.cpp:224-226
 		sufix_size = (k - lut_prefix_length) / 4;                 // kmc_file.cpp:230-232
 		rec_size = sufix_size + counter_size;
 		std::vector<uint8_t> raw;
@@ -581,6 +586,103 @@ struct KmcDbO {
 		}
 	}
 };
+
+// ---- random access: CKMCFile::CheckKmer / GetCountersForRead ----------------------------------
+// mmer.h:33-58 -- which m-mers may be signatures (mmer packed like a k-mer, first base most significant)
+bool mmer_is_allowed(uint32_t mmer, uint32_t len) {
+	if ((mmer & 0x3f) == 0x3f) return false;                  // ...TTT
+	if ((mmer & 0x3f) == 0x3b) return false;                  // ...TGT
+	if ((mmer & 0x3c) == 0x3c) return false;                  // ...TT?
+	for (uint32_t j = 0; j + 3 < len; j++) {                  // AA anywhere behind the third base
+		if ((mmer & 0xf) == 0) return false;
+		mmer >>= 2;
+	}
+	if (mmer == 0) return false;                              // AAA...
+	if (mmer == 0x04) return false;                           // ACA...
+	if ((mmer & 0xf) == 0) return false;                      // ?AA...
+	return true;
+}
+
+// mmer.h:63-88 -- norm[]: the smaller of an m-mer and its reverse complement among the allowed ones, 4^len if neither is
+uint32_t mmer_norm(uint32_t mmer, uint32_t len) {
+	const uint32_t special = 1u << (2 * len);
+	const uint32_t rev = (uint32_t)revcomp(mmer, (int)len);
+	const uint32_t a = mmer_is_allowed(mmer, len) ? mmer : special, b = mmer_is_allowed(rev, len) ? rev : special;
+	return std::min(a, b);
+}
+
+// kmer_api.h:653-673 -- CKmerAPI::get_signature: the minimum norm over the k-mer's m-mers
+uint32_t kmer_signature(uint64_t v, int k, int len) {
+	uint32_t best = 0xFFFFFFFFu;
+	for (int i = 0; i + len <= k; i++) {
+		const uint32_t mmer = (uint32_t)(v >> (2 * (k - len - i))) & ((1u << (2 * len)) - 1);
+		best = std::min(best, mmer_norm(mmer, (uint32_t)len));
+	}
+	return best;
+}
+
+// kmc_file.cpp:320-356 (CheckKmer) + :1358-1436 (BinarySearch, inclusive bounds, suffix bytes compared most significant
+// first, counter range check).  The guard word makes the last slot end one record past the file; that probe reads beyond
+// the buffer in the reference and is treated as "no record" here.
+uint32_t db_check_kmer(const KmcDbO& db, uint64_t v) {
+	const uint32_t suffix_bases = db.k - db.lut_prefix_length;
+	const uint64_t prefix = suffix_bases >= 32 ? 0 : v >> (2 * suffix_bases);
+	const uint64_t single_lut = 1ULL << (2 * db.lut_prefix_length);
+	if (db.signature_len < 5 || db.signature_len > 11) return 0;
+	const uint64_t bin_start = (uint64_t)db.signature_map[kmer_signature(v, (int)db.k, (int)db.signature_len)] * single_lut;
+	if (bin_start + prefix + 1 >= db.lut.size()) return 0;
+	int64_t index_start = (int64_t)db.lut[bin_start + prefix], index_stop = (int64_t)db.lut[bin_start + prefix + 1] - 1;
+	if ((uint64_t)index_start >= db.total) return 0;
+	while (index_start <= index_stop) {
+		const int64_t mid = (index_start + index_stop) / 2;
+		if ((uint64_t)mid >= db.total) { index_stop = mid - 1; continue; }
+		const uint8_t* rec = &db.suf[(uint64_t)mid * db.rec_size];
+		int cmp = 0;                                              // sign of (record suffix - pattern suffix)
+		for (uint32_t a = 0; a < db.sufix_size && cmp == 0; a++) {
+			const uint32_t pattern = (uint32_t)(v >> (8 * (db.sufix_size - 1 - a))) & 0xff;
+			cmp = (int)rec[a] - (int)pattern;
+		}
+		if (cmp == 0) {
+			uint32_t c = 0;
+			for (uint32_t b = 0; b < db.counter_size && b < 4; b++) c |= (uint32_t)rec[db.sufix_size + b] << (8 * b);
+			return (c >= db.min_count && c <= db.max_count) ? c : 0;
+		}
+		if (cmp < 0) index_start = mid + 1;
+		else index_stop = mid - 1;
+	}
+	return 0;
+}
+
+// kmc_file.cpp:879-897, 1130-1352 -- GetCountersForRead (KMC2 layout).  The reference walks super-k-mers (maximal runs of
+// windows that share a signature); per window that is: a byte outside ACGTacgt -> 0, else the counter of the window's
+// k-mer (the smaller of it and its reverse complement when the database holds both strands) in the bin of its signature.
+int64_t db_counters_for_read(const KmcDbO& db, const char* read, int64_t len, uint32_t* counters) {
+	if (len < (int64_t)db.k) return 0;                            // kmc_file.cpp:884-888
+	const int k = (int)db.k;
+	for (int64_t i = 0; i + k <= len; i++) {
+		uint64_t v = 0;
+		bool valid = true;
+		for (int j = 0; j < k; j++) {
+			int code;
+			switch (read[i + j]) {                                // CKmerAPI::num_codes, kmer_api.h:268-273
+				case 'A': case 'a': code = 0; break;
+				case 'C': case 'c': code = 1; break;
+				case 'G': case 'g': code = 2; break;
+				case 'T': case 't': code = 3; break;
+				default: code = -1;
+			}
+			if (code < 0) { valid = false; break; }
+			v = (v << 2) | (uint64_t)code;
+		}
+		if (!valid) { counters[i] = 0; continue; }
+		if (db.both_strands) {
+			const uint64_t rc = revcomp(v, k);
+			if (!(v < rc)) v = rc;                                // kmc_file.cpp:1261-1264
+		}
+		counters[i] = db_check_kmer(db, v);
+	}
+	return len - k + 1;
+}
 
 struct Item { uint64_t kmer; uint32_t occ; };
 
@@ -703,6 +805,25 @@ int64_t kmxo_list(const char* db_base, uint64_t* kmers, uint32_t* counts, int64_
 	if (k_out) *k_out = (int32_t)db.k;
 	if (total_out) *total_out = db.total;
 	return n;
+}
+
+uint32_t kmxo_signature(uint64_t kmer, int k, int len) { return kmer_signature(kmer, k, len); }
+
+// CheckKmer per packed k-mer; returns n or -1
+int64_t kmxo_check_kmers(const char* db_base, const uint64_t* kmers, int64_t n, uint32_t* counts) {
+	KmcDbO db;
+	if (!db.open(db_base)) return -1;
+	for (int64_t i = 0; i < n; i++) counts[i] = db_check_kmer(db, kmers[i]);
+	return n;
+}
+
+// GetCountersForRead for reads stored back to back (read r = bytes offsets[r] .. offsets[r+1]); returns the counters written or -1
+int64_t kmxo_counters_for_reads(const char* db_base, const char* bases, const int64_t* offsets, int64_t n_reads, uint32_t* counters) {
+	KmcDbO db;
+	if (!db.open(db_base)) return -1;
+	int64_t at = 0;
+	for (int64_t r = 0; r < n_reads; r++) at += db_counters_for_read(db, bases + offsets[r], offsets[r + 1] - offsets[r], counters + at);
+	return at;
 }
 
 // build from a KMC db and save to out_dir; stats[3] = {attempts, accepted, rest}

@@ -15,7 +15,9 @@
 //   query  <model_dir> <packed_u64.bin> <k> <out_i32.bin> <threads>
 //   query_ascii <model_dir> <strings.bin> <k> <out_i32.bin> <threads>    n strings of k raw bytes each (N, lower case allowed)
 //   list   <db_base> <out.bin>         (u64 kmer, u32 count) records in listing order
-//   kat    <out.txt>                   known-answer values for hash / canonical / OccuBin
+//   check  <db_base> <packed_u64.bin> <out_u32.bin>     CKMCFile::OpenForRA + CheckKmer per k-mer (0 when it says false)
+//   reads  <db_base> <reads.txt> <out_u32.bin>          CKMCFile::GetCountersForRead per line, counters back to back
+//   kat    <out.txt>                   known-answer values for hash / canonical / OccuBin / KMC signatures
 #include "kmodel.hpp"
 #include <chrono>
 
@@ -109,6 +111,56 @@ static int cmd_list(int argc, char** argv) {
 	return 0;
 }
 
+// random access: kmc_file.cpp:27-58 (OpenForRA), :320-356 (CheckKmer), :879-897 (GetCountersForRead)
+static int cmd_check(int argc, char** argv) {
+	if (argc < 5) return 2;
+	CKMCFile db;
+	if (!db.OpenForRA(argv[2])) { printf("cannot open db %s\n", argv[2]); return 1; }
+	FILE* f = fopen(argv[3], "rb");
+	if (!f) { printf("cannot open %s\n", argv[3]); return 1; }
+	fseek(f, 0, SEEK_END);
+	size_t n = ftell(f) / 8;
+	fseek(f, 0, SEEK_SET);
+	vector<uint64_t> packed(n);
+	if (n && fread(packed.data(), 8, n, f) != n) return 1;
+	fclose(f);
+	const int k = (int)db.KmerLength();
+	vector<uint32_t> out(n, 0);
+	CKmerAPI kmer(k);
+	size_t hits = 0;
+	for (size_t i = 0; i < n; i++) {
+		kmer.from_string(Tools::uint64_to_string(packed[i], k));
+		uint32 c = 0;
+		if (db.CheckKmer(kmer, c)) { out[i] = c; hits++; }
+	}
+	FILE* fo = fopen(argv[4], "wb");
+	if (n) fwrite(out.data(), 4, n, fo);
+	fclose(fo);
+	printf("{\"n\": %zu, \"hits\": %zu}\n", n, hits);
+	return 0;
+}
+
+static int cmd_reads(int argc, char** argv) {
+	if (argc < 5) return 2;
+	CKMCFile db;
+	if (!db.OpenForRA(argv[2])) { printf("cannot open db %s\n", argv[2]); return 1; }
+	ifstream in(argv[3]);
+	FILE* fo = fopen(argv[4], "wb");
+	string line;
+	size_t n_reads = 0, n_counters = 0;
+	while (getline(in, line)) {
+		vector<uint32_t> counters;
+		if (db.GetCountersForRead(line, counters) && !counters.empty()) {
+			fwrite(counters.data(), 4, counters.size(), fo);
+			n_counters += counters.size();
+		}
+		n_reads++;
+	}
+	fclose(fo);
+	printf("{\"reads\": %zu, \"counters\": %zu}\n", n_reads, n_counters);
+	return 0;
+}
+
 static int cmd_kat(int argc, char** argv) {
 	if (argc < 3) return 2;
 	FILE* fo = fopen(argv[2], "w");
@@ -124,6 +176,25 @@ static int cmd_kat(int argc, char** argv) {
 					(unsigned long long)Tools::murmur_hash64(s.c_str(), len, HashSeeds[si]));
 			}
 			fprintf(fo, "minkmer %s %s\n", s.c_str(), Tools::get_min_kmer(s).c_str());
+			for (int sl = 5; sl <= 11; sl += 2) {             // CKmerAPI::get_signature, kmer_api.h:653-673
+				if (sl > len) break;
+				CKmerAPI ka(len);
+				ka.from_string(s);
+				fprintf(fo, "signature %s %d %u\n", s.c_str(), sl, ka.get_signature(sl));
+			}
+		}
+	}
+	{
+		// signatures of strings rich in the excluded patterns (AA inside, TT* / TGT endings, ACA beginning)
+		const char* pat[] = { "AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "ACAACAACAACAACAACAACAACAACAACAA", "TGTTGTTGTTGTTGTTGTTGTTGTTGTTGTT",
+		                      "AACCAACCAACCAACCAACCAACCAACCAAC", "ACGTTTACGTTTACGTTTACGTTTACGTTTA", "CAAGCAAGCAAGCAAGCAAGCAAGCAAGCAA", "GATTACAGATTACAGATTACAGATTACAGAT" };
+		for (const char* p : pat) {
+			string s(p);
+			for (int sl = 5; sl <= 11; sl++) {
+				CKmerAPI ka((uint32)s.size());
+				ka.from_string(s);
+				fprintf(fo, "signature %s %d %u\n", s.c_str(), sl, ka.get_signature(sl));
+			}
 		}
 	}
 	int cfgs[4][2] = { {1024, 7}, {256, 7}, {1024, 6}, {65536, 8} };
@@ -139,12 +210,14 @@ static int cmd_kat(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 2) { printf("usage: ref_driver build|query|query_ascii|list|kat ...\n"); return 2; }
+	if (argc < 2) { printf("usage: ref_driver build|query|query_ascii|list|check|reads|kat ...\n"); return 2; }
 	string c = argv[1];
 	if (c == "build") return cmd_build(argc, argv);
 	if (c == "query") return cmd_query(argc, argv);
 	if (c == "query_ascii") return cmd_query_ascii(argc, argv);
 	if (c == "list") return cmd_list(argc, argv);
+	if (c == "check") return cmd_check(argc, argv);
+	if (c == "reads") return cmd_reads(argc, argv);
 	if (c == "kat") return cmd_kat(argc, argv);
 	return 2;
 }

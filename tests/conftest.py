@@ -54,7 +54,33 @@ def oracle():
     lib.kmxo_query_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.kmxo_query_path.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.kmxo_query_ascii.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    lib.kmxo_signature.restype = C.c_uint32
+    lib.kmxo_signature.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    lib.kmxo_check_kmers.restype = C.c_int64
+    lib.kmxo_check_kmers.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.kmxo_counters_for_reads.restype = C.c_int64
+    lib.kmxo_counters_for_reads.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     return lib
+
+
+@pytest.fixture(scope="session")
+def ra_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "ra.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def ra_dbs(tmp_path_factory):
+    """regenerates the seeded random-access databases of tests/golden/cases.py on demand (cached per session)"""
+    import cases
+    root = str(tmp_path_factory.mktemp("kmx_ra_cases"))
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = cases.make_ra_db(name, root)
+        return cache[name]
+    return get
 
 
 @pytest.fixture(scope="session")

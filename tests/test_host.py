@@ -63,6 +63,26 @@ def test_murmur_and_canonical_known_answers(kat_lines, oracle):
     assert lib.kmx_host_murmur64(b"CGTACGTACGTACGTACGTACGTACGTAC", 29, 46757) == 2953946542005570904
 
 
+def test_kmc_signature_known_answers(kat_lines, oracle):
+    """CKmerAPI::get_signature (kmer_api.h:653-673, mmer.h:33-88): library, oracle and the test-data writer against the reference"""
+    from kmcex_b200 import synth
+    lib = kx.lib()
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    n = 0
+    for parts in kat_lines:
+        if parts[0] != "signature":
+            continue
+        s, sl, want = parts[1], int(parts[2]), int(parts[3])
+        v = 0
+        for ch in s:
+            v = (v << 2) | code[ch]
+        assert lib.kmx_host_signature(v, len(s), sl) == want, (s, sl)
+        assert oracle.kmxo_signature(v, len(s), sl) == want, (s, sl)
+        assert int(synth.kmc_signatures(np.array([v], dtype=np.uint64), len(s), sl)[0]) == want, (s, sl)
+        n += 1
+    assert n >= 400
+
+
 def test_seed_table(oracle):
     lib = kx.lib()
     seeds = [lib.kmx_host_seed(i) for i in range(128)]

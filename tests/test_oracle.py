@@ -93,3 +93,55 @@ def test_oracle_matches_live_reference_on_a_fresh_seed(k, lut, csz, cs, ci, nh, 
     oracle.kmxo_query_packed(h, q.ctypes.data, q.size, occ.ctypes.data)
     oracle.kmxo_free(h)
     assert (occ == ref).all()
+
+
+# ---- random access: CKMCFile::CheckKmer / GetCountersForRead ---------------------------------------
+def _oracle_ra(oracle, base, q, reads):
+    counts = np.zeros(q.size, dtype=np.uint32)
+    assert oracle.kmxo_check_kmers(base.encode(), q.ctypes.data, q.size, counts.ctypes.data) == q.size
+    flat, off = cases.flat_reads(reads)
+    k_total = int(off[-1]) + 1
+    rc = np.zeros(k_total, dtype=np.uint32)
+    n = oracle.kmxo_counters_for_reads(base.encode(), flat.ctypes.data, off.ctypes.data, len(reads), rc.ctypes.data)
+    assert n >= 0
+    return counts, rc[:n]
+
+
+@pytest.mark.parametrize("name", sorted(cases.RA_CASES))
+def test_oracle_random_access_matches_reference_goldens(name, oracle, ra_dbs, ra_golden):
+    g = ra_golden[name]
+    base, sp = ra_dbs(name)
+    assert cases.md5_file(base + ".kmc_pre") == g["db_md5"]["kmc_pre"] and cases.md5_file(base + ".kmc_suf") == g["db_md5"]["kmc_suf"]
+    q = cases.ra_queries(sp, g["params"]["seed"] + 100)
+    reads = cases.ra_reads(sp, g["params"]["seed"] + 200)
+    assert hashlib.md5(q.tobytes()).hexdigest() == g["query_md5"] and hashlib.md5(b"\n".join(reads)).hexdigest() == g["reads_md5"]
+    counts, rc = _oracle_ra(oracle, base, q, reads)
+    assert int((counts != 0).sum()) == g["check_hits"] and counts[:32].tolist() == g["check_head"]
+    assert hashlib.md5(counts.tobytes()).hexdigest() == g["check_md5"]
+    assert rc.size == g["read_counters"] and int((rc != 0).sum()) == g["read_counters_nonzero"]
+    assert hashlib.md5(rc.tobytes()).hexdigest() == g["read_counters_md5"]
+    if g["params"]["signature_bins"] and g["params"]["min_count"] == 1:
+        # ground truth: with a real signature map every stored k-mer is found with its counter
+        assert (counts[:6000] == sp.counts[np.searchsorted(sp.kmers, q[:6000])]).all()
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("k,lut,sig,csz,bins,one_strand", [(31, 7, 6, 2, 3, False), (19, 3, 8, 1, 2, True), (27, 7, 11, 4, 6, False), (15, 3, 10, 2, 1, False)])
+def test_oracle_random_access_matches_live_reference(k, lut, sig, csz, bins, one_strand, oracle, tmp_path):
+    from kmcex_b200 import synth
+    base = str(tmp_path / "db")
+    cs = 255 if csz == 1 else 1023
+    sp = synth.synth_reads_spectrum(30_000, 25, 100, k=k, seed=300 + k, ci=1, cs=cs, device="cpu")
+    synth.write_kmc_db(base, sp.kmers, sp.counts, k=k, lut_prefix_length=lut, n_bins=bins, counter_size=csz, min_count=2, max_count=cs - 1,
+                       signature_len=sig, signature_bins=True, one_strand=one_strand)
+    q = cases.ra_queries(sp, 1000 + k)
+    reads = cases.ra_reads(sp, 2000 + k)
+    qf, cf, rf, of = (str(tmp_path / n) for n in ("q.bin", "c.bin", "reads.txt", "rc.bin"))
+    q.tofile(qf)
+    with open(rf, "wb") as f:
+        f.write(b"\n".join(reads) + b"\n")
+    subprocess.run([REF, "check", base, qf, cf], check=True, capture_output=True)
+    subprocess.run([REF, "reads", base, rf, of], check=True, capture_output=True)
+    counts, rc = _oracle_ra(oracle, base, q, reads)
+    assert (counts == np.fromfile(cf, dtype=np.uint32)).all()
+    assert rc.size == os.path.getsize(of) // 4 and (rc == np.fromfile(of, dtype=np.uint32)).all()
