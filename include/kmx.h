@@ -136,6 +136,10 @@ void kmx_db_close(kmx_db* db);
  * `counters` (room for the sum); a window with a byte other than ACGTacgt counts 0; canonical k-mers are looked up when the
  * database holds both strands.  *n_counters_out (may be NULL) = counters written.                                          */
 int kmx_db_check_kmers(kmx_db* db, const uint64_t* kmers, int64_t n, uint32_t* counts);
+/* CKMCFile::SetMinCount / SetMaxCount / ResetMinMaxCounts kmc_file.cpp:670-734: narrow the counter range (inside the header's)
+ * that the listing and the random-access calls apply; kmx_db_info reports the current range                                */
+int kmx_db_set_count_range(kmx_db* db, uint32_t min_count, uint32_t max_count);
+int kmx_db_reset_count_range(kmx_db* db);
 int kmx_db_counters_for_reads(kmx_db* db, const char* bases, const int64_t* offsets, int64_t n_reads, uint32_t* counters, int64_t* n_counters_out);
 
 /* ---- host-side pieces of the path, exposed for known-answer tests (no GPU needed) --------- */

@@ -72,6 +72,8 @@ SIGNATURES = {
     "kmx_db_list": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "kmx_db_close": (None, [C.c_void_p]),
     "kmx_db_check_kmers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kmx_db_set_count_range": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "kmx_db_reset_count_range": (C.c_int, [C.c_void_p]),
     "kmx_db_counters_for_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
     "kmx_host_murmur64": (C.c_uint64, [C.c_char_p, C.c_int, C.c_uint32]),
     "kmx_host_hash_packed": (C.c_uint64, [C.c_uint64, C.c_int, C.c_uint32]),

@@ -587,6 +587,8 @@ extern "C" kmx_db* kmx_db_open(const char* db_base) {
 	memcpy(&h.min_count, p + 20, 4);
 	memcpy(&h.max_count, p + 24, 4);
 	memcpy(&h.total_kmers, p + 28, 8);
+	db->orig_min_count = h.min_count;
+	db->orig_max_count = h.max_count;
 	db->both_strands = p[36] == 0;                        // kmc_file.cpp:208-209: the byte says "forward strand only"
 	h.both_strands = db->both_strands ? 1 : 0;
 	const uint64_t body = pre_size - 12;                  // two markers and the header_offset word removed

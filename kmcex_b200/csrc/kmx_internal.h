@@ -126,6 +126,8 @@ struct kmx_db {
 	std::string pre_name;
 	uint64_t sig_offset = 0;          // byte offset of the signature map in .kmc_pre
 	bool both_strands = true;         // kmc_file.cpp:208-209
+	uint32_t orig_min_count = 0, orig_max_count = 0;   // the header's counter range (SetMinCount / SetMaxCount narrow info.min/max_count)
+	std::mutex ra_mu;                 // guards the lazy creation of d_sigmap
 	uint32_t* d_sigmap = nullptr;     // [4^signature_len + 1] bin of every signature
 };
 

@@ -110,6 +110,7 @@ int ra_prepare(kmx_db* db, RaDb* r, cudaStream_t s) {
 	const uint64_t slots = 1ULL << (2 * h.lut_prefix_length);
 	if (h.lut_entries % slots != 0) return fail(KMX_EFORMAT, "%llu LUT entries are not a whole number of bins of 4^%u slots", (unsigned long long)h.lut_entries, h.lut_prefix_length);
 	CU(cudaSetDevice(db->device));
+	std::lock_guard<std::mutex> lock(db->ra_mu);
 	if (!db->d_sigmap) {
 		const size_t n_sig = ((size_t)1 << (2 * h.signature_len)) + 1;
 		std::vector<uint32_t> map(n_sig);
@@ -157,6 +158,24 @@ struct CtxLease {
 extern "C" uint32_t kmx_host_signature(uint64_t kmer, int k, int signature_len) {
 	if (k < 1 || k > 32 || signature_len < 5 || signature_len > 11 || signature_len > k) return 0xFFFFFFFFu;
 	return kmer_signature(kmer & mask2(k), k, signature_len);
+}
+
+// CKMCFile::SetMinCount / SetMaxCount / ResetMinMaxCounts (kmc_file.cpp:670-734): the range may only be narrowed within the
+// header's; it applies to the listing filter and to the random-access range check alike, as in the reference
+extern "C" int kmx_db_set_count_range(kmx_db* db, uint32_t min_count, uint32_t max_count) {
+	if (!db) return fail(KMX_EARG, "null argument");
+	if (min_count < db->orig_min_count || max_count > db->orig_max_count || min_count > max_count)
+		return fail(KMX_ERANGE, "counter range [%u, %u] is not inside the database's [%u, %u]", min_count, max_count, db->orig_min_count, db->orig_max_count);
+	db->info.min_count = min_count;
+	db->info.max_count = max_count;
+	return KMX_OK;
+}
+
+extern "C" int kmx_db_reset_count_range(kmx_db* db) {
+	if (!db) return fail(KMX_EARG, "null argument");
+	db->info.min_count = db->orig_min_count;
+	db->info.max_count = db->orig_max_count;
+	return KMX_OK;
 }
 
 extern "C" int kmx_db_check_kmers(kmx_db* db, const uint64_t* kmers, int64_t n, uint32_t* counts) {

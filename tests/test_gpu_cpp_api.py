@@ -106,3 +106,49 @@ def test_user_program_over_two_gpus_in_one_process(case_dbs, golden, tmp_path):
         got = np.array([int(x) for x in lines[: q.size]], dtype=np.int32)
         import hashlib
         assert hashlib.md5(got.tobytes()).hexdigest() == golden[name]["occ_md5"]
+
+
+def test_kmc_random_access_user_program(ra_dbs, ra_golden, oracle, tmp_path):
+    """the CKMCFile / CKmerAPI calls of the reference's kmc_api (OpenForRA, CheckKmer, GetCountersForRead, SetMinCount ...)
+    through include/kmc_ra.hpp; answers against the oracle (itself pinned to the compiled reference, tests/golden/ra.json)"""
+    name = "ra_k31_sig7"
+    base, sp = ra_dbs(name)
+    p = cases.RA_CASES[name]
+    exe = str(tmp_path / "ra_program")
+    _compile(os.path.join(ROOT, "tests", "cpp", "ra_program.cpp"), exe)
+    q = np.ascontiguousarray(cases.ra_queries(sp, p["seed"] + 100)[::40])
+    reads = [r for r in cases.ra_reads(sp, p["seed"] + 200)[::4] + [b"ACGTN", b"A" * 31] if b"\n" not in r and r]
+    kfile, rfile, ofile = str(tmp_path / "k.txt"), str(tmp_path / "r.txt"), str(tmp_path / "o.txt")
+    with open(kfile, "w") as f:
+        f.write("\n".join("".join(map(chr, row)) for row in synth.to_ascii(q, sp.k)) + "\n")
+    with open(rfile, "wb") as f:
+        f.write(b"\n".join(reads) + b"\n")
+    r = subprocess.run([exe, base, kfile, rfile, ofile], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want = np.zeros(q.size, dtype=np.uint32)
+    assert oracle.kmxo_check_kmers(base.encode(), q.ctypes.data, q.size, want.ctypes.data) == q.size
+    flat, off = cases.flat_reads(reads)
+    wr = np.zeros(int(off[-1]) + 1, dtype=np.uint32)
+    n = oracle.kmxo_counters_for_reads(base.encode(), flat.ctypes.data, off.ctypes.data, len(reads), wr.ctypes.data)
+    sizes = [max(0, len(x) - sp.k + 1) for x in reads]
+    assert n == sum(sizes)
+    cuts = np.cumsum([0] + sizes)
+    lines = open(ofile).read().split("\n")
+    assert lines[0] == f"k {sp.k} total {sp.kmers.size} min 1 max 1023 both 1"
+    at = 1
+    assert lines[at: at + q.size] == [f"{int(c != 0)} {int(c)}" for c in want]
+    at += q.size
+    for i, x in enumerate(reads):
+        exp = "-" if len(x) < sp.k else " ".join(str(int(c)) for c in wr[cuts[i]: cuts[i + 1]])
+        assert lines[at + i] == exp, (i, x)
+    at += len(reads)
+    assert lines[at] == "setmin 1 3 toolow 0"
+    at += 1
+    assert lines[at: at + q.size] == [str(int(c) if c >= 3 else 0) for c in want]          # CheckKmer under SetMinCount(3)
+    at += q.size
+    assert lines[at: at + q.size] == [str(int(c)) for c in want]                          # batch form after ResetMinMaxCounts
+    at += q.size
+    for i, x in enumerate(reads):
+        exp = " ".join([str(sizes[i])] + [str(int(c)) for c in wr[cuts[i]: cuts[i + 1]]])
+        assert lines[at + i] == exp, (i, x)
+    assert (want != 0).sum() > 100
