@@ -75,3 +75,26 @@ def test_fastq_to_model_end_to_end(oracle, tmp_path):
     occ = m.kmer_to_occ(want_k)
     exact = (occ == np.minimum(want_c, 1023)).mean()
     assert exact > 0.6 and (occ == 0).mean() < 0.01          # the model answers its own k-mers (binned above 31)
+    # the counter's database is also searchable the way CKMCFile::CheckKmer searches it (one bin, zero signature map),
+    # and the reads it was counted from get their own k-mers' counters back (GetCountersForRead)
+    db = kx.KmcDatabase(base)
+    assert (db.check_kmers(want_k) == np.minimum(want_c, 1023)).all()
+    with open(fq) as f:
+        reads = [ln.strip() for i, ln in enumerate(f) if i % 4 == 1][:50]
+    lookup = dict(zip(want_k.tolist(), np.minimum(want_c, 1023).tolist()))
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    for r, got in zip(reads, db.counters_for_reads(reads)):
+        want = []
+        for i in range(len(r) - 30):
+            w = r[i: i + 31]
+            if any(ch not in code for ch in w):
+                want.append(0)
+                continue
+            v = rc = 0
+            for ch in w:
+                v = (v << 2) | code[ch]
+            for ch in reversed(w):
+                rc = (rc << 2) | (3 - code[ch])
+            want.append(lookup.get(min(v, rc), 0))
+        assert got.tolist() == want
+    db.close()
