@@ -43,3 +43,18 @@ def test_cli_fails_loudly_without_a_gpu(case_dbs, tmp_path):
     assert r.returncode == 1, (r.returncode, r.stdout, r.stderr)
     assert "CUDA" in r.stdout + r.stderr or "GPU" in r.stdout + r.stderr or "device" in r.stdout + r.stderr
     assert not (work / os.path.basename(base) / "km.bin").exists()
+
+
+def test_random_access_program_builds_and_fails_loudly_without_a_gpu(ra_dbs, tmp_path):
+    """include/kmc_ra.hpp (CKMCFile / CKmerAPI names of the reference's kmc_api): compiles with -Wall, and OpenForRA
+    reports failure -- it does not fall back to a host search -- when there is no device"""
+    warnings = _compile(os.path.join(ROOT, "tests", "cpp", "ra_program.cpp"), str(tmp_path / "ra_program"))
+    assert "warning" not in warnings
+    if kx.lib().kmx_device_count() > 0:
+        pytest.skip("a GPU is present: the GPU suite runs the program for real")
+    base, _ = ra_dbs("ra_k23_one_strand")
+    for name in ("k.txt", "r.txt"):
+        (tmp_path / name).write_text("ACGT\n")
+    r = subprocess.run([str(tmp_path / "ra_program"), base, str(tmp_path / "k.txt"), str(tmp_path / "r.txt"), str(tmp_path / "o.txt")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stdout
+    assert "CUDA" in r.stdout or "GPU" in r.stdout or "device" in r.stdout
