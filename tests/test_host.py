@@ -190,13 +190,51 @@ def test_kmc_header_parse_without_gpu(case_dbs, golden):
 def test_compute_entry_points_fail_loudly_without_gpu(case_dbs):
     if kx.lib().kmx_device_count() > 0:
         pytest.skip("a CUDA device is present")
-    base, _ = case_dbs("tiny_ci1")
+    base, sp = case_dbs("tiny_ci1")
     m = kx.get_model(1, 1023, 7, 5)
     with pytest.raises(kx.KmxError) as e:
         m.init(base)
     assert e.value.code == 4          # KMX_ENOGPU: no CPU fallback
     with pytest.raises(kx.KmxError):
         m.kmer_to_occ("ACGTACGTACGTACGTACGTACGTACGTACG")
+    db = kx.KmcDatabase(base)
+    with pytest.raises(kx.KmxError) as e:
+        db.check_kmers(sp.kmers[:10])          # random access: no host-side search either
+    assert e.value.code == 4
+    with pytest.raises(kx.KmxError):
+        db.counters_for_reads([b"A" * 40])
+    db.close()
+
+
+def test_counter_range_of_a_database_can_only_be_narrowed(ra_dbs):
+    """CKMCFile::SetMinCount / SetMaxCount / ResetMinMaxCounts (kmc_file.cpp:670-734)"""
+    base, _ = ra_dbs("ra_k31_range")           # header range [3, 40]
+    db = kx.KmcDatabase(base)
+    lib = kx.lib()
+    assert (db.info["min_count"], db.info["max_count"], db.info["both_strands"], db.info["signature_len"]) == (3, 40, 1, 7)
+    assert lib.kmx_db_set_count_range(db._h, 5, 30) == 0 and (db.info["min_count"], db.info["max_count"]) == (5, 30)
+    for lo, hi in ((2, 30), (5, 41), (31, 30)):
+        assert lib.kmx_db_set_count_range(db._h, lo, hi) != 0
+    assert (db.info["min_count"], db.info["max_count"]) == (5, 30)
+    assert lib.kmx_db_reset_count_range(db._h) == 0 and (db.info["min_count"], db.info["max_count"]) == (3, 40)
+    db.close()
+
+
+def test_signature_is_strand_symmetric_and_bounded():
+    """norm(m) = norm(revcomp(m)) (mmer.h:63-88), so a k-mer and its reverse complement share the signature, hence the bin"""
+    lib = kx.lib()
+    rng = np.random.default_rng(5)
+    for k, sl in ((31, 7), (27, 9), (32, 11), (15, 5), (23, 6)):
+        for v in rng.integers(0, 1 << 62, 300, dtype=np.uint64):
+            v = int(v) & ((1 << (2 * k)) - 1)
+            rc, t = 0, v
+            for _ in range(k):
+                rc = (rc << 2) | (3 - (t & 3))
+                t >>= 2
+            a = lib.kmx_host_signature(v, k, sl)
+            assert a == lib.kmx_host_signature(rc, k, sl) and a <= 4 ** sl
+    assert lib.kmx_host_signature(0, 31, 7) == 4 ** 7            # poly-A: no allowed m-mer
+    assert lib.kmx_host_signature(0, 31, 4) == 0xFFFFFFFF        # signature lengths outside 5..11 are refused
 
 
 def test_team_item_routing_is_a_bijection_onto_the_owners_shards():
